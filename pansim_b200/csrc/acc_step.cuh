@@ -1,0 +1,218 @@
+// acc_step.cuh -- K5: accessory-genome generation step on the bit-packed
+// presence/absence matrix (1 bit per gene, gene g in word g/32 bit g%32).
+//
+//   gather-by-parent       population.rs:450-465
+//   gene gain/loss flips   population.rs:488-510   (multi-hit = parity)
+//   HGT (gain only)        population.rs:544-751, accessory branch
+//
+// Exact per-cell forms of the reference's per-row event loops:
+//   flips: a gene of compartment c is hit Poisson(rate_c) times per row, the
+//          bit flips iff the count is odd: p_c = (1 - exp(-2 rate_c)) / 2.
+//   HGT:   donor d emits Poisson(lambda_c) events, recipient uniform on the
+//          other N-1 rows, gene uniform on the K_dc genes of compartment c the
+//          donor carries (post-mutation snapshot), value always 1
+//          (population.rs:632-680). Hence cell (r,g) with bit 0 gains with
+//          probability 1 - exp(-lambda_c/(N-1) * S_g),
+//          S_g = sum over donors carrying g of 1/K_dc; cells are independent
+//          given the snapshot.
+#pragma once
+#include "common.cuh"
+
+namespace pansim {
+
+struct AccArgs {
+    const uint32_t *old_state;
+    uint32_t *new_state;
+    const uint32_t *parents;
+    uint32_t n_rows, n_genes, stride_words;
+    uint2 key;
+    uint32_t gen;
+    uint32_t n_comp;
+    uint32_t comp_lo[2], comp_hi[2];
+    uint32_t flip_thr[2];        // round(p_c * 2^32)
+    double hgt_scale[2];         // lambda_c / (N-1)
+    uint32_t *rowK;              // [2][n_rows] genes of compartment c present (post-mutation)
+    uint32_t *gain_thr;          // [n_genes]
+    uint32_t *dump_flip;         // optional [n_rows * stride_words]
+    uint32_t *dump_gain;
+};
+
+__device__ __forceinline__ uint32_t comp_mask_for_word(uint32_t w, uint32_t lo, uint32_t hi)
+{
+    // bits of word w (genes 32w..32w+31) that fall in [lo,hi)
+    const uint32_t g0 = w * 32u;
+    if (hi <= g0 || lo >= g0 + 32u) return 0u;
+    const uint32_t a = lo > g0 ? lo - g0 : 0u;
+    const uint32_t b = hi < g0 + 32u ? hi - g0 : 32u;
+    const uint32_t upto_b = b >= 32u ? 0xFFFFFFFFu : ((1u << b) - 1u);
+    const uint32_t upto_a = (1u << a) - 1u;
+    return upto_b & ~upto_a;
+}
+
+// 32 Bernoulli bits for word w of row `row`: bit b set iff u_b < thr(gene 32w+b).
+// thr comes from per-gene thresholds `per_gene` (HGT) or per-compartment `ct` (flips).
+template <bool PER_GENE>
+__device__ __forceinline__ uint32_t bernoulli_word(const AccArgs &a, uint32_t stream, uint32_t row,
+                                                   uint32_t w, uint32_t active, const uint32_t *per_gene)
+{
+    uint32_t out = 0;
+    if (!active) return 0;
+    const uint32_t m0 = PER_GENE ? 0u : comp_mask_for_word(w, a.comp_lo[0], a.comp_hi[0]);
+#pragma unroll 1
+    for (uint32_t q = 0; q < 8; q++) {
+        if (((active >> (4 * q)) & 0xFu) == 0) continue;
+        uint4 ctr = make_ctr(w, row, a.gen, stream);
+        ctr.w |= q;
+        const uint4 r = philox4x32_10(ctr, a.key);
+        const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (uint32_t c = 0; c < 4; c++) {
+            const uint32_t b = 4 * q + c;
+            uint32_t thr;
+            if (PER_GENE) {
+                const uint32_t g = w * 32u + b;
+                thr = g < a.n_genes ? per_gene[g] : 0u;
+            } else {
+                thr = ((m0 >> b) & 1u) ? a.flip_thr[0] : a.flip_thr[1];
+            }
+            if (u[c] < thr) out |= 1u << b;
+        }
+    }
+    return out & active;
+}
+
+// gather + flips + per-row compartment popcounts. One warp per row.
+template <bool DUMP>
+__global__ void __launch_bounds__(256) acc_gather_flip_kernel(const AccArgs a)
+{
+    const uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t lane = threadIdx.x & 31;
+    if (row >= a.n_rows) return;
+    const uint32_t *src = a.old_state + (uint64_t)a.parents[row] * a.stride_words;
+    uint32_t *dst = a.new_state + (uint64_t)row * a.stride_words;
+    uint32_t k0 = 0, k1 = 0;
+    for (uint32_t w = lane; w < a.stride_words; w += 32) {
+        uint32_t m[2] = {0u, 0u};
+        for (uint32_t c = 0; c < a.n_comp; c++) m[c] = comp_mask_for_word(w, a.comp_lo[c], a.comp_hi[c]);
+        uint32_t active = 0;
+        if (a.flip_thr[0]) active |= m[0];
+        if (a.flip_thr[1]) active |= m[1];
+        const uint32_t flips = bernoulli_word<false>(a, STREAM_ACC_FLIP, row, w, active, nullptr);
+        const uint32_t v = src[w] ^ flips;
+        dst[w] = v;
+        if (DUMP) a.dump_flip[(uint64_t)row * a.stride_words + w] = flips;
+        k0 += __popc(v & m[0]);
+        k1 += __popc(v & m[1]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        k0 += __shfl_xor_sync(0xffffffffu, k0, o);
+        k1 += __shfl_xor_sync(0xffffffffu, k1, o);
+    }
+    if (lane == 0) {
+        a.rowK[row] = k0;
+        a.rowK[a.n_rows + row] = k1;
+    }
+}
+
+// per-gene HGT gain threshold from the post-mutation snapshot. One CTA (8 warps)
+// per 32-gene word; warp q sums donors q, q+8, ... in order, then the eight
+// partial sums are added in warp order: deterministic.
+__global__ void __launch_bounds__(256) acc_gain_threshold_kernel(const AccArgs a)
+{
+    __shared__ double part[8][32];
+    const uint32_t w = blockIdx.x;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t g = w * 32u + lane;
+    int c = -1;
+    for (uint32_t k = 0; k < a.n_comp; k++)
+        if (g >= a.comp_lo[k] && g < a.comp_hi[k] && a.hgt_scale[k] > 0.0) c = (int)k;
+    double s = 0.0;
+    for (uint32_t d = warp; d < a.n_rows; d += 8) {
+        const uint32_t word = a.new_state[(uint64_t)d * a.stride_words + w];
+        if (c >= 0 && ((word >> lane) & 1u)) {
+            const uint32_t K = a.rowK[(uint32_t)c * a.n_rows + d];
+            s += 1.0 / (double)K;          // K >= 1 because the donor carries g
+        }
+    }
+    part[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0 && g < a.n_genes) {
+        double S = 0.0;
+        for (int q = 0; q < 8; q++) S += part[q][lane];
+        uint32_t thr = 0;
+        if (c >= 0 && S > 0.0) {
+            const double p = -expm1(-a.hgt_scale[c] * S);
+            const double t = rint(p * 4294967296.0);
+            thr = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+        }
+        a.gain_thr[g] = thr;
+    }
+}
+
+// HGT apply: absent genes gain with their per-gene probability. Thread per word.
+template <bool DUMP>
+__global__ void __launch_bounds__(256) acc_hgt_apply_kernel(const AccArgs a)
+{
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t total = (uint64_t)a.n_rows * a.stride_words;
+    if (idx >= total) return;
+    const uint32_t row = (uint32_t)(idx / a.stride_words), w = (uint32_t)(idx % a.stride_words);
+    uint32_t valid = 0;
+    for (uint32_t c = 0; c < a.n_comp; c++)
+        if (a.hgt_scale[c] > 0.0) valid |= comp_mask_for_word(w, a.comp_lo[c], a.comp_hi[c]);
+    const uint32_t cur = a.new_state[idx];
+    const uint32_t active = valid & ~cur;      // a hit on a present gene writes 1 over 1
+    const uint32_t gain = bernoulli_word<true>(a, STREAM_ACC_HGT, row, w, active, a.gain_thr);
+    if (gain) a.new_state[idx] = cur | gain;
+    if (DUMP) a.dump_gain[idx] = gain;
+}
+
+// plain gather (replay mode / next_generation alone)
+__global__ void __launch_bounds__(256) acc_gather_kernel(const uint32_t *old_state, uint32_t *new_state,
+                                                         const uint32_t *parents, uint32_t n_rows,
+                                                         uint32_t stride_words)
+{
+    const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (uint64_t)n_rows * stride_words) return;
+    const uint32_t row = (uint32_t)(idx / stride_words), w = (uint32_t)(idx % stride_words);
+    new_state[idx] = old_state[(uint64_t)parents[row] * stride_words + w];
+}
+
+// replay: flips (XOR, order-free) and HGT sets (OR, order-free)
+__global__ void acc_apply_flips_kernel(uint32_t *state, const uint32_t *row, const uint32_t *gene, size_t n,
+                                       uint32_t stride_words)
+{
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    atomicXor(&state[(uint64_t)row[k] * stride_words + (gene[k] >> 5)], 1u << (gene[k] & 31u));
+}
+
+__global__ void acc_apply_sets_kernel(uint32_t *state, const uint32_t *row, const uint32_t *gene, size_t n,
+                                      uint32_t stride_words)
+{
+    const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    atomicOr(&state[(uint64_t)row[k] * stride_words + (gene[k] >> 5)], 1u << (gene[k] & 31u));
+}
+
+// K8: gene counts (population.rs:847-855). Same CTA shape as the threshold kernel.
+__global__ void __launch_bounds__(256) acc_gene_counts_kernel(const uint32_t *state, uint32_t n_rows,
+                                                              uint32_t n_genes, uint32_t stride_words,
+                                                              uint32_t *counts)
+{
+    __shared__ uint32_t part[8][32];
+    const uint32_t w = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t s = 0;
+    for (uint32_t d = warp; d < n_rows; d += 8) s += (state[(uint64_t)d * stride_words + w] >> lane) & 1u;
+    part[warp][lane] = s;
+    __syncthreads();
+    const uint32_t g = w * 32u + lane;
+    if (warp == 0 && g < n_genes) {
+        uint32_t t = 0;
+        for (int q = 0; q < 8; q++) t += part[q][lane];
+        counts[g] = t;
+    }
+}
+
+}  // namespace pansim

@@ -1,0 +1,220 @@
+// common.cuh -- device-side building blocks shared by all kernels:
+// Philox4x32-10, a bit-stream reader over it, Poisson-by-inversion tables,
+// and the sm_100a PTX wrappers (mbarrier, cp.async.bulk = TMA 1-D bulk copies).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pansim {
+
+// ---------------------------------------------------------------------------
+// geometry of the packed core alignment
+// ---------------------------------------------------------------------------
+// 2 bits per site (A=0,C=1,G=2,T=3  <->  reference one-hot 1,2,4,8), site s of a
+// row lives in 32-bit word s/16 at bit 2*(s%16). Rows are padded to whole
+// REGIONs. A region is the unit one warp processes per pipeline stage and the
+// unit the RNG is keyed on: lane l of the warp owns words {l, l+32, ..., l+480}
+// of the region (bank-conflict-free in shared memory), i.e. 256 sites.
+constexpr uint32_t REGION_BYTES = 2048;
+constexpr uint32_t REGION_WORDS = REGION_BYTES / 4;      // 512
+constexpr uint32_t REGION_SITES = REGION_BYTES * 4;      // 8192
+constexpr uint32_t BLOCK_SITES = 256;                    // sites per lane per region
+constexpr uint32_t WORDS_PER_LANE = 16;
+
+// RNG stream ids (counter word 3, high half)
+constexpr uint32_t STREAM_CORE_MUT = 1;
+constexpr uint32_t STREAM_CORE_HR = 2;
+constexpr uint32_t STREAM_ACC_FLIP = 3;
+constexpr uint32_t STREAM_ACC_HGT = 4;
+constexpr uint32_t STREAM_PARENTS = 5;
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11). Counter-based: output is a pure
+// function of (key, counter), so results do not depend on thread/GPU count.
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ void philox_round(uint32_t &c0, uint32_t &c1, uint32_t &c2,
+                                                      uint32_t &c3, uint32_t k0, uint32_t k1)
+{
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    const uint32_t n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    const uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+}
+
+__host__ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key)
+{
+    uint32_t c0 = ctr.x, c1 = ctr.y, c2 = ctr.z, c3 = ctr.w;
+    uint32_t k0 = key.x, k1 = key.y;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        philox_round(c0, c1, c2, c3, k0, k1);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+// Counter layout used everywhere:  x = column block id (site block / gene word),
+// y = individual (row), z = generation, w = (stream << 16) | refill index.
+__host__ __device__ __forceinline__ uint4 make_ctr(uint32_t block, uint32_t row, uint32_t gen,
+                                                   uint32_t stream)
+{
+    return make_uint4(block, row, gen, stream << 16);
+}
+
+// 128-bit shift register over successive Philox outputs.
+struct BitStream {
+    uint32_t r0, r1, r2, r3;
+    int left;
+    uint4 ctr;
+    uint2 key;
+
+    __device__ __forceinline__ BitStream(uint4 c, uint2 k) : left(0), ctr(c), key(k) {}
+
+    __device__ __forceinline__ void refill()
+    {
+        const uint4 o = philox4x32_10(ctr, key);
+        ctr.w += 1;
+        r0 = o.x; r1 = o.y; r2 = o.z; r3 = o.w;
+        left = 128;
+    }
+    // n in [1,31]
+    __device__ __forceinline__ uint32_t take(int n)
+    {
+        if (left < n) refill();
+        const uint32_t v = r0 & ((1u << n) - 1u);
+        r0 = __funnelshift_r(r0, r1, n);
+        r1 = __funnelshift_r(r1, r2, n);
+        r2 = __funnelshift_r(r2, r3, n);
+        r3 >>= n;
+        left -= n;
+        return v;
+    }
+    __device__ __forceinline__ uint32_t take32()
+    {
+        if (left < 32) refill();
+        const uint32_t v = r0;
+        r0 = r1; r1 = r2; r2 = r3; r3 = 0;
+        left -= 32;
+        return v;
+    }
+    // exactly uniform on [0,n): Lemire multiply-shift with rejection
+    __device__ __forceinline__ uint32_t below(uint32_t n)
+    {
+        uint32_t x = take32();
+        uint64_t m = (uint64_t)x * n;
+        uint32_t l = (uint32_t)m;
+        if (l < n) {
+            const uint32_t t = (0u - n) % n;
+            while (l < t) {
+                x = take32();
+                m = (uint64_t)x * n;
+                l = (uint32_t)m;
+            }
+        }
+        return (uint32_t)(m >> 32);
+    }
+};
+
+// Poisson by CDF inversion from one 32-bit uniform: k = #{j : T[j] <= u} with
+// T[j] = round(CDF(j) * 2^32) (built on the host in f64), padded with
+// 0xFFFFFFFF to a power of two. A mean above the table range is drawn as a sum
+// of n_sub independent Poisson(mean / n_sub) (exact by additivity).
+struct PoissonTable {
+    const uint32_t *thr;   // shared-memory pointer inside kernels
+    uint32_t size;         // power of two
+    uint32_t n_sub;        // 0 = rate is zero
+    uint32_t kmax;
+};
+
+__device__ __forceinline__ uint32_t poisson_from_uniform(const uint32_t *thr, uint32_t size,
+                                                         uint32_t kmax, uint32_t u)
+{
+    uint32_t pos = 0;
+    for (uint32_t step = size >> 1; step > 0; step >>= 1)
+        if (thr[pos + step - 1] <= u) pos += step;
+    return pos < kmax ? pos : kmax;
+}
+
+// ---------------------------------------------------------------------------
+// sm_100a PTX: mbarrier + 1-D bulk async copies (TMA engine, UBLKCP in SASS)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {}
+}
+
+// global -> shared bulk copy, completion signalled on an mbarrier (bytes % 16 == 0)
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// shared -> global bulk copy (bulk async-group completion)
+__device__ __forceinline__ void bulk_s2g(void *gdst, const void *smem_src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+
+template <int N>
+__device__ __forceinline__ void bulk_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
+template <int N>
+__device__ __forceinline__ void bulk_wait()
+{
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// make generic-proxy shared-memory writes visible to the async proxy (TMA)
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+}  // namespace pansim

@@ -1,0 +1,104 @@
+// distance.cuh -- K7: pairwise core Hamming / accessory Jaccard counts
+// (population.rs:787-837 with distances.rs:22-77) on the packed layouts.
+//
+// Core: the reference XORs one-hot bytes and halves the popcount
+// (population.rs:817) = number of differing sites. On 2-bit codes a site
+// differs iff either bit of the XOR is set:
+//   d = a ^ b;  m = (d | d >> 1) & 0x5555...;  differing sites = popc(m)
+// Two words share one POPC by parking the second mask in the odd bits.
+// Row padding is zero in every row, so it never contributes.
+#pragma once
+#include "common.cuh"
+
+namespace pansim {
+
+__device__ __forceinline__ uint32_t diff_sites4(const uint4 a, const uint4 b)
+{
+    const uint32_t d0 = a.x ^ b.x, d1 = a.y ^ b.y, d2 = a.z ^ b.z, d3 = a.w ^ b.w;
+    const uint32_t m0 = (d0 | (d0 >> 1)) & 0x55555555u;
+    const uint32_t m1 = (d1 | (d1 << 1)) & 0xAAAAAAAAu;
+    const uint32_t m2 = (d2 | (d2 >> 1)) & 0x55555555u;
+    const uint32_t m3 = (d3 | (d3 << 1)) & 0xAAAAAAAAu;
+    return __popc(m0 | m1) + __popc(m2 | m3);
+}
+
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// v1: one CTA per (pair, column chunk). Chunks are the slow grid dimension so
+// that concurrently running CTAs touch the same column slab of all rows
+// (N * chunk bytes is sized to stay L2-resident); partial counts are combined
+// with integer atomics (order-independent, exact).
+constexpr int PAIR_THREADS = 256;
+
+__global__ void __launch_bounds__(PAIR_THREADS) pair_core_kernel(const uint8_t *state, uint64_t row_stride,
+                                                                 uint32_t chunk_vec4, uint32_t row_vec4,
+                                                                 const uint32_t *range1, const uint32_t *range2,
+                                                                 uint32_t n_pairs, uint32_t *core_diff)
+{
+    __shared__ uint32_t wsum[PAIR_THREADS / 32];
+    const uint32_t chunk = blockIdx.y;
+    const uint32_t v_lo = chunk * chunk_vec4;
+    const uint32_t v_hi = min(row_vec4, v_lo + chunk_vec4);
+    for (uint32_t p = blockIdx.x; p < n_pairs; p += gridDim.x) {
+        const uint4 *ra = reinterpret_cast<const uint4 *>(state + (uint64_t)range1[p] * row_stride);
+        const uint4 *rb = reinterpret_cast<const uint4 *>(state + (uint64_t)range2[p] * row_stride);
+        uint32_t acc = 0;
+        uint32_t v = v_lo + threadIdx.x;
+        for (; v + 3 * PAIR_THREADS < v_hi; v += 4 * PAIR_THREADS) {
+            const uint4 a0 = ld_stream(ra + v), b0 = ld_stream(rb + v);
+            const uint4 a1 = ld_stream(ra + v + PAIR_THREADS), b1 = ld_stream(rb + v + PAIR_THREADS);
+            const uint4 a2 = ld_stream(ra + v + 2 * PAIR_THREADS), b2 = ld_stream(rb + v + 2 * PAIR_THREADS);
+            const uint4 a3 = ld_stream(ra + v + 3 * PAIR_THREADS), b3 = ld_stream(rb + v + 3 * PAIR_THREADS);
+            acc += diff_sites4(a0, b0) + diff_sites4(a1, b1) + diff_sites4(a2, b2) + diff_sites4(a3, b3);
+        }
+        for (; v < v_hi; v += PAIR_THREADS) acc += diff_sites4(ld_stream(ra + v), ld_stream(rb + v));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t t = 0;
+            for (int q = 0; q < PAIR_THREADS / 32; q++) t += wsum[q];
+            if (gridDim.y == 1) core_diff[p] = t; else atomicAdd(&core_diff[p], t);
+        }
+        __syncthreads();
+    }
+}
+
+// accessory: one warp per pair; intersection and union popcounts (distances.rs:62-68)
+__global__ void __launch_bounds__(256) pair_acc_kernel(const uint32_t *acc, uint32_t stride_words,
+                                                       uint32_t n_words, const uint32_t *range1,
+                                                       const uint32_t *range2, uint32_t n_pairs,
+                                                       uint32_t *inter, uint32_t *uni)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t wpb = blockDim.x >> 5;
+    for (uint32_t p = blockIdx.x * wpb + (threadIdx.x >> 5); p < n_pairs; p += gridDim.x * wpb) {
+        const uint32_t *ra = acc + (uint64_t)range1[p] * stride_words;
+        const uint32_t *rb = acc + (uint64_t)range2[p] * stride_words;
+        uint32_t in = 0, un = 0;
+        for (uint32_t w = lane; w < n_words; w += 32) {
+            const uint32_t x = ra[w], y = rb[w];
+            in += __popc(x & y);
+            un += __popc(x | y);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            in += __shfl_xor_sync(0xffffffffu, in, o);
+            un += __shfl_xor_sync(0xffffffffu, un, o);
+        }
+        if (lane == 0) {
+            if (inter) inter[p] = in;
+            if (uni) uni[p] = un;
+        }
+    }
+}
+
+}  // namespace pansim

@@ -1,0 +1,1149 @@
+// pansim_b200.cu -- context management and the C ABI of include/pansim_b200.h.
+// All device work is in the kernels of *.cuh; this file owns memory, streams,
+// launch configuration and error mapping. There is no CPU fallback.
+#include "../../include/pansim_b200.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "acc_step.cuh"
+#include "common.cuh"
+#include "core_step.cuh"
+#include "distance.cuh"
+#include "pack.cuh"
+#include "replay.cuh"
+#include "select.cuh"
+
+using namespace pansim;
+
+namespace {
+
+std::string g_create_error;
+
+struct HostPoissonTable {
+    std::vector<uint32_t> thr;
+    uint32_t size = 1, nsub = 0, kmax = 0;
+    uint32_t *d_thr = nullptr;
+    double mean_per_draw = 0.0;
+};
+
+// thresholds T[j] = round(CDF(j) * 2^32) of Poisson(mean / nsub), see common.cuh
+void build_poisson_table(double mean, HostPoissonTable &t)
+{
+    t.thr.clear();
+    if (!(mean > 0.0)) {
+        t.nsub = 0; t.size = 1; t.kmax = 0; t.thr.assign(1, 0xFFFFFFFFu);
+        return;
+    }
+    t.nsub = (uint32_t)std::ceil(mean / 64.0);
+    if (t.nsub < 1) t.nsub = 1;
+    const long double m = (long double)mean / (long double)t.nsub;
+    t.mean_per_draw = (double)m;
+    long double p = expl(-m), cdf = p;
+    for (uint32_t j = 0; j < POISSON_TABLE_MAX - 1; j++) {
+        const long double scaled = cdf * 4294967296.0L;
+        if (scaled >= 4294967295.5L) { t.thr.push_back(0xFFFFFFFFu); break; }
+        t.thr.push_back((uint32_t)llroundl(scaled));
+        p *= m / (long double)(j + 1);
+        cdf += p;
+    }
+    if (t.thr.back() != 0xFFFFFFFFu) t.thr.push_back(0xFFFFFFFFu);
+    t.kmax = (uint32_t)t.thr.size() - 1;
+    uint32_t size = 1;
+    while (size < t.thr.size() + 1) size <<= 1;
+    t.size = size;
+    t.thr.resize(size, 0xFFFFFFFFu);
+}
+
+struct EventPool {
+    std::vector<cudaEvent_t> ev;
+    size_t used = 0;
+    cudaEvent_t get()
+    {
+        if (used == ev.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            ev.push_back(e);
+        }
+        return ev[used++];
+    }
+    void reset() { used = 0; }
+    void destroy()
+    {
+        for (auto e : ev) cudaEventDestroy(e);
+        ev.clear();
+        used = 0;
+    }
+};
+
+enum TimeGroup { TG_SELECT = 0, TG_ACC, TG_CORE, TG_PAIR_CORE, TG_PAIR_ACC, TG_COUNT };
+
+}  // namespace
+
+struct pansim_ctx {
+    pansim_config cfg;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+
+    uint32_t N = 0, G = 0;
+    uint64_t L = 0, site_begin = 0, site_end = 0, Ll = 0;
+    uint32_t n_regions = 0, region0 = 0;
+    uint64_t core_stride = 0;
+    uint32_t acc_stride_words = 0, acc_words = 0;
+
+    uint8_t *core[2] = {nullptr, nullptr};
+    uint32_t *acc[2] = {nullptr, nullptr};
+    int core_cur = 0, acc_cur = 0;
+    bool has_core = false, has_acc = false;
+
+    uint32_t *d_parents = nullptr;
+    double *d_lw = nullptr, *d_logfit = nullptr, *d_avgdist = nullptr;
+    int32_t *d_num_genes = nullptr;
+    double *d_tmp_a = nullptr, *d_tmp_b = nullptr, *d_weights = nullptr, *d_cum = nullptr;
+    int *d_err = nullptr;
+    uint32_t *d_inter = nullptr;
+    uint32_t *d_rowK = nullptr, *d_gain_thr = nullptr;
+    bool avgdist_valid = false;
+
+    HostPoissonTable tab_mut, tab_hr;
+    uint32_t flip_thr[2] = {0, 0};
+    double flip_p[2] = {0, 0};
+    double hgt_scale[2] = {0, 0};
+    double p_mut_site = 0, p_hr_site = 0;
+
+    // pair buffers
+    uint32_t *d_r1 = nullptr, *d_r2 = nullptr, *d_cd = nullptr, *d_in = nullptr, *d_un = nullptr;
+    size_t pair_cap = 0;
+
+    // replay staging
+    void *d_replay = nullptr;
+    size_t replay_cap = 0;
+    unsigned long long *d_hkeys = nullptr;
+    uint32_t *d_hvals = nullptr;
+    size_t hash_cap = 0;
+
+    // staging for upload/download
+    uint8_t *d_stage = nullptr;
+    size_t stage_cap = 0;
+
+    // event dump
+    bool dump_enabled = false;
+    uint32_t dump_cap = 0;
+    uint32_t *d_dump_counters = nullptr;
+    uint32_t *d_mut_row = nullptr, *d_mut_site = nullptr, *d_mut_seq = nullptr;
+    uint8_t *d_mut_allele = nullptr;
+    uint32_t *d_hr_rec = nullptr, *d_hr_locus = nullptr, *d_hr_donor = nullptr, *d_hr_seq = nullptr;
+    uint8_t *d_hr_value = nullptr;
+    uint32_t *d_dump_flip = nullptr, *d_dump_gain = nullptr;
+
+    // timing
+    bool timing_enabled = true;
+    EventPool pool;
+    struct Span { cudaEvent_t a, b; int group; };
+    std::vector<Span> spans;
+    cudaEvent_t t_begin = nullptr, t_end = nullptr;
+    uint32_t launches = 0;
+
+    uint32_t core_grid = 0;
+    size_t core_smem = 0;
+};
+
+namespace {
+
+#define FAIL(ctx, code, ...)                                 \
+    do {                                                     \
+        char _b[512];                                        \
+        snprintf(_b, sizeof _b, __VA_ARGS__);                \
+        (ctx)->err = _b;                                     \
+        return (code);                                       \
+    } while (0)
+
+#define CU(ctx, call)                                                                            \
+    do {                                                                                         \
+        cudaError_t _e = (call);                                                                 \
+        if (_e != cudaSuccess)                                                                   \
+            FAIL(ctx, PANSIM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e),   \
+                 __FILE__, __LINE__);                                                            \
+    } while (0)
+
+#define LAUNCH_CHECK(ctx)                                                                        \
+    do {                                                                                         \
+        (ctx)->launches++;                                                                       \
+        cudaError_t _e = cudaGetLastError();                                                     \
+        if (_e != cudaSuccess)                                                                   \
+            FAIL(ctx, PANSIM_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
+                 __FILE__, __LINE__);                                                            \
+    } while (0)
+
+inline uint32_t div_up64(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+struct ScopedSpan {
+    pansim_ctx *c;
+    int group;
+    cudaEvent_t a = nullptr;
+    ScopedSpan(pansim_ctx *ctx, int g) : c(ctx), group(g)
+    {
+        if (c->timing_enabled) {
+            a = c->pool.get();
+            cudaEventRecord(a, c->stream);
+        }
+    }
+    ~ScopedSpan()
+    {
+        if (c->timing_enabled) {
+            cudaEvent_t b = c->pool.get();
+            cudaEventRecord(b, c->stream);
+            c->spans.push_back({a, b, group});
+        }
+    }
+};
+
+void timing_begin(pansim_ctx *c)
+{
+    c->launches = 0;
+    c->spans.clear();
+    c->pool.reset();
+    if (c->timing_enabled) {
+        c->t_begin = c->pool.get();
+        cudaEventRecord(c->t_begin, c->stream);
+    }
+}
+
+void timing_end(pansim_ctx *c)
+{
+    if (c->timing_enabled) {
+        c->t_end = c->pool.get();
+        cudaEventRecord(c->t_end, c->stream);
+    }
+}
+
+int ensure_stage(pansim_ctx *c, size_t bytes)
+{
+    if (bytes <= c->stage_cap) return 0;
+    if (c->d_stage) cudaFree(c->d_stage);
+    c->d_stage = nullptr;
+    c->stage_cap = 0;
+    CU(c, cudaMalloc(&c->d_stage, bytes));
+    c->stage_cap = bytes;
+    return 0;
+}
+
+int check_device_flag(pansim_ctx *c, int code, const char *what)
+{
+    int flag = 0;
+    CU(c, cudaMemcpyAsync(&flag, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (flag) {
+        cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream);
+        FAIL(c, code, "%s", what);
+    }
+    return 0;
+}
+
+// ---- kernel group launchers (asynchronous on ctx->stream) -----------------
+
+int launch_fitness(pansim_ctx *c)
+{
+    const uint32_t *acc = c->acc[c->acc_cur];
+    fitness_kernel<<<div_up64(c->N, 64), 64, 0, c->stream>>>(acc, c->N, c->G, c->acc_stride_words, c->d_lw,
+                                                             c->d_logfit, c->d_num_genes);
+    LAUNCH_CHECK(c);
+    return 0;
+}
+
+int launch_competition(pansim_ctx *c)
+{
+    if (c->N < 2) FAIL(c, PANSIM_ERR_INVALID, "average_distance needs pop_size >= 2");
+    if (!c->d_inter) CU(c, cudaMalloc(&c->d_inter, (size_t)c->N * c->N * sizeof(uint32_t)));
+    if (launch_fitness(c)) return PANSIM_ERR_CUDA;           // row popcounts (num_genes)
+    const uint32_t nb = div_up64(c->N, 32);
+    acc_inter_kernel<<<dim3(nb, nb), 256, 0, c->stream>>>(c->acc[c->acc_cur], c->N, c->acc_stride_words,
+                                                          c->acc_words, c->d_inter);
+    LAUNCH_CHECK(c);
+    avg_distance_kernel<<<div_up64(c->N, 128), 128, 0, c->stream>>>(c->d_inter, c->d_num_genes, c->N,
+                                                                    c->cfg.core_genes, c->d_avgdist);
+    LAUNCH_CHECK(c);
+    c->avgdist_valid = true;
+    return 0;
+}
+
+int launch_select(pansim_ctx *c, uint32_t gen, bool use_avgdist)
+{
+    if (launch_fitness(c)) return PANSIM_ERR_CUDA;
+    SelectArgs a;
+    a.logfit = c->d_logfit;
+    a.num_genes = c->d_num_genes;
+    a.avgdist = use_avgdist ? c->d_avgdist : nullptr;
+    a.n_rows = c->N;
+    a.n_genes = c->G;
+    a.avg_gene_num = c->cfg.avg_gene_num;
+    a.no_control_genome_size = c->cfg.no_control_genome_size;
+    a.log_penalty = std::log(c->cfg.genome_size_penalty);
+    a.competition_strength = c->cfg.competition_strength;
+    a.key = make_uint2((uint32_t)c->cfg.seed, (uint32_t)(c->cfg.seed >> 32));
+    a.gen = gen;
+    a.tmp_a = c->d_tmp_a;
+    a.tmp_b = c->d_tmp_b;
+    a.weights = c->d_weights;
+    a.cumulative = c->d_cum;
+    a.parents = c->d_parents;
+    a.err_flag = c->d_err;
+    select_parents_kernel<<<1, SEL_THREADS, 0, c->stream>>>(a);
+    LAUNCH_CHECK(c);
+    return 0;
+}
+
+void fill_acc_args(pansim_ctx *c, AccArgs &a, uint32_t gen)
+{
+    memset(&a, 0, sizeof a);
+    a.old_state = c->acc[c->acc_cur];
+    a.new_state = c->acc[c->acc_cur ^ 1];
+    a.parents = c->d_parents;
+    a.n_rows = c->N;
+    a.n_genes = c->G;
+    a.stride_words = c->acc_stride_words;
+    a.key = make_uint2((uint32_t)c->cfg.seed, (uint32_t)(c->cfg.seed >> 32));
+    a.gen = gen;
+    a.n_comp = c->cfg.n_compartments;
+    for (int k = 0; k < 2; k++) {
+        a.comp_lo[k] = c->cfg.comp_lo[k];
+        a.comp_hi[k] = c->cfg.comp_hi[k];
+        a.flip_thr[k] = c->flip_thr[k];
+        a.hgt_scale[k] = c->hgt_scale[k];
+    }
+    a.rowK = c->d_rowK;
+    a.gain_thr = c->d_gain_thr;
+    a.dump_flip = c->d_dump_flip;
+    a.dump_gain = c->d_dump_gain;
+}
+
+int launch_acc_step(pansim_ctx *c, uint32_t gen)
+{
+    if (c->G == 0) return 0;
+    AccArgs a;
+    fill_acc_args(c, a, gen);
+    const uint32_t rows_per_cta = 8;
+    if (c->dump_enabled)
+        acc_gather_flip_kernel<true><<<div_up64(c->N, rows_per_cta), 256, 0, c->stream>>>(a);
+    else
+        acc_gather_flip_kernel<false><<<div_up64(c->N, rows_per_cta), 256, 0, c->stream>>>(a);
+    LAUNCH_CHECK(c);
+    const bool hgt = (a.hgt_scale[0] > 0.0 || a.hgt_scale[1] > 0.0);
+    if (hgt) {
+        acc_gain_threshold_kernel<<<c->acc_words, 256, 0, c->stream>>>(a);
+        LAUNCH_CHECK(c);
+        const uint64_t total = (uint64_t)c->N * c->acc_stride_words;
+        if (c->dump_enabled)
+            acc_hgt_apply_kernel<true><<<div_up64(total, 256), 256, 0, c->stream>>>(a);
+        else
+            acc_hgt_apply_kernel<false><<<div_up64(total, 256), 256, 0, c->stream>>>(a);
+        LAUNCH_CHECK(c);
+    } else if (c->dump_enabled) {
+        CU(c, cudaMemsetAsync(c->d_dump_gain, 0, (size_t)c->N * c->acc_stride_words * 4, c->stream));
+    }
+    c->acc_cur ^= 1;
+    return 0;
+}
+
+void fill_core_args(pansim_ctx *c, CoreStepArgs &a, uint32_t gen)
+{
+    memset(&a, 0, sizeof a);
+    a.old_state = c->core[c->core_cur];
+    a.new_state = c->core[c->core_cur ^ 1];
+    a.parents = c->d_parents;
+    a.n_rows = c->N;
+    a.n_regions = c->n_regions;
+    a.row_stride = c->core_stride;
+    a.region0 = c->region0;
+    a.site_limit = c->site_end;
+    a.key = make_uint2((uint32_t)c->cfg.seed, (uint32_t)(c->cfg.seed >> 32));
+    a.gen = gen;
+    a.mut_thr = c->tab_mut.d_thr; a.mut_size = c->tab_mut.size; a.mut_nsub = c->tab_mut.nsub; a.mut_kmax = c->tab_mut.kmax;
+    a.hr_thr = c->tab_hr.d_thr; a.hr_size = c->tab_hr.size; a.hr_nsub = c->tab_hr.nsub; a.hr_kmax = c->tab_hr.kmax;
+    a.dump_counters = c->d_dump_counters;
+    a.dump_cap = c->dump_cap;
+    a.d_mut_row = c->d_mut_row; a.d_mut_site = c->d_mut_site; a.d_mut_seq = c->d_mut_seq; a.d_mut_allele = c->d_mut_allele;
+    a.d_hr_rec = c->d_hr_rec; a.d_hr_locus = c->d_hr_locus; a.d_hr_donor = c->d_hr_donor; a.d_hr_seq = c->d_hr_seq;
+    a.d_hr_value = c->d_hr_value;
+}
+
+int launch_core_step(pansim_ctx *c, uint32_t gen, bool rng)
+{
+    if (c->Ll == 0) return 0;
+    CoreStepArgs a;
+    fill_core_args(c, a, gen);
+    const bool any_rng = rng && (a.mut_nsub || a.hr_nsub);
+    if (!any_rng) {
+        core_step_kernel<false, false><<<c->core_grid, CS_THREADS, c->core_smem, c->stream>>>(a);
+    } else if (c->dump_enabled) {
+        core_step_kernel<true, true><<<c->core_grid, CS_THREADS, c->core_smem, c->stream>>>(a);
+    } else {
+        core_step_kernel<true, false><<<c->core_grid, CS_THREADS, c->core_smem, c->stream>>>(a);
+    }
+    LAUNCH_CHECK(c);
+    c->core_cur ^= 1;
+    return 0;
+}
+
+int require_state(pansim_ctx *c)
+{
+    if (!c->has_core || !c->has_acc) FAIL(c, PANSIM_ERR_STATE, "state not initialised: call pansim_set_initial or pansim_upload_*");
+    return 0;
+}
+
+int step_device(pansim_ctx *c, uint32_t gen)
+{
+    {
+        ScopedSpan s(c, TG_SELECT);
+        bool use_avg = false;
+        if (c->cfg.competition_strength > 0.0) {          // main.rs:438-440
+            if (int rc = launch_competition(c)) return rc;
+            use_avg = true;
+        }
+        if (int rc = launch_select(c, gen, use_avg)) return rc;
+    }
+    {
+        ScopedSpan s(c, TG_ACC);
+        if (int rc = launch_acc_step(c, gen)) return rc;
+    }
+    {
+        ScopedSpan s(c, TG_CORE);
+        if (int rc = launch_core_step(c, gen, true)) return rc;
+    }
+    c->avgdist_valid = false;
+    return 0;
+}
+
+}  // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+void pansim_config_init(pansim_config *cfg)
+{
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->struct_size = (uint32_t)sizeof(*cfg);
+    cfg->genome_size_penalty = 0.99;
+}
+
+const char *pansim_version(void) { return "pansim_b200 0.1 (sm_100a)"; }
+
+const char *pansim_last_error(const pansim_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+double pansim_core_distance(uint32_t core_diff, uint64_t core_size)
+{
+    return (double)core_diff / (double)core_size;                 // population.rs:822
+}
+
+double pansim_acc_distance(uint32_t inter, uint32_t uni, uint32_t core_genes)
+{
+    return 1.0 - (((double)inter + (double)core_genes) / ((double)uni + (double)core_genes));   // :828-830
+}
+
+void pansim_destroy(pansim_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    void *ptrs[] = {c->core[0], c->core[1], c->acc[0], c->acc[1], c->d_parents, c->d_lw, c->d_logfit, c->d_avgdist,
+                    c->d_num_genes, c->d_tmp_a, c->d_tmp_b, c->d_weights, c->d_cum, c->d_err, c->d_inter, c->d_rowK,
+                    c->d_gain_thr, c->tab_mut.d_thr, c->tab_hr.d_thr, c->d_r1, c->d_r2, c->d_cd, c->d_in, c->d_un,
+                    c->d_replay, c->d_hkeys, c->d_hvals, c->d_stage, c->d_dump_counters, c->d_mut_row, c->d_mut_site,
+                    c->d_mut_seq, c->d_mut_allele, c->d_hr_rec, c->d_hr_locus, c->d_hr_donor, c->d_hr_seq,
+                    c->d_hr_value, c->d_dump_flip, c->d_dump_gain};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    c->pool.destroy();
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int pansim_create(const pansim_config *cfg, pansim_ctx **out)
+{
+    if (!cfg || !out) { g_create_error = "null argument"; return PANSIM_ERR_INVALID; }
+    *out = nullptr;
+    if (cfg->struct_size != sizeof(pansim_config)) { g_create_error = "pansim_config.struct_size mismatch"; return PANSIM_ERR_INVALID; }
+    pansim_ctx *c = new pansim_ctx();
+    c->cfg = *cfg;
+    auto fail = [&](int code) { g_create_error = c->err; pansim_destroy(c); return code; };
+    auto body = [&]() -> int {
+        if (cfg->pop_size < 1) FAIL(c, PANSIM_ERR_INVALID, "pop_size must be >= 1");
+        if (cfg->core_size < 1) FAIL(c, PANSIM_ERR_INVALID, "core_size must be >= 1");
+        if (cfg->core_size > 0xFFFFFFFFull) FAIL(c, PANSIM_ERR_INVALID, "core_size above 2^32-1 is not supported");
+        if (cfg->n_compartments > 2) FAIL(c, PANSIM_ERR_INVALID, "at most two gene compartments (main.rs:341-367)");
+        c->N = cfg->pop_size;
+        c->G = cfg->pan_size;
+        c->L = cfg->core_size;
+        c->site_begin = cfg->site_begin;
+        c->site_end = cfg->site_end;
+        if (c->site_begin == 0 && c->site_end == 0) c->site_end = c->L;
+        if (c->site_end > c->L || c->site_begin > c->site_end) FAIL(c, PANSIM_ERR_INVALID, "bad column shard [%llu,%llu)", (unsigned long long)c->site_begin, (unsigned long long)c->site_end);
+        if (c->site_begin % PANSIM_SITE_ALIGN) FAIL(c, PANSIM_ERR_INVALID, "site_begin must be a multiple of %u", PANSIM_SITE_ALIGN);
+        if (c->site_end != c->L && c->site_end % PANSIM_SITE_ALIGN) FAIL(c, PANSIM_ERR_INVALID, "site_end must be core_size or a multiple of %u", PANSIM_SITE_ALIGN);
+        c->Ll = c->site_end - c->site_begin;
+        c->region0 = (uint32_t)(c->site_begin / REGION_SITES);
+        c->n_regions = (uint32_t)((c->Ll + REGION_SITES - 1) / REGION_SITES);
+        c->core_stride = (uint64_t)c->n_regions * REGION_BYTES;
+        if ((uint64_t)c->N * c->n_regions >= 0x7FFFFFFFull) FAIL(c, PANSIM_ERR_INVALID, "pop_size x regions exceeds 2^31");
+        c->acc_words = (c->G + 31) / 32;
+        c->acc_stride_words = ((c->acc_words + 3) / 4) * 4;
+        if (c->acc_stride_words == 0) c->acc_stride_words = 4;
+        for (uint32_t k = 0; k < cfg->n_compartments; k++)
+            if (cfg->comp_lo[k] > cfg->comp_hi[k] || cfg->comp_hi[k] > c->G) FAIL(c, PANSIM_ERR_INVALID, "compartment %u out of range", k);
+        if ((cfg->hr_mean > 0.0 || cfg->hgt_mean[0] > 0.0 || cfg->hgt_mean[1] > 0.0) && c->N < 2)
+            FAIL(c, PANSIM_ERR_INVALID, "recombination needs pop_size >= 2 (Uniform::new(0, nrows-1), population.rs:584)");
+        if (cfg->core_mut_mean < 0 || cfg->hr_mean < 0) FAIL(c, PANSIM_ERR_INVALID, "negative event mean");
+        if (!(cfg->genome_size_penalty > 0.0)) FAIL(c, PANSIM_ERR_INVALID, "genome_size_penalty must be > 0");
+
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) FAIL(c, PANSIM_ERR_CUDA, "no CUDA device: libpansim_b200 has no CPU fallback");
+        if (cfg->device < 0 || cfg->device >= ndev) FAIL(c, PANSIM_ERR_INVALID, "device %d out of range (0..%d)", cfg->device, ndev - 1);
+        CU(c, cudaSetDevice(cfg->device));
+        cudaDeviceProp prop;
+        CU(c, cudaGetDeviceProperties(&prop, cfg->device));
+        if (prop.major < 10) FAIL(c, PANSIM_ERR_CUDA, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
+        c->sm_count = prop.multiProcessorCount;
+        CU(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+
+        // per-cell rates
+        const double rate_mut = cfg->core_mut_mean / (double)c->L;
+        const double rate_hr = cfg->hr_mean / (double)c->L;
+        c->p_mut_site = -std::expm1(-rate_mut);
+        c->p_hr_site = -std::expm1(-rate_hr);
+        build_poisson_table(rate_mut * BLOCK_SITES, c->tab_mut);
+        build_poisson_table(rate_hr * BLOCK_SITES, c->tab_hr);
+        for (HostPoissonTable *t : {&c->tab_mut, &c->tab_hr}) {
+            CU(c, cudaMalloc(&t->d_thr, t->size * sizeof(uint32_t)));
+            CU(c, cudaMemcpy(t->d_thr, t->thr.data(), t->size * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        }
+        for (uint32_t k = 0; k < cfg->n_compartments; k++) {
+            const double sites = (double)(cfg->comp_hi[k] - cfg->comp_lo[k]);
+            if (sites > 0 && cfg->acc_mut_mean[k] > 0) {
+                const double rate = cfg->acc_mut_mean[k] / sites;            // per gene per row
+                const double p = -0.5 * std::expm1(-2.0 * rate);
+                c->flip_p[k] = p;
+                const double t = std::rint(p * 4294967296.0);
+                c->flip_thr[k] = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+            }
+            if (cfg->hgt_mean[k] > 0) c->hgt_scale[k] = cfg->hgt_mean[k] / (double)(c->N - 1);
+        }
+
+        const size_t core_bytes = (size_t)c->N * c->core_stride;
+        const size_t acc_bytes = (size_t)c->N * c->acc_stride_words * 4;
+        for (int b = 0; b < 2; b++) {
+            if (core_bytes) {
+                if (cudaMalloc(&c->core[b], core_bytes) != cudaSuccess) FAIL(c, PANSIM_ERR_NOMEM, "cudaMalloc of %zu bytes (packed core) failed", core_bytes);
+                CU(c, cudaMemset(c->core[b], 0, core_bytes));
+            }
+            CU(c, cudaMalloc(&c->acc[b], acc_bytes));
+            CU(c, cudaMemset(c->acc[b], 0, acc_bytes));
+        }
+        const size_t n = c->N;
+        CU(c, cudaMalloc(&c->d_parents, n * 4));
+        CU(c, cudaMalloc(&c->d_lw, (size_t)(c->G ? c->G : 1) * 8));
+        CU(c, cudaMemset(c->d_lw, 0, (size_t)(c->G ? c->G : 1) * 8));
+        CU(c, cudaMalloc(&c->d_logfit, n * 8));
+        CU(c, cudaMalloc(&c->d_avgdist, n * 8));
+        CU(c, cudaMalloc(&c->d_num_genes, n * 4));
+        CU(c, cudaMalloc(&c->d_tmp_a, n * 8));
+        CU(c, cudaMalloc(&c->d_tmp_b, n * 8));
+        CU(c, cudaMalloc(&c->d_weights, n * 8));
+        CU(c, cudaMalloc(&c->d_cum, n * 8));
+        CU(c, cudaMalloc(&c->d_err, sizeof(int)));
+        CU(c, cudaMemset(c->d_err, 0, sizeof(int)));
+        CU(c, cudaMalloc(&c->d_rowK, 2 * n * 4));
+        CU(c, cudaMalloc(&c->d_gain_thr, (size_t)(c->G ? c->G : 1) * 4));
+        CU(c, cudaMalloc(&c->d_dump_counters, 2 * sizeof(uint32_t)));
+        CU(c, cudaMemset(c->d_dump_counters, 0, 2 * sizeof(uint32_t)));
+
+        // launch shape of the fused core kernel: persistent, grid = SMs x resident CTAs
+        c->core_smem = core_step_smem_bytes(c->tab_mut.size, c->tab_hr.size);
+        CU(c, cudaFuncSetAttribute(core_step_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->core_smem));
+        CU(c, cudaFuncSetAttribute(core_step_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->core_smem));
+        CU(c, cudaFuncSetAttribute(core_step_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->core_smem));
+        int occ = 0;
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, core_step_kernel<true, false>, CS_THREADS, c->core_smem));
+        if (occ < 1) FAIL(c, PANSIM_ERR_CUDA, "core_step_kernel does not fit on an SM (smem %zu)", c->core_smem);
+        const uint64_t items = (uint64_t)c->N * c->n_regions;
+        uint64_t grid = (uint64_t)c->sm_count * occ;
+        const uint64_t need = (items + CS_WARPS - 1) / CS_WARPS;
+        if (grid > need) grid = need;
+        if (grid < 1) grid = 1;
+        c->core_grid = (uint32_t)grid;
+        return 0;
+    };
+    int rc = body();
+    if (rc) return fail(rc);
+    *out = c;
+    return PANSIM_OK;
+}
+
+int pansim_get_info(pansim_ctx *c, pansim_info *o)
+{
+    if (!c || !o) return PANSIM_ERR_INVALID;
+    memset(o, 0, sizeof *o);
+    o->core_row_stride_bytes = c->core_stride;
+    o->acc_row_stride_bytes = (uint64_t)c->acc_stride_words * 4;
+    o->local_sites = c->Ll;
+    o->core_state_bytes = (uint64_t)c->N * c->core_stride;
+    o->algorithmic_bytes_per_generation = 2ull * c->N * ((c->Ll + 3) / 4) + 2ull * c->N * ((c->G + 7) / 8);
+    o->algorithmic_bytes_per_pair = 2ull * ((c->Ll + 3) / 4) + 2ull * ((c->G + 7) / 8);
+    o->sm_count = (uint32_t)c->sm_count;
+    o->core_step_grid = c->core_grid;
+    o->core_step_block = CS_THREADS;
+    o->core_step_smem = (uint32_t)c->core_smem;
+    return 0;
+}
+
+int pansim_get_rates(pansim_ctx *c, double *out)
+{
+    if (!c || !out) return PANSIM_ERR_INVALID;
+    out[0] = c->p_mut_site; out[1] = c->p_hr_site; out[2] = c->flip_p[0]; out[3] = c->flip_p[1];
+    return 0;
+}
+
+int pansim_set_timing(pansim_ctx *c, int enabled)
+{
+    if (!c) return PANSIM_ERR_INVALID;
+    c->timing_enabled = enabled != 0;
+    return 0;
+}
+
+int pansim_get_timing(pansim_ctx *c, pansim_timing *o)
+{
+    if (!c || !o) return PANSIM_ERR_INVALID;
+    memset(o, 0, sizeof *o);
+    o->launches = c->launches;
+    CU(c, cudaSetDevice(c->cfg.device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (!c->timing_enabled || !c->t_begin || !c->t_end) return 0;
+    CU(c, cudaEventElapsedTime(&o->total_ms, c->t_begin, c->t_end));
+    float g[TG_COUNT] = {0};
+    for (auto &s : c->spans) {
+        float ms = 0;
+        CU(c, cudaEventElapsedTime(&ms, s.a, s.b));
+        g[s.group] += ms;
+    }
+    o->select_ms = g[TG_SELECT]; o->acc_step_ms = g[TG_ACC]; o->core_step_ms = g[TG_CORE];
+    o->pair_core_ms = g[TG_PAIR_CORE]; o->pair_acc_ms = g[TG_PAIR_ACC];
+    return 0;
+}
+
+// ---- state ----------------------------------------------------------------
+int pansim_upload_core(pansim_ctx *c, const uint8_t *bytes)
+{
+    if (!c || !bytes) return PANSIM_ERR_INVALID;
+    CU(c, cudaSetDevice(c->cfg.device));
+    if (c->Ll == 0) { c->has_core = true; return 0; }
+    // stage at most ~256 MiB of host bytes at a time
+    uint32_t rows_per = (uint32_t)std::max<uint64_t>(1, (256ull << 20) / c->Ll);
+    if (rows_per > c->N) rows_per = c->N;
+    if (int rc = ensure_stage(c, (size_t)rows_per * c->Ll)) return rc;
+    uint8_t *dst = c->core[c->core_cur];
+    for (uint32_t r0 = 0; r0 < c->N; r0 += rows_per) {
+        const uint32_t nr = std::min(rows_per, c->N - r0);
+        CU(c, cudaMemcpyAsync(c->d_stage, bytes + (size_t)r0 * c->Ll, (size_t)nr * c->Ll, cudaMemcpyHostToDevice, c->stream));
+        const uint64_t words = (uint64_t)nr * (c->core_stride / 4);
+        pack_core_kernel<<<div_up64(words, 256), 256, 0, c->stream>>>(c->d_stage, c->Ll, r0, nr, dst, c->core_stride, c->d_err);
+        LAUNCH_CHECK(c);
+    }
+    if (int rc = check_device_flag(c, PANSIM_ERR_INVALID, "core matrix holds a byte that is not one-hot {1,2,4,8}")) return rc;
+    c->has_core = true;
+    return 0;
+}
+
+int pansim_upload_acc(pansim_ctx *c, const uint8_t *bytes)
+{
+    if (!c || (!bytes && c->G)) return PANSIM_ERR_INVALID;
+    CU(c, cudaSetDevice(c->cfg.device));
+    if (c->G) {
+        if (int rc = ensure_stage(c, (size_t)c->N * c->G)) return rc;
+        CU(c, cudaMemcpyAsync(c->d_stage, bytes, (size_t)c->N * c->G, cudaMemcpyHostToDevice, c->stream));
+        const uint64_t words = (uint64_t)c->N * c->acc_stride_words;
+        pack_acc_kernel<<<div_up64(words, 256), 256, 0, c->stream>>>(c->d_stage, c->G, c->N, c->acc[c->acc_cur], c->acc_stride_words, c->d_err);
+        LAUNCH_CHECK(c);
+        if (int rc = check_device_flag(c, PANSIM_ERR_INVALID, "accessory matrix holds a byte that is not 0/1")) return rc;
+    }
+    c->has_acc = true;
+    c->avgdist_valid = false;
+    return 0;
+}
+
+int pansim_set_initial(pansim_ctx *c, const uint8_t *core_row, const uint8_t *acc_row)
+{
+    if (!c || !core_row || (!acc_row && c->G)) return PANSIM_ERR_INVALID;
+    CU(c, cudaSetDevice(c->cfg.device));
+    if (c->Ll) {
+        if (int rc = ensure_stage(c, (size_t)c->Ll)) return rc;
+        CU(c, cudaMemcpyAsync(c->d_stage, core_row + c->site_begin, c->Ll, cudaMemcpyHostToDevice, c->stream));
+        uint8_t *dst = c->core[c->core_cur];
+        pack_core_kernel<<<div_up64(c->core_stride / 4, 256), 256, 0, c->stream>>>(c->d_stage, c->Ll, 0, 1, dst, c->core_stride, c->d_err);
+        LAUNCH_CHECK(c);
+        if (c->N > 1) {
+            const uint64_t vecs = (uint64_t)(c->N - 1) * (c->core_stride / 16);
+            replicate_row_kernel<<<div_up64(vecs, 256), 256, 0, c->stream>>>(dst, c->core_stride, c->N);
+            LAUNCH_CHECK(c);
+        }
+        if (int rc = check_device_flag(c, PANSIM_ERR_INVALID, "core row holds a byte that is not one-hot {1,2,4,8}")) return rc;
+    }
+    c->has_core = true;
+    if (c->G) {
+        std::vector<uint8_t> full((size_t)c->N * c->G);
+        for (uint32_t r = 0; r < c->N; r++) memcpy(full.data() + (size_t)r * c->G, acc_row, c->G);
+        return pansim_upload_acc(c, full.data());
+    }
+    c->has_acc = true;
+    return 0;
+}
+
+int pansim_download_core(pansim_ctx *c, uint8_t *out)
+{
+    if (!c || !out) return PANSIM_ERR_INVALID;
+    CU(c, cudaSetDevice(c->cfg.device));
+    if (c->Ll == 0) return 0;
+    uint32_t rows_per = (uint32_t)std::max<uint64_t>(1, (256ull << 20) / c->Ll);
+    if (rows_per > c->N) rows_per = c->N;
+    if (int rc = ensure_stage(c, (size_t)rows_per * c->Ll)) return rc;
+    const uint64_t wpr = (c->Ll + 15) / 16;
+    for (uint32_t r0 = 0; r0 < c->N; r0 += rows_per) {
+        const uint32_t nr = std::min(rows_per, c->N - r0);
+        unpack_core_kernel<<<div_up64((uint64_t)nr * wpr, 256), 256, 0, c->stream>>>(c->core[c->core_cur], c->core_stride, c->Ll, r0, nr, c->d_stage);
+        LAUNCH_CHECK(c);
+        CU(c, cudaMemcpyAsync(out + (size_t)r0 * c->Ll, c->d_stage, (size_t)nr * c->Ll, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+int pansim_export_core_csv(pansim_ctx *c, uint32_t row_begin, uint32_t row_end, char *out)
+{
+    if (!c || !out || row_begin > row_end || row_end > c->N) return PANSIM_ERR_INVALID;
+    CU(c, cudaSetDevice(c->cfg.device));
+    if (c->Ll == 0) return 0;
+    const size_t row_bytes = 2 * (size_t)c->Ll;
+    uint32_t rows_per = (uint32_t)std::max<uint64_t>(1, (256ull << 20) / row_bytes);
+    if (int rc = ensure_stage(c, (size_t)std::min<uint32_t>(rows_per, std::max(1u, row_end - row_begin)) * row_bytes)) return rc;
+    const uint64_t wpr = (c->Ll + 15) / 16;
+    for (uint32_t r0 = row_begin; r0 < row_end; r0 += rows_per) {
+        const uint32_t nr = std::min(rows_per, row_end - r0);
+        export_core_csv_kernel<<<div_up64((uint64_t)nr * wpr, 256), 256, 0, c->stream>>>(c->core[c->core_cur], c->core_stride, c->Ll, r0, nr, (char *)c->d_stage);
+        LAUNCH_CHECK(c);
+        CU(c, cudaMemcpyAsync(out + (size_t)(r0 - row_begin) * row_bytes, c->d_stage, (size_t)nr * row_bytes, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+int pansim_download_acc(pansim_ctx *c, uint8_t *out)
+{
+    if (!c || (!out && c->G)) return PANSIM_ERR_INVALID;
+    CU(c, cudaSetDevice(c->cfg.device));
+    if (c->G == 0) return 0;
+    if (int rc = ensure_stage(c, (size_t)c->N * c->G)) return rc;
+    unpack_acc_kernel<<<div_up64((uint64_t)c->N * c->G, 256), 256, 0, c->stream>>>(c->acc[c->acc_cur], c->acc_stride_words, c->G, c->N, c->d_stage);
+    LAUNCH_CHECK(c);
+    CU(c, cudaMemcpyAsync(out, c->d_stage, (size_t)c->N * c->G, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int pansim_set_selection(pansim_ctx *c, const double *s)
+{
+    if (!c || (!s && c->G)) return PANSIM_ERR_INVALID;
+    CU(c, cudaSetDevice(c->cfg.device));
+    if (c->G == 0) return 0;
+    std::vector<double> lw(c->G);
+    for (uint32_t j = 0; j < c->G; j++) lw[j] = std::log(1.0 + s[j] * 1.0);   // population.rs:306 with x = 1
+    CU(c, cudaMemcpyAsync(c->d_lw, lw.data(), (size_t)c->G * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- operators ------------------------------------------------------------
+int pansim_average_distance(pansim_ctx *c, double *out)
+{
+    if (!c) return PANSIM_ERR_INVALID;
+    if (int rc = require_state(c)) return rc;
+    CU(c, cudaSetDevice(c->cfg.device));
+    timing_begin(c);
+    {
+        ScopedSpan s(c, TG_SELECT);
+        if (int rc = launch_competition(c)) return rc;
+    }
+    timing_end(c);
+    if (out) CU(c, cudaMemcpyAsync(out, c->d_avgdist, (size_t)c->N * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int pansim_sample_indices(pansim_ctx *c, uint32_t gen, const double *avg, uint32_t *parents_out)
+{
+    if (!c) return PANSIM_ERR_INVALID;
+    if (int rc = require_state(c)) return rc;
+    CU(c, cudaSetDevice(c->cfg.device));
+    bool use_avg = false;
+    if (avg) {
+        CU(c, cudaMemcpyAsync(c->d_avgdist, avg, (size_t)c->N * 8, cudaMemcpyHostToDevice, c->stream));
+        use_avg = true;
+    } else if (c->cfg.competition_strength > 0.0) {
+        if (!c->avgdist_valid) FAIL(c, PANSIM_ERR_STATE, "competition_strength > 0: call pansim_average_distance first or pass avg_pairwise_dists");
+        use_avg = true;
+    }
+    timing_begin(c);
+    {
+        ScopedSpan s(c, TG_SELECT);
+        if (int rc = launch_select(c, gen, use_avg)) return rc;
+    }
+    timing_end(c);
+    if (parents_out) CU(c, cudaMemcpyAsync(parents_out, c->d_parents, (size_t)c->N * 4, cudaMemcpyDeviceToHost, c->stream));
+    return check_device_flag(c, PANSIM_ERR_WEIGHTS, "WeightedIndex::new would fail: a weight is negative/NaN or the total is not positive (population.rs:440)");
+}
+
+int pansim_get_weights(pansim_ctx *c, double *weights, int32_t *num_genes, double *logfit)
+{
+    if (!c) return PANSIM_ERR_INVALID;
+    CU(c, cudaSetDevice(c->cfg.device));
+    if (weights) CU(c, cudaMemcpyAsync(weights, c->d_weights, (size_t)c->N * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (num_genes) CU(c, cudaMemcpyAsync(num_genes, c->d_num_genes, (size_t)c->N * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (logfit) CU(c, cudaMemcpyAsync(logfit, c->d_logfit, (size_t)c->N * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int pansim_get_parents(pansim_ctx *c, uint32_t *out)
+{
+    if (!c || !out) return PANSIM_ERR_INVALID;
+    CU(c, cudaSetDevice(c->cfg.device));
+    CU(c, cudaMemcpyAsync(out, c->d_parents, (size_t)c->N * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int upload_parents(pansim_ctx *c, const uint32_t *parents)
+{
+    for (uint32_t i = 0; i < c->N; i++)
+        if (parents[i] >= c->N) FAIL(c, PANSIM_ERR_INVALID, "parents[%u] = %u out of range", i, parents[i]);
+    CU(c, cudaMemcpyAsync(c->d_parents, parents, (size_t)c->N * 4, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+int pansim_step_with_parents(pansim_ctx *c, uint32_t gen, const uint32_t *parents)
+{
+    if (!c || !parents) return PANSIM_ERR_INVALID;
+    if (int rc = require_state(c)) return rc;
+    CU(c, cudaSetDevice(c->cfg.device));
+    if (int rc = upload_parents(c, parents)) return rc;
+    if (c->dump_enabled) CU(c, cudaMemsetAsync(c->d_dump_counters, 0, 2 * sizeof(uint32_t), c->stream));
+    timing_begin(c);
+    {
+        ScopedSpan s(c, TG_ACC);
+        if (int rc = launch_acc_step(c, gen)) return rc;
+    }
+    {
+        ScopedSpan s(c, TG_CORE);
+        if (int rc = launch_core_step(c, gen, true)) return rc;
+    }
+    timing_end(c);
+    c->avgdist_valid = false;
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int pansim_step(pansim_ctx *c, uint32_t gen) { return pansim_run_generations(c, gen, 1); }
+
+int pansim_run_generations(pansim_ctx *c, uint32_t gen0, uint32_t n)
+{
+    if (!c) return PANSIM_ERR_INVALID;
+    if (int rc = require_state(c)) return rc;
+    CU(c, cudaSetDevice(c->cfg.device));
+    if (c->dump_enabled) CU(c, cudaMemsetAsync(c->d_dump_counters, 0, 2 * sizeof(uint32_t), c->stream));
+    timing_begin(c);
+    for (uint32_t g = 0; g < n; g++)
+        if (int rc = step_device(c, gen0 + g)) return rc;
+    timing_end(c);
+    return check_device_flag(c, PANSIM_ERR_WEIGHTS, "WeightedIndex::new would fail: a weight is negative/NaN or the total is not positive (population.rs:440)");
+}
+
+int pansim_next_generation(pansim_ctx *c, const uint32_t *parents)
+{
+    if (!c || !parents) return PANSIM_ERR_INVALID;
+    if (int rc = require_state(c)) return rc;
+    CU(c, cudaSetDevice(c->cfg.device));
+    if (int rc = upload_parents(c, parents)) return rc;
+    timing_begin(c);
+    if (c->G) {
+        const uint64_t total = (uint64_t)c->N * c->acc_stride_words;
+        acc_gather_kernel<<<div_up64(total, 256), 256, 0, c->stream>>>(c->acc[c->acc_cur], c->acc[c->acc_cur ^ 1], c->d_parents, c->N, c->acc_stride_words);
+        LAUNCH_CHECK(c);
+        c->acc_cur ^= 1;
+    }
+    if (int rc = launch_core_step(c, 0, false)) return rc;
+    timing_end(c);
+    c->avgdist_valid = false;
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int pansim_step_replay(pansim_ctx *c, const pansim_events *ev)
+{
+    if (!c || !ev || !ev->parents) return PANSIM_ERR_INVALID;
+    if (int rc = require_state(c)) return rc;
+    CU(c, cudaSetDevice(c->cfg.device));
+    const size_t nm = ev->n_core_mut, nh = ev->n_hr, nf = ev->n_acc_flip, ng = ev->n_hgt;
+    if (nm + nh >= 0xFFFFFFFEull) FAIL(c, PANSIM_ERR_INVALID, "too many core events for one replay step");
+    for (size_t k = 0; k < nm; k++)
+        if (ev->core_mut_row[k] >= c->N || ev->core_mut_site[k] >= c->L) FAIL(c, PANSIM_ERR_INVALID, "core mutation event %zu out of range", k);
+    for (size_t k = 0; k < nh; k++)
+        if (ev->hr_recipient[k] >= c->N || ev->hr_locus[k] >= c->L) FAIL(c, PANSIM_ERR_INVALID, "HR event %zu out of range", k);
+    for (size_t k = 0; k < nf; k++)
+        if (ev->acc_flip_row[k] >= c->N || ev->acc_flip_gene[k] >= c->G) FAIL(c, PANSIM_ERR_INVALID, "flip event %zu out of range", k);
+    for (size_t k = 0; k < ng; k++)
+        if (ev->hgt_recipient[k] >= c->N || ev->hgt_gene[k] >= c->G) FAIL(c, PANSIM_ERR_INVALID, "HGT event %zu out of range", k);
+
+    // main.rs:445-447
+    if (int rc = pansim_next_generation(c, ev->parents)) return rc;
+
+    // stage all event arrays in one device buffer
+    auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t need = al(nm * 4) * 2 + al(nm) + al(nh * 4) * 2 + al(nh) + al(nf * 4) * 2 + al(ng * 4) * 2 + 256;
+    if (need > c->replay_cap) {
+        if (c->d_replay) cudaFree(c->d_replay);
+        c->d_replay = nullptr; c->replay_cap = 0;
+        if (cudaMalloc(&c->d_replay, need) != cudaSuccess) FAIL(c, PANSIM_ERR_NOMEM, "cudaMalloc(%zu) for replay events failed", need);
+        c->replay_cap = need;
+    }
+    uint8_t *base = (uint8_t *)c->d_replay;
+    size_t off = 0;
+    auto put = [&](const void *src, size_t bytes) -> void * {
+        void *d = base + off;
+        if (bytes) cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, c->stream);
+        off += al(bytes);
+        return d;
+    };
+    CoreWriteList mut, hr;
+    mut.row = (uint32_t *)put(ev->core_mut_row, nm * 4);
+    mut.site = (uint32_t *)put(ev->core_mut_site, nm * 4);
+    mut.value = (uint8_t *)put(ev->core_mut_allele, nm);
+    mut.n = nm; mut.index_base = 0;
+    hr.row = (uint32_t *)put(ev->hr_recipient, nh * 4);
+    hr.site = (uint32_t *)put(ev->hr_locus, nh * 4);
+    hr.value = (uint8_t *)put(ev->hr_value, nh);
+    hr.n = nh; hr.index_base = (uint32_t)nm;
+    uint32_t *f_row = (uint32_t *)put(ev->acc_flip_row, nf * 4);
+    uint32_t *f_gene = (uint32_t *)put(ev->acc_flip_gene, nf * 4);
+    uint32_t *g_row = (uint32_t *)put(ev->hgt_recipient, ng * 4);
+    uint32_t *g_gene = (uint32_t *)put(ev->hgt_gene, ng * 4);
+    CU(c, cudaGetLastError());
+
+    // core: mutations then HR as one ordered write list (population.rs:537, :745)
+    if (nm + nh > 0 && c->Ll) {
+        size_t cap = 1024;
+        while (cap < 2 * (nm + nh)) cap <<= 1;
+        if (cap > c->hash_cap) {
+            if (c->d_hkeys) cudaFree(c->d_hkeys);
+            if (c->d_hvals) cudaFree(c->d_hvals);
+            c->d_hkeys = nullptr; c->d_hvals = nullptr; c->hash_cap = 0;
+            if (cudaMalloc(&c->d_hkeys, cap * 8) != cudaSuccess || cudaMalloc(&c->d_hvals, cap * 4) != cudaSuccess)
+                FAIL(c, PANSIM_ERR_NOMEM, "cudaMalloc for the replay hash table (%zu slots) failed", cap);
+            c->hash_cap = cap;
+        }
+        cap = c->hash_cap;
+        CU(c, cudaMemsetAsync(c->d_hkeys, 0, cap * 8, c->stream));
+        CU(c, cudaMemsetAsync(c->d_hvals, 0, cap * 4, c->stream));
+        uint8_t *state = c->core[c->core_cur];
+        for (CoreWriteList *l : {&mut, &hr}) {
+            if (!l->n) continue;
+            replay_insert_kernel<<<div_up64(l->n, 256), 256, 0, c->stream>>>(*l, c->site_begin, c->site_end, c->Ll, c->d_hkeys, c->d_hvals, cap - 1);
+            LAUNCH_CHECK(c);
+        }
+        for (CoreWriteList *l : {&mut, &hr}) {
+            if (!l->n) continue;
+            replay_apply_kernel<<<div_up64(l->n, 256), 256, 0, c->stream>>>(*l, c->site_begin, c->site_end, c->Ll, c->d_hkeys, c->d_hvals, cap - 1, state, c->core_stride, c->d_err);
+            LAUNCH_CHECK(c);
+        }
+    }
+    // accessory: flips (population.rs:504-508) then HGT sets (:745 with value 1)
+    if (nf) {
+        acc_apply_flips_kernel<<<div_up64(nf, 256), 256, 0, c->stream>>>(c->acc[c->acc_cur], f_row, f_gene, nf, c->acc_stride_words);
+        LAUNCH_CHECK(c);
+    }
+    if (ng) {
+        acc_apply_sets_kernel<<<div_up64(ng, 256), 256, 0, c->stream>>>(c->acc[c->acc_cur], g_row, g_gene, ng, c->acc_stride_words);
+        LAUNCH_CHECK(c);
+    }
+    return check_device_flag(c, PANSIM_ERR_INVALID, "replay event carries an allele that is not one-hot {1,2,4,8}");
+}
+
+// ---- distances ------------------------------------------------------------
+static int ensure_pairs(pansim_ctx *c, size_t n)
+{
+    if (n <= c->pair_cap) return 0;
+    for (uint32_t **p : {&c->d_r1, &c->d_r2, &c->d_cd, &c->d_in, &c->d_un}) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+    }
+    c->pair_cap = 0;
+    for (uint32_t **p : {&c->d_r1, &c->d_r2, &c->d_cd, &c->d_in, &c->d_un})
+        if (cudaMalloc(p, n * 4) != cudaSuccess) FAIL(c, PANSIM_ERR_NOMEM, "cudaMalloc for %zu pairs failed", n);
+    c->pair_cap = n;
+    return 0;
+}
+
+static int pair_counts_impl(pansim_ctx *c, const uint32_t *r1, const uint32_t *r2, size_t P, uint32_t *d_cd,
+                            uint32_t *d_in, uint32_t *d_un)
+{
+    if (P > 0x7FFFFFFFull) FAIL(c, PANSIM_ERR_INVALID, "more than 2^31 pairs per call");
+    for (size_t k = 0; k < P; k++)
+        if (r1[k] >= c->N || r2[k] >= c->N) FAIL(c, PANSIM_ERR_INVALID, "pair %zu out of range", k);
+    CU(c, cudaMemcpyAsync(c->d_r1, r1, P * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->d_r2, r2, P * 4, cudaMemcpyHostToDevice, c->stream));
+    timing_begin(c);
+    if (d_cd) {
+        ScopedSpan s(c, TG_PAIR_CORE);
+        if (c->Ll == 0) {
+            CU(c, cudaMemsetAsync(d_cd, 0, P * 4, c->stream));
+        } else {
+            const uint32_t row_vec4 = (uint32_t)(c->core_stride / 16);
+            // column chunk sized so that N x chunk stays L2 resident
+            uint64_t chunk_bytes = (48ull << 20) / c->N;
+            chunk_bytes = (chunk_bytes / 4096) * 4096;
+            if (chunk_bytes < 4096) chunk_bytes = 4096;
+            if (chunk_bytes > c->core_stride) chunk_bytes = ((c->core_stride + 4095) / 4096) * 4096;
+            uint32_t chunk_vec4 = (uint32_t)(chunk_bytes / 16);
+            uint32_t n_chunks = (row_vec4 + chunk_vec4 - 1) / chunk_vec4;
+            if (n_chunks > 65535) { n_chunks = 65535; chunk_vec4 = (row_vec4 + n_chunks - 1) / n_chunks; chunk_vec4 = ((chunk_vec4 + 255) / 256) * 256; n_chunks = (row_vec4 + chunk_vec4 - 1) / chunk_vec4; }
+            if (n_chunks > 1) CU(c, cudaMemsetAsync(d_cd, 0, P * 4, c->stream));
+            const uint32_t gx = (uint32_t)std::min<size_t>(P, 1u << 20);
+            pair_core_kernel<<<dim3(gx, n_chunks), PAIR_THREADS, 0, c->stream>>>(c->core[c->core_cur], c->core_stride, chunk_vec4, row_vec4, c->d_r1, c->d_r2, (uint32_t)P, d_cd);
+            LAUNCH_CHECK(c);
+        }
+    }
+    if (d_in || d_un) {
+        ScopedSpan s(c, TG_PAIR_ACC);
+        const uint32_t grid = (uint32_t)std::min<size_t>((P + 7) / 8, (size_t)c->sm_count * 16);
+        pair_acc_kernel<<<grid ? grid : 1, 256, 0, c->stream>>>(c->acc[c->acc_cur], c->acc_stride_words, c->acc_words, c->d_r1, c->d_r2, (uint32_t)P, d_in, d_un);
+        LAUNCH_CHECK(c);
+    }
+    timing_end(c);
+    return 0;
+}
+
+int pansim_pair_counts(pansim_ctx *c, const uint32_t *r1, const uint32_t *r2, size_t P, uint32_t *core_diff,
+                       uint32_t *inter, uint32_t *uni)
+{
+    if (!c || (P && (!r1 || !r2))) return PANSIM_ERR_INVALID;
+    if (int rc = require_state(c)) return rc;
+    if (P == 0) return 0;
+    CU(c, cudaSetDevice(c->cfg.device));
+    if (int rc = ensure_pairs(c, P)) return rc;
+    if (int rc = pair_counts_impl(c, r1, r2, P, core_diff ? c->d_cd : nullptr, (inter || uni) ? c->d_in : nullptr, (inter || uni) ? c->d_un : nullptr)) return rc;
+    if (core_diff) CU(c, cudaMemcpyAsync(core_diff, c->d_cd, P * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (inter) CU(c, cudaMemcpyAsync(inter, c->d_in, P * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (uni) CU(c, cudaMemcpyAsync(uni, c->d_un, P * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int pansim_pair_counts_device(pansim_ctx *c, const uint32_t *r1, const uint32_t *r2, size_t P, void *d_cd,
+                              void *d_in, void *d_un)
+{
+    if (!c || (P && (!r1 || !r2))) return PANSIM_ERR_INVALID;
+    if (int rc = require_state(c)) return rc;
+    if (P == 0) return 0;
+    CU(c, cudaSetDevice(c->cfg.device));
+    if (int rc = ensure_pairs(c, P)) return rc;
+    if (int rc = pair_counts_impl(c, r1, r2, P, (uint32_t *)d_cd, (uint32_t *)d_in, (uint32_t *)d_un)) return rc;
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int pansim_gene_counts(pansim_ctx *c, uint32_t *counts)
+{
+    if (!c || (!counts && c->G)) return PANSIM_ERR_INVALID;
+    if (int rc = require_state(c)) return rc;
+    if (c->G == 0) return 0;
+    CU(c, cudaSetDevice(c->cfg.device));
+    acc_gene_counts_kernel<<<c->acc_words, 256, 0, c->stream>>>(c->acc[c->acc_cur], c->N, c->G, c->acc_stride_words, c->d_gain_thr);
+    LAUNCH_CHECK(c);
+    CU(c, cudaMemcpyAsync(counts, c->d_gain_thr, (size_t)c->G * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- event dump -------------------------------------------------------------
+int pansim_enable_event_dump(pansim_ctx *c, size_t max_core_events)
+{
+    if (!c || max_core_events == 0 || max_core_events > 0x7FFFFFFFull) return PANSIM_ERR_INVALID;
+    CU(c, cudaSetDevice(c->cfg.device));
+    if (c->dump_enabled) FAIL(c, PANSIM_ERR_STATE, "event dump already enabled");
+    const size_t n = max_core_events;
+    CU(c, cudaMalloc(&c->d_mut_row, n * 4)); CU(c, cudaMalloc(&c->d_mut_site, n * 4));
+    CU(c, cudaMalloc(&c->d_mut_seq, n * 4)); CU(c, cudaMalloc(&c->d_mut_allele, n));
+    CU(c, cudaMalloc(&c->d_hr_rec, n * 4)); CU(c, cudaMalloc(&c->d_hr_locus, n * 4));
+    CU(c, cudaMalloc(&c->d_hr_donor, n * 4)); CU(c, cudaMalloc(&c->d_hr_seq, n * 4));
+    CU(c, cudaMalloc(&c->d_hr_value, n));
+    const size_t accw = (size_t)c->N * c->acc_stride_words * 4;
+    CU(c, cudaMalloc(&c->d_dump_flip, accw)); CU(c, cudaMalloc(&c->d_dump_gain, accw));
+    CU(c, cudaMemset(c->d_dump_flip, 0, accw)); CU(c, cudaMemset(c->d_dump_gain, 0, accw));
+    c->dump_cap = (uint32_t)n;
+    c->dump_enabled = true;
+    return 0;
+}
+
+int pansim_fetch_event_dump(pansim_ctx *c, pansim_event_dump *o)
+{
+    if (!c || !o) return PANSIM_ERR_INVALID;
+    if (!c->dump_enabled) FAIL(c, PANSIM_ERR_STATE, "event dump not enabled");
+    CU(c, cudaSetDevice(c->cfg.device));
+    CU(c, cudaStreamSynchronize(c->stream));
+    memset(o, 0, sizeof *o);
+    uint32_t cnt[2];
+    CU(c, cudaMemcpy(cnt, c->d_dump_counters, sizeof cnt, cudaMemcpyDeviceToHost));
+    if (cnt[0] > c->dump_cap || cnt[1] > c->dump_cap) FAIL(c, PANSIM_ERR_NOMEM, "event dump overflow: %u SNP / %u HR events, capacity %u", cnt[0], cnt[1], c->dump_cap);
+    auto fetch = [&](const void *d, size_t bytes) -> void * {
+        void *h = malloc(bytes ? bytes : 1);
+        if (bytes) cudaMemcpy(h, d, bytes, cudaMemcpyDeviceToHost);
+        return h;
+    };
+    o->n_core_mut = cnt[0];
+    o->core_mut_row = (uint32_t *)fetch(c->d_mut_row, cnt[0] * 4ul);
+    o->core_mut_site = (uint32_t *)fetch(c->d_mut_site, cnt[0] * 4ul);
+    o->core_mut_seq = (uint32_t *)fetch(c->d_mut_seq, cnt[0] * 4ul);
+    o->core_mut_allele = (uint8_t *)fetch(c->d_mut_allele, cnt[0]);
+    o->n_hr = cnt[1];
+    o->hr_recipient = (uint32_t *)fetch(c->d_hr_rec, cnt[1] * 4ul);
+    o->hr_locus = (uint32_t *)fetch(c->d_hr_locus, cnt[1] * 4ul);
+    o->hr_donor = (uint32_t *)fetch(c->d_hr_donor, cnt[1] * 4ul);
+    o->hr_seq = (uint32_t *)fetch(c->d_hr_seq, cnt[1] * 4ul);
+    o->hr_value = (uint8_t *)fetch(c->d_hr_value, cnt[1]);
+    const size_t words = (size_t)c->N * c->acc_stride_words;
+    std::vector<uint32_t> tmp(words ? words : 1);
+    for (int which = 0; which < 2; which++) {
+        uint8_t *m = (uint8_t *)malloc(((size_t)c->N * c->G) > 0 ? (size_t)c->N * c->G : 1);
+        CU(c, cudaMemcpy(tmp.data(), which ? c->d_dump_gain : c->d_dump_flip, words * 4, cudaMemcpyDeviceToHost));
+        for (uint32_t r = 0; r < c->N; r++)
+            for (uint32_t g = 0; g < c->G; g++)
+                m[(size_t)r * c->G + g] = (uint8_t)((tmp[(size_t)r * c->acc_stride_words + (g >> 5)] >> (g & 31)) & 1u);
+        if (which) o->acc_gain_mask = m; else o->acc_flip_mask = m;
+    }
+    CU(c, cudaGetLastError());
+    return 0;
+}
+
+void pansim_free_event_dump(pansim_event_dump *d)
+{
+    if (!d) return;
+    free(d->core_mut_row); free(d->core_mut_site); free(d->core_mut_seq); free(d->core_mut_allele);
+    free(d->hr_recipient); free(d->hr_locus); free(d->hr_donor); free(d->hr_seq); free(d->hr_value);
+    free(d->acc_flip_mask); free(d->acc_gain_mask);
+    memset(d, 0, sizeof *d);
+}
+
+}  // extern "C"

@@ -1,0 +1,481 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle on the
+same inputs. Integer / byte / index results must be bit-exact; f64 results are
+bit-exact where the summation order is reproduced, otherwise rtol is stated."""
+import numpy as np
+import pytest
+
+import pansim_b200 as pb
+from oracle import binding as ob
+from helpers import oracle_apply_gpu_events, random_state, sample_pairs, small_params
+
+pytestmark = pytest.mark.gpu
+
+
+def make(p, **kw):
+    return pb.Pansim.from_params(p, **kw)
+
+
+# ---------------------------------------------------------------- T: layout
+@pytest.mark.parametrize("N,L,G", [(3, 9, 10), (5, 16, 32), (7, 8191, 33), (4, 8193, 1), (6, 20000, 4000),
+                                   (2, 70001, 95)])
+def test_upload_download_round_trip(N, L, G):
+    rng = np.random.default_rng(N * L + G)
+    core, acc = random_state(rng, N, L, G)
+    p = pb.Params(pop_size=N, core_size=L, pan_genes=G + 5, core_genes=5)
+    with make(p) as sim:
+        sim.upload(core, acc)
+        assert (sim.download_core() == core).all()
+        assert (sim.download_acc() == acc).all()
+
+
+def test_upload_rejects_non_onehot():
+    p = pb.Params(pop_size=2, core_size=40, pan_genes=12, core_genes=2)
+    core = np.ones((2, 40), np.uint8)
+    core[1, 7] = 3
+    with make(p) as sim:
+        with pytest.raises(pb.PansimError) as e:
+            sim.upload(core_onehot=core)
+        assert e.value.code == -1
+
+
+def test_set_initial_is_clonal():
+    p = small_params()
+    d = pb.derive(p)
+    rng = np.random.default_rng(0)
+    row = (1 << rng.integers(0, 4, p.core_size)).astype(np.uint8)
+    arow = (rng.random(d.pan_size) < 0.25).astype(np.uint8)
+    with make(p) as sim:
+        sim.set_initial(row, arow)
+        assert (sim.download_core() == row[None, :]).all()
+        assert (sim.download_acc() == arow[None, :]).all()
+
+
+def test_export_core_csv_matches_int_to_base():
+    # population.rs:877-879, 154-162
+    rng = np.random.default_rng(4)
+    core, acc = random_state(rng, 5, 37, 8)
+    p = pb.Params(pop_size=5, core_size=37, pan_genes=10, core_genes=2)
+    with make(p) as sim:
+        sim.upload(core, acc)
+        txt = sim.export_core_csv(0, 5).decode()
+    lut = {1: "A", 2: "C", 4: "G", 8: "T"}
+    want = "".join(",".join(lut[int(x)] for x in row) + "\n" for row in core)
+    assert txt == want
+
+
+# ------------------------------------------------------------ D: distances
+def test_KAT_H1_J1_through_cabi():
+    r1 = np.array([1, 2, 4, 8, 1, 2, 4, 8, 1], np.uint8)
+    r2 = np.array([1, 4, 4, 2, 8, 2, 4, 8, 2], np.uint8)
+    x = np.array([1, 0, 1, 1, 0, 0, 1, 0, 1, 1], np.uint8)
+    y = np.array([1, 1, 0, 1, 0, 0, 0, 0, 1, 0], np.uint8)
+    p = pb.Params(pop_size=2, core_size=9, pan_genes=12, core_genes=2)
+    with make(p) as sim:
+        sim.upload(np.stack([r1, r2]), np.stack([x, y]))
+        cd, it, un = sim.pair_counts([0], [1])
+        assert (cd[0], it[0], un[0]) == (4, 3, 7)
+        core_d, acc_d = sim.pairwise_distances([0, 1], [1, 0])
+        assert core_d.tolist() == [0.4444444444444444] * 2
+        assert acc_d.tolist() == [0.4444444444444444] * 2
+
+
+@pytest.mark.parametrize("N,L,G,P", [(2, 1, 1, 4), (9, 100, 31, 200), (33, 8192, 64, 500), (17, 50001, 333, 400),
+                                     (64, 300000, 4000, 1000)])
+def test_pair_counts_match_oracle(N, L, G, P):
+    rng = np.random.default_rng(L + G)
+    core, acc = random_state(rng, N, L, G)
+    # make some rows near-identical so small distances occur too
+    core[1] = core[0]
+    core[1, ::7] = 8
+    r1, r2 = sample_pairs(rng, N, P)
+    p = pb.Params(pop_size=N, core_size=L, pan_genes=G + 3, core_genes=3)
+    with make(p) as sim:
+        sim.upload(core, acc)
+        cd, it, un = sim.pair_counts(r1, r2)
+        core_d, acc_d = sim.pairwise_distances(r1, r2)
+    ocore = ob.Population(core, True, 3)
+    opan = ob.Population(acc, False, 3)
+    assert (cd == ocore.pair_counts(r1, r2)).all()
+    oi, ou = opan.pair_counts(r1, r2)
+    assert (it == oi).all() and (un == ou).all()
+    assert (core_d == ocore.pairwise_distances(r1, r2)).all()       # bit-exact f64
+    assert (acc_d == opan.pairwise_distances(r1, r2)).all()
+
+
+def test_pair_counts_self_and_repeated_pairs():
+    rng = np.random.default_rng(8)
+    core, acc = random_state(rng, 6, 1000, 40)
+    p = pb.Params(pop_size=6, core_size=1000, pan_genes=40, core_genes=0)
+    r1 = np.array([0, 0, 3, 3, 5], np.uint32)
+    r2 = np.array([0, 1, 2, 2, 5], np.uint32)
+    with make(p) as sim:
+        sim.upload(core, acc)
+        cd, it, un = sim.pair_counts(r1, r2)
+    assert cd[0] == 0 and cd[4] == 0 and cd[2] == cd[3]
+    assert it[0] == un[0] == acc[0].sum()
+
+
+# ------------------------------------------------------------- Q: reductions
+def test_gene_counts_and_frequencies():
+    rng = np.random.default_rng(5)
+    core, acc = random_state(rng, 37, 64, 1001)
+    p = pb.Params(pop_size=37, core_size=64, pan_genes=1011, core_genes=10)
+    with make(p) as sim:
+        sim.upload(core, acc)
+        opan = ob.Population(acc, False, 10)
+        assert (sim.gene_counts() == opan.gene_counts()).all()
+        assert (sim.gene_frequencies() == opan.gene_frequencies()).all()
+        assert sim.calc_gene_freq() == opan.calc_gene_freq()
+
+
+# ------------------------------------------------------------ G: gather
+def test_next_generation_matches_oracle():
+    rng = np.random.default_rng(6)
+    N, L, G = 21, 25000, 130
+    core, acc = random_state(rng, N, L, G)
+    parents = rng.integers(0, N, N).astype(np.uint32)
+    p = pb.Params(pop_size=N, core_size=L, pan_genes=G, core_genes=0)
+    with make(p) as sim:
+        sim.upload(core, acc)
+        sim.next_generation(parents)
+        assert (sim.download_core() == core[parents]).all()
+        assert (sim.download_acc() == acc[parents]).all()
+        with pytest.raises(pb.PansimError):
+            sim.next_generation(np.full(N, N, np.uint32))
+
+
+# ---------------------------------------------------- F, C, W: selection
+def test_fitness_and_average_distance_bit_exact():
+    rng = np.random.default_rng(7)
+    N, G = 80, 700
+    core, acc = random_state(rng, N, 50, G, 0.25)
+    acc[5] = acc[4]                       # identical rows -> small distances
+    sel = rng.normal(0, 0.1, G)
+    sel[3] = -1.0                          # lethal gene (population.rs:312-318)
+    p = pb.Params(pop_size=N, core_size=50, pan_genes=G + 50, core_genes=50, competition_strength=0.7,
+                  genome_size_penalty=0.98)
+    d = pb.derive(p)
+    opan = ob.Population(acc, False, 50)
+    with make(p) as sim:
+        sim.upload(core, acc)
+        sim.set_selection(sel)
+        avg = sim.average_distance()
+        assert (avg == opan.average_distance()).all()          # bit-exact (same f64 op order)
+        sim.sample_indices(0)
+        w, ng, lf = sim.weights()
+    ow, ong, olf = opan.selection_weights(d.avg_gene_num, opan.average_distance(), sel, False, 0.98, 0.7)
+    assert (ng == ong).all()
+    assert (lf == olf).all()                                    # bit-exact column-order sum
+    assert (lf[acc[:, 3] == 1] == 0.0).all()
+    # softmax chain: CUDA libm exp/log differ from glibc by ulps -> rtol 1e-12
+    np.testing.assert_allclose(w / w.sum(), ow / ow.sum(), rtol=1e-12)
+
+
+def test_average_distance_identical_population_is_min_positive():
+    p = pb.Params(pop_size=5, core_size=16, pan_genes=40, core_genes=8, competition_strength=1.0)
+    with make(p) as sim:
+        sim.upload(np.ones((5, 16), np.uint8), np.ones((5, 32), np.uint8))
+        assert (sim.average_distance() == np.finfo(np.float64).tiny).all()
+
+
+def test_parent_draws_follow_weights_and_are_reproducible():
+    rng = np.random.default_rng(9)
+    N, G = 40, 64
+    core, acc = random_state(rng, N, 50, G, 0.5)
+    sel = rng.normal(0, 0.3, G).clip(-0.9, None)
+    p = pb.Params(pop_size=N, core_size=50, pan_genes=G, core_genes=0, seed=5)
+    counts = np.zeros(N)
+    with make(p) as sim:
+        sim.upload(core, acc)
+        sim.set_selection(sel)
+        first = sim.sample_indices(0)
+        assert (sim.sample_indices(0) == first).all()          # counter-based: same key, same draw
+        assert (sim.parents() == first).all()
+        w, _, _ = sim.weights()
+        n_gen = 400
+        for g in range(n_gen):
+            counts += np.bincount(sim.sample_indices(g), minlength=N)
+    expected = w / w.sum() * N * n_gen
+    chi2 = ((counts - expected) ** 2 / expected).sum()
+    assert chi2 < 100          # 39 dof: mean 39, sd 8.8
+
+
+def test_sample_indices_error_where_reference_panics():
+    # WeightedIndex::new(...).unwrap() panics on NaN weights (population.rs:440)
+    p = pb.Params(pop_size=4, core_size=16, pan_genes=8, core_genes=0, competition_strength=1.0)
+    with make(p) as sim:
+        sim.upload(np.ones((4, 16), np.uint8), np.ones((4, 8), np.uint8))
+        with pytest.raises(pb.PansimError) as e:
+            sim.sample_indices(0, np.array([1.0, -1.0, 1.0, 1.0]))     # ln(-1) = NaN
+        assert e.value.code == -4
+        assert sim.sample_indices(0, np.ones(4)).max() < 4              # context still usable
+
+
+# ------------------------------------------------------- K6: replay mode
+@pytest.mark.parametrize("seed", [0, 1])
+def test_replay_step_bit_exact_vs_oracle(seed):
+    rng = np.random.default_rng(seed)
+    N, L, G = 24, 20000, 300
+    core, acc = random_state(rng, N, L, G)
+    ocore, opan = ob.Population(core, True, 0), ob.Population(acc, False, 0)
+    p = pb.Params(pop_size=N, core_size=L, pan_genes=G, core_genes=0)
+    main_rng = ob.make_rng(seed)
+    with make(p) as sim:
+        sim.upload(core, acc)
+        for gen in range(3):
+            parents = rng.integers(0, N, N).astype(np.uint32)
+            ocore.next_generation(parents)
+            opan.next_generation(parents)
+            ev = ob.EventLog()
+            # oracle generate mode = the reference's event loops (population.rs:467-751)
+            ocore.mutate_alleles([3000.0], [(0, L)], seed, gen, ev)
+            opan.mutate_alleles([40.0, 300.0], [(0, 250), (250, G)], seed, gen, ev)
+            ocore.recombine([1500.0], [(0, L)], main_rng, seed, gen, ev)
+            opan.recombine([30.0, 10.0], [(0, 250), (250, G)], main_rng, seed, gen, ev)
+            a = ev.arrays()
+            # force same-cell collisions: repeat a block of events with other alleles
+            sim.step_replay(parents,
+                            core_mut=(a["core_mut_row"], a["core_mut_site"], a["core_mut_allele"]),
+                            acc_flip=(a["acc_flip_row"], a["acc_flip_gene"]),
+                            hr=(a["hr_recipient"], a["hr_locus"], a["hr_value"]),
+                            hgt=(a["hgt_recipient"], a["hgt_gene"]))
+            assert (sim.download_core() == ocore.m).all()
+            assert (sim.download_acc() == opan.m).all()
+
+
+def test_replay_last_writer_wins_with_forced_collisions():
+    N, L, G = 4, 100, 8
+    core = np.ones((N, L), np.uint8)
+    acc = np.zeros((N, G), np.uint8)
+    p = pb.Params(pop_size=N, core_size=L, pan_genes=G, core_genes=0)
+    rng = np.random.default_rng(3)
+    M = 5000
+    row = rng.integers(0, N, M).astype(np.uint32)
+    site = rng.integers(0, 10, M).astype(np.uint32)            # 40 cells, 5000 writes
+    val = (1 << rng.integers(1, 4, M)).astype(np.uint8)
+    hrow = rng.integers(0, N, 700).astype(np.uint32)
+    hsite = rng.integers(0, 12, 700).astype(np.uint32)
+    hval = (1 << rng.integers(0, 4, 700)).astype(np.uint8)
+    frow = rng.integers(0, N, 999).astype(np.uint32)
+    fgene = rng.integers(0, G, 999).astype(np.uint32)
+    parents = np.arange(N, dtype=np.uint32)
+    ocore, opan = ob.Population(core, True), ob.Population(acc, False)
+    ocore.apply_core_writes(row, site, val)
+    ocore.apply_core_writes(hrow, hsite, hval)
+    opan.apply_acc_flips(frow, fgene)
+    opan.apply_acc_sets(np.array([1, 1], np.uint32), np.array([2, 2], np.uint32))
+    with make(p) as sim:
+        sim.upload(core, acc)
+        sim.step_replay(parents, core_mut=(row, site, val), acc_flip=(frow, fgene), hr=(hrow, hsite, hval),
+                        hgt=([1, 1], [2, 2]))
+        assert (sim.download_core() == ocore.m).all()
+        assert (sim.download_acc() == opan.m).all()
+
+
+def test_replay_empty_events_is_gather():
+    rng = np.random.default_rng(2)
+    core, acc = random_state(rng, 5, 77, 9)
+    parents = np.array([4, 4, 0, 1, 2], np.uint32)
+    with make(pb.Params(pop_size=5, core_size=77, pan_genes=9, core_genes=0)) as sim:
+        sim.upload(core, acc)
+        sim.step_replay(parents)
+        assert (sim.download_core() == core[parents]).all()
+
+
+# ----------------------------------------- K4/K5: generate mode vs oracle
+@pytest.mark.parametrize("kw", [
+    dict(),                                                       # defaults-like rates
+    dict(HR_rate=1.0, HGT_rate=1.0, rate_genes2=1000.0),          # cfg3: heavy recombination
+    dict(core_mu=0.9, HR_rate=0.5),                               # many events per block
+    dict(core_size=8192 * 3 + 5, HR_rate=0.3),                    # ragged last region
+    dict(HR_rate=0.0, HGT_rate=0.0),                              # recombination off (main.rs:459-464)
+    dict(prop_genes2=0.0), dict(prop_genes2=1.0),                 # single compartment
+    dict(prop_positive=0.2, competition_strength=0.5),            # cfg2: selection on
+])
+def test_generate_step_equals_oracle_replay_of_its_own_events(kw):
+    """The fused generate-mode step draws events from Philox and applies them in
+    one pass. Dumping those events and replaying them on the ORACLE with the
+    reference's operator order / snapshot / last-writer semantics must give the
+    same state bit for bit (this checks gather, SNP apply, the HR snapshot
+    recomputation, flips and HGT application)."""
+    p = small_params(**kw)
+    d = pb.derive(p)
+    rng = np.random.default_rng(11)
+    core_row = (1 << rng.integers(0, 4, p.core_size)).astype(np.uint8)
+    acc_row = (rng.random(d.pan_size) < d.avg_gene_freq_adj).astype(np.uint8)
+    sel = ob.selection_coefficients(ob.default_params(prop_positive=p.prop_positive), d.pan_size, ob.make_rng(1))
+    ocore = ob.Population(np.tile(core_row, (p.pop_size, 1)), True, p.core_genes)
+    opan = ob.Population(np.tile(acc_row, (p.pop_size, 1)), False, p.core_genes)
+    with make(p) as sim:
+        sim.set_initial(core_row, acc_row)
+        sim.set_selection(sel)
+        sim.enable_event_dump(4_000_000)
+        for gen in range(p.n_gen):
+            sim.step(gen)
+            ev = sim.fetch_event_dump()
+            oracle_apply_gpu_events(ev, sim.parents(), ocore, opan)
+            assert (sim.download_core() == ocore.m).all(), f"core differs at gen {gen}"
+            assert (sim.download_acc() == opan.m).all(), f"accessory differs at gen {gen}"
+            if p.HR_rate > 0:
+                assert len(ev["hr_recipient"]) > 0
+                assert (ev["hr_recipient"] != ev["hr_donor"]).all()      # population.rs:616-619
+            assert set(np.unique(ev["core_mut_allele"])) <= {2, 4, 8}   # population.rs:531 quirk
+
+
+def test_hr_value_is_donor_post_mutation_snapshot():
+    # population.rs:693-695: value = donor row after mutate_alleles, before any HR apply
+    p = small_params(HR_rate=1.0, core_mu=0.3, n_gen=1)
+    d = pb.derive(p)
+    rng = np.random.default_rng(12)
+    core, acc = random_state(rng, p.pop_size, p.core_size, d.pan_size)
+    with make(p) as sim:
+        sim.upload(core, acc)
+        sim.enable_event_dump(4_000_000)
+        parents = rng.integers(0, p.pop_size, p.pop_size).astype(np.uint32)
+        sim.step_with_parents(0, parents)
+        ev = sim.fetch_event_dump()
+    snap = ob.Population(core, True)
+    snap.next_generation(parents)
+    o = np.lexsort((ev["core_mut_seq"], ev["core_mut_row"]))
+    snap.apply_core_writes(ev["core_mut_row"][o], ev["core_mut_site"][o], ev["core_mut_allele"][o])
+    assert (snap.m[ev["hr_donor"], ev["hr_locus"]] == ev["hr_value"]).all()
+    assert len(ev["hr_value"]) > 1000
+
+
+def test_generate_mode_event_rates():
+    """Event counts follow the reference's Poisson means (main.rs:275-280, 348-366)."""
+    p = small_params(pop_size=64, core_size=200000, n_gen=1, HR_rate=0.5, HGT_rate=0.5)
+    d = pb.derive(p)
+    rng = np.random.default_rng(13)
+    core, acc = random_state(rng, p.pop_size, p.core_size, d.pan_size, 0.25)
+    with make(p) as sim:
+        sim.upload(core, acc)
+        sim.enable_event_dump(8_000_000)
+        sim.step_with_parents(0, np.arange(p.pop_size, dtype=np.uint32))
+        ev = sim.fetch_event_dump()
+        rates = sim.rates()
+    N = p.pop_size
+    n_mut, n_hr = len(ev["core_mut_row"]), len(ev["hr_recipient"])
+    exp_mut, exp_hr = N * d.n_core_mutations, N * d.n_recombinations_core
+    assert abs(n_mut - exp_mut) < 5 * np.sqrt(exp_mut)
+    assert abs(n_hr - exp_hr) < 5 * np.sqrt(exp_hr)
+    # uniform positions: chi-square over 50 bins of the site coordinate
+    h = np.bincount((ev["core_mut_site"].astype(np.int64) * 50) // p.core_size, minlength=50)
+    assert ((h - n_mut / 50) ** 2 / (n_mut / 50)).sum() < 110
+    # alleles uniform on {C,G,T}
+    a = np.bincount(ev["core_mut_allele"], minlength=9)[[2, 4, 8]]
+    assert ((a - n_mut / 3) ** 2 / (n_mut / 3)).sum() < 20
+    # donors uniform over the other rows
+    hd = np.bincount(ev["hr_donor"], minlength=N)
+    assert ((hd - n_hr / N) ** 2 / (n_hr / N)).sum() < 2 * N
+    # flips: per-gene probability (1 - exp(-2 rate)) / 2
+    for c, (lo, hi) in enumerate(d.comp):
+        f = ev["acc_flip_mask"][:, lo:hi].mean()
+        sd = np.sqrt(rates[2 + c] * (1 - rates[2 + c]) / (N * (hi - lo)))
+        assert abs(f - rates[2 + c]) < 5 * sd
+    assert abs(rates[0] - (1 - np.exp(-d.n_core_mutations / p.core_size))) < 1e-15
+
+
+def test_hgt_gain_probability_matches_event_process():
+    """Gain probability of an absent gene = 1 - exp(-lambda_c/(N-1) * sum_d x_dg / K_dc)
+    (derived from population.rs:616-680)."""
+    p = small_params(pop_size=200, core_size=64, pan_genes=120, core_genes=20, HGT_rate=20.0, core_mu=0.5,
+                     rate_genes1=0.0, rate_genes2=0.0, n_gen=1)
+    d = pb.derive(p)
+    rng = np.random.default_rng(14)
+    N, G = p.pop_size, d.pan_size
+    core = np.ones((N, 64), np.uint8)
+    freq = np.linspace(0.05, 0.9, G)
+    acc = (rng.random((N, G)) < freq[None, :]).astype(np.uint8)
+    with make(p) as sim:
+        sim.upload(core, acc)
+        sim.enable_event_dump(1 << 16)
+        sim.step_with_parents(0, np.arange(N, dtype=np.uint32))
+        gain = sim.fetch_event_dump()["acc_gain_mask"]
+        new = sim.download_acc()
+    assert (new == (acc | gain)).all()
+    assert (gain & acc).sum() == 0
+    z = 0.0
+    for c, (lo, hi) in enumerate(d.comp):
+        K = acc[:, lo:hi].sum(axis=1).astype(np.float64)
+        S = ((acc[:, lo:hi] == 1) / np.where(K > 0, K, 1)[:, None]).sum(axis=0)
+        pg = 1 - np.exp(-d.n_recombinations_pan[c] / (N - 1) * S)
+        absent = (acc[:, lo:hi] == 0)
+        exp_gain = (absent * pg[None, :]).sum()
+        var = (absent * (pg * (1 - pg))[None, :]).sum()
+        got = gain[:, lo:hi].sum()
+        z = max(z, abs(got - exp_gain) / np.sqrt(var))
+        assert exp_gain > 100
+    assert z < 5
+
+
+# ------------------------------------------------- E: column sharding
+def test_column_shards_reproduce_single_context():
+    """Results do not depend on how the core columns are split over contexts/GPUs:
+    the RNG is keyed by (seed, gen, row, site block)."""
+    p = small_params(core_size=8192 * 5 + 77, HR_rate=0.5, n_gen=3, prop_positive=0.1)
+    d = pb.derive(p)
+    rng = np.random.default_rng(15)
+    core_row = (1 << rng.integers(0, 4, p.core_size)).astype(np.uint8)
+    acc_row = (rng.random(d.pan_size) < 0.25).astype(np.uint8)
+    sel = rng.normal(0, 0.05, d.pan_size)
+    r1, r2 = sample_pairs(rng, p.pop_size, 200)
+    cuts = [0, 8192 * 2, 8192 * 3, p.core_size]
+    with make(p) as whole:
+        shards = [make(p, site_begin=a, site_end=b) for a, b in zip(cuts[:-1], cuts[1:])]
+        for s in [whole] + shards:
+            s.set_initial(core_row, acc_row)
+            s.set_selection(sel)
+            s.run_generations(0, p.n_gen)
+        full = whole.download_core()
+        got = np.concatenate([s.download_core() for s in shards], axis=1)
+        assert (got == full).all()
+        for s in shards:
+            assert (s.download_acc() == whole.download_acc()).all()
+            assert (s.parents() == whole.parents()).all()
+        cd, it, un = whole.pair_counts(r1, r2)
+        part = sum(s.pair_counts(r1, r2)[0].astype(np.int64) for s in shards)
+        assert (part == cd).all()
+        for s in shards:
+            s.close()
+
+
+def test_run_generations_equals_repeated_step():
+    p = small_params(n_gen=4, competition_strength=0.3, prop_positive=0.3)
+    d = pb.derive(p)
+    rng = np.random.default_rng(16)
+    core, acc = random_state(rng, p.pop_size, p.core_size, d.pan_size)
+    sel = rng.normal(0, 0.05, d.pan_size)
+    with make(p) as a, make(p) as b:
+        for s in (a, b):
+            s.upload(core, acc)
+            s.set_selection(sel)
+        a.run_generations(0, 4)
+        for g in range(4):
+            b.step(g)
+        assert (a.download_core() == b.download_core()).all()
+        assert (a.download_acc() == b.download_acc()).all()
+        # host-driven loop (reference call order, main.rs:435-464) gives the same result
+    with make(p) as c:
+        c.upload(core, acc)
+        c.set_selection(sel)
+        for g in range(4):
+            avg = c.average_distance()
+            parents = c.sample_indices(g, avg)
+            c.step_with_parents(g, parents)
+        with make(p) as a2:
+            a2.upload(core, acc)
+            a2.set_selection(sel)
+            a2.run_generations(0, 4)
+            assert (a2.download_core() == c.download_core()).all()
+            assert (a2.download_acc() == c.download_acc()).all()
+
+
+def test_state_required_and_error_codes():
+    p = small_params()
+    with make(p) as sim:
+        with pytest.raises(pb.PansimError) as e:
+            sim.step(0)
+        assert e.value.code == -5
+    with pytest.raises(pb.PansimError):
+        make(pb.Params(pop_size=1, core_size=100, pan_genes=10, core_genes=0))   # HR needs N >= 2
