@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- generations/sec of the Pansim Wright-Fisher step (and distances/sec
+of the pairwise pass) on B200, with the kernel roofline and the CPU baseline.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port)
+
+Workload (BASELINE.json configs[1], "cfg2"): pop_size 1000 x core 1.2 Mbp,
+6000 pan genes (4000 accessory), selection on (prop_positive 0.1), competition
+0.5, 100 000 sampled pairs. A step = one generation, main.rs:435-464. The
+per-generation distance pass of --print_dist (main.rs:502-504) is timed
+separately and reported under "distances".
+
+N > 1 (torchrun, one rank per GPU): weak scaling over columns -- every rank holds
+all individuals for its own 1.2 Mbp slice of an N x 1.2 Mbp alignment (accessory
+matrix replicated), so the job processes N cfg2-shaped slabs per step and `value`
+counts slab-generations per second. The generation step needs no collective; the
+distance pass all-reduces the per-pair partial core counts over NCCL.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG2 = dict(pop_size=1000, core_size=1_200_000, pan_genes=6000, core_genes=2000, n_gen=100,
+            max_distances=100_000, prop_positive=0.1, competition_strength=0.5, seed=0)
+PEAK_FALLBACK_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
+# dram__bytes_read.sum + dram__bytes_write.sum of core_step_kernel from the committed
+# ncu --set full capture (profiles/), per launch at this workload; None until captured
+NCU_CORE_STEP_DRAM_BYTES = None
+
+
+def selection_coefficients(rng, n, prop_positive, pos_lambda=10.0, neg_lambda=10.0):
+    """main.rs:289-319 (host side keeps this; numpy generator instead of StdRng)."""
+    s = np.zeros(n)
+    if prop_positive < 0:
+        return s
+    for i in range(n):
+        if rng.random() <= prop_positive:
+            s[i] = rng.exponential(1.0 / pos_lambda)
+        else:
+            v = rng.exponential(1.0 / neg_lambda)
+            while v > 1.0:
+                v = rng.exponential(1.0 / neg_lambda)
+            s[i] = -v
+    return s
+
+
+def sample_pairs(rng, n, p):
+    """main.rs:413-427"""
+    r1 = rng.integers(0, n, p).astype(np.uint32)
+    r2 = rng.integers(0, n - 1, p).astype(np.uint32)
+    r2 = (r2 + (r2 >= r1)).astype(np.uint32)
+    return r1, r2
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return PEAK_FALLBACK_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def cpu_baseline_sample(n_gen: int, with_distances: bool, pairs: int):
+    """Times the oracle port (CPU restatement of the reference, threads where the
+    reference uses rayon) on a bounded sample of the same workload."""
+    from oracle import binding as ob
+    threads = ob.lib().ora_max_threads()
+    kw = dict(CFG2)
+    kw["max_distances"] = pairs
+    p = ob.default_params(threads=threads, **kw)
+    t_gen, t_dist = ob.time_generations(p, n_gen, with_distances, use_tables=True)
+    return threads, t_gen, t_dist
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path. The Rust
+    crate cannot be built here (no cargo), so this is the oracle port."""
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    # bounded sample: each step = one cfg2 generation on the host cores (a few s each)
+    steps_run = min(steps, 3)
+    pairs = 2000
+    threads, t_gen, t_dist = cpu_baseline_sample(args.warmup if args.warmup < 1 else 1, False, pairs)  # warm page cache / omp
+    threads, t_gen, t_dist = cpu_baseline_sample(steps_run, True, pairs)
+    ms = 1e3 * t_gen / steps_run
+    val = steps_run / t_gen
+    pairs_per_s = steps_run * pairs / t_dist if t_dist > 0 else None
+    line = {
+        "impl": "reference", "metric": "generations/sec", "value": val, "unit": "generations/s",
+        "n_gpus": args.gpus, "steps": steps_run, "warmup": 1, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": "cfg2", "pop_size": 1000, "core_size": 1200000, "pan_genes": 6000,
+                   "selection": "prop_positive=0.1", "competition_strength": 0.5},
+        "cpu_baseline": {"value": val, "unit": "generations/s", "cores": threads, "kind": "port",
+                         "sample": f"{steps_run} full cfg2 generations (oracle C port of population.rs, OpenMP over rows/pairs "
+                                   f"where the reference uses rayon); distance pass on {pairs} pairs"},
+        "distances": {"value": pairs_per_s, "unit": "pairs/s"},
+        "e2e": {"value": val, "unit": "generations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-gens", type=int, default=2)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import pansim_b200 as pb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; pansim_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    W = max(3, args.warmup)
+    K = max(1, args.steps)
+    # this rank's slab: columns [rank*L, (rank+1)*L) of a (world*L)-site alignment
+    L = CFG2["core_size"]
+    align = 8192
+    Lslab = L if world == 1 else ((L + align - 1) // align) * align     # shard starts must be region aligned
+    total_L = L if world == 1 else Lslab * world
+    kw = dict(CFG2)
+    kw["core_size"] = total_L
+    # keep the per-site rates of cfg2: lambda scales with the alignment length (main.rs:275)
+    p = pb.Params(**kw)
+    d = pb.derive(p)
+    site_begin, site_end = (0, 0) if world == 1 else (rank * Lslab, min(total_L, (rank + 1) * Lslab))
+    sim = pb.Pansim.from_params(p, device=local_rank, site_begin=site_begin, site_end=site_end)
+    info = sim.info()
+
+    rng = np.random.default_rng(CFG2["seed"])           # identical on every rank
+    sel = selection_coefficients(rng, d.pan_size, p.prop_positive)
+    core_row = (1 << rng.integers(0, 4, total_L)).astype(np.uint8)
+    acc_row = (rng.random(d.pan_size) < d.avg_gene_freq_adj).astype(np.uint8)
+    r1, r2 = sample_pairs(rng, p.pop_size, p.max_distances)
+    sim.set_initial(core_row, acc_row)
+    sim.set_selection(sel)
+
+    # ---- warm-up (also diversifies the clonal start) -------------------------
+    gen = 0
+    sim.run_generations(gen, W)
+    gen += W
+    sim.pair_counts(r1, r2)
+
+    # ---- timed region: device-resident, K generations ------------------------
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    t0 = time.perf_counter()
+    sim.run_generations(gen, K)                 # K x (competition, fitness, parents, acc step, core step)
+    tm = sim.timing()                            # synchronises the context's stream
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    gen += K
+    dev_ms = max_over_ranks(float(tm.total_ms))
+    core_ms = float(tm.core_step_ms) / K
+    launches = int(tm.launches)
+
+    # ---- distance pass (device time of the kernels; pairs resident) ----------
+    n_dist = max(3, min(10, K))
+    pair_core_ms = pair_acc_ms = 0.0
+    barrier()
+    if world == 1:
+        for _ in range(n_dist):
+            sim.pair_counts(r1, r2)
+            t = sim.timing()
+            pair_core_ms += t.pair_core_ms
+            pair_acc_ms += t.pair_acc_ms
+            launches_dist = int(t.launches)
+    else:
+        d_cd = torch.zeros(p.max_distances, dtype=torch.int32, device="cuda")
+        d_in = torch.zeros_like(d_cd)
+        d_un = torch.zeros_like(d_cd)
+        for _ in range(n_dist):
+            sim.pair_counts_device(r1, r2, d_cd.data_ptr(), d_in.data_ptr(), d_un.data_ptr())
+            t = sim.timing()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dist.all_reduce(d_cd)                # partial core counts summed over column shards
+            e1.record()
+            torch.cuda.synchronize()
+            pair_core_ms += t.pair_core_ms + e0.elapsed_time(e1)
+            pair_acc_ms += t.pair_acc_ms
+            launches_dist = int(t.launches)
+    barrier()
+    pair_ms = max_over_ranks((pair_core_ms + pair_acc_ms) / n_dist)
+
+    # ---- end to end through the reference-facing API with HOST buffers --------
+    # per generation, exactly the calls main.rs:435-464 makes, vectors crossing the boundary
+    Ke = min(K, 50)
+    barrier()
+    t0 = time.perf_counter()
+    for g in range(Ke):
+        avg = sim.average_distance()                       # d2h N f64
+        parents = sim.sample_indices(gen + g, avg)         # h2d N f64, d2h N u32
+        sim.step_with_parents(gen + g, parents)            # h2d N u32
+    barrier()
+    e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0) / Ke)
+    gen += Ke
+    t0 = time.perf_counter()
+    for _ in range(3):
+        cd, it, un = sim.pair_counts(r1, r2)               # h2d 2 x P u32, d2h 3 x P u32
+    e2e_pair_ms = 1e3 * (time.perf_counter() - t0) / 3
+    clocks = sampler.stop() if sampler else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    N, P = p.pop_size, p.max_distances
+    core_bytes = 2 * N * ((info.local_sites + 3) // 4)              # read + write of the packed slab
+    achieved = core_bytes / (core_ms * 1e-3) / 1e9 if core_ms > 0 else 0.0
+    gen_bytes = int(info.algorithmic_bytes_per_generation)
+    ms_per_step = dev_ms / K
+    value = world * K / (dev_ms * 1e-3)
+    pair_bytes = int(info.algorithmic_bytes_per_pair)
+    pairs_per_s = world * P / (pair_ms * 1e-3)
+
+    line = {
+        "metric": "generations/sec", "value": value, "unit": "generations/s", "n_gpus": world,
+        "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u2/u1 packed integers (f64 fitness)", "data": "synthetic",
+        "config": {"workload": "cfg2", "pop_size": N, "core_size_per_gpu": int(info.local_sites),
+                   "pan_genes": p.pan_genes, "accessory_genes": d.pan_size, "selection": "prop_positive=0.1",
+                   "competition_strength": p.competition_strength, "pairs": P,
+                   "sharding": "columns; accessory replicated; no collective in the generation step",
+                   "l2": "inputs larger than L2 (2 x %.0f MB packed state, double buffered)" % (info.core_state_bytes / 1e6),
+                   "timing": "CUDA events on the library stream around K generations, max over ranks"},
+        "wall_ms_per_step": wall_ms / K,
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"kernel": "core_step_kernel<RNG> (fused gather + SNP + HR, TMA bulk pipeline)",
+                     "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": NCU_CORE_STEP_DRAM_BYTES, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": core_bytes, "launch_ms": core_ms,
+                     "step_algorithmic_bytes": gen_bytes,
+                     "step_frac": gen_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                     "kernel_share_of_step": core_ms / ms_per_step if ms_per_step > 0 else None,
+                     "breakdown_ms": {"select": tm.select_ms / K, "acc_step": tm.acc_step_ms / K, "core_step": core_ms}},
+        "distances": {"value": pairs_per_s, "unit": "pairs/s", "ms_per_pass": pair_ms, "pairs": P,
+                      "core_ms": pair_core_ms / n_dist, "acc_ms": pair_acc_ms / n_dist,
+                      "streaming_GBps": pair_bytes * P / (pair_ms * 1e-3) / 1e9,
+                      "streaming_frac_of_hbm_peak": pair_bytes * P / (pair_ms * 1e-3) / 1e9 / peak,
+                      "e2e_pairs_per_s": P / (e2e_pair_ms * 1e-3),
+                      "e2e_h2d_bytes": 8 * P, "e2e_d2h_bytes": 12 * P},
+        "e2e": {"value": world / (e2e_ms * 1e-3), "unit": "generations/s",
+                "h2d_bytes_per_step": 12 * N, "d2h_bytes_per_step": 12 * N, "ms_per_step": e2e_ms,
+                "path": "pansim_average_distance -> pansim_sample_indices -> pansim_step_with_parents, host vectors"},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        pairs_cpu = 2000
+        threads, t_gen, t_dist = cpu_baseline_sample(args.cpu_gens, True, pairs_cpu)
+        line["cpu_baseline"] = {
+            "value": args.cpu_gens / t_gen, "unit": "generations/s", "cores": threads, "kind": "port",
+            "sample": f"{args.cpu_gens} cfg2 generations from the clonal start (oracle C port, OpenMP where the "
+                      f"reference uses rayon); distance pass on {pairs_cpu} of the pairs",
+            "distances_pairs_per_s": args.cpu_gens * pairs_cpu / t_dist if t_dist > 0 else None}
+    print(json.dumps(line), flush=True)
+    sim.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -193,7 +193,7 @@ class Population:
     """Oracle population over a numpy [nrows x ncols] uint8 matrix (reference layout)."""
 
     def __init__(self, matrix: np.ndarray, core: bool, core_genes: int = 0):
-        self.m = np.ascontiguousarray(matrix, dtype=np.uint8)
+        self.m = np.array(matrix, dtype=np.uint8, order="C", copy=True)   # never alias the caller's buffer
         self.core = bool(core)
         self.core_genes = int(core_genes)
 

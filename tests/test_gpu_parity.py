@@ -478,4 +478,4 @@ def test_state_required_and_error_codes():
             sim.step(0)
         assert e.value.code == -5
     with pytest.raises(pb.PansimError):
-        make(pb.Params(pop_size=1, core_size=100, pan_genes=10, core_genes=0))   # HR needs N >= 2
+        make(pb.Params(pop_size=1, core_size=1000, pan_genes=10, core_genes=0, HR_rate=1.0))   # HR needs N >= 2
