@@ -109,6 +109,7 @@ struct pansim_ctx {
     uint32_t *d_inter = nullptr;
     uint32_t *d_rowK = nullptr, *d_gain_thr = nullptr;
     bool avgdist_valid = false;
+    bool fitness_valid = false;   // d_logfit / d_num_genes match the current accessory state
 
     HostPoissonTable tab_mut, tab_hr;
     uint32_t flip_thr[2] = {0, 0};
@@ -249,10 +250,12 @@ int check_device_flag(pansim_ctx *c, int code, const char *what)
 
 int launch_fitness(pansim_ctx *c)
 {
+    if (c->fitness_valid) return 0;
     const uint32_t *acc = c->acc[c->acc_cur];
-    fitness_kernel<<<div_up64(c->N, 64), 64, 0, c->stream>>>(acc, c->N, c->G, c->acc_stride_words, c->d_lw,
+    fitness_kernel<<<div_up64(c->N, FIT_WARPS), FIT_WARPS * 32, 0, c->stream>>>(acc, c->N, c->G, c->acc_stride_words, c->d_lw,
                                                              c->d_logfit, c->d_num_genes);
     LAUNCH_CHECK(c);
+    c->fitness_valid = true;
     return 0;
 }
 
@@ -265,7 +268,7 @@ int launch_competition(pansim_ctx *c)
     acc_inter_kernel<<<dim3(nb, nb), 256, 0, c->stream>>>(c->acc[c->acc_cur], c->N, c->acc_stride_words,
                                                           c->acc_words, c->d_inter);
     LAUNCH_CHECK(c);
-    avg_distance_kernel<<<div_up64(c->N, 128), 128, 0, c->stream>>>(c->d_inter, c->d_num_genes, c->N,
+    avg_distance_kernel<<<div_up64(c->N, AVG_WARPS), AVG_WARPS * 32, 0, c->stream>>>(c->d_inter, c->d_num_genes, c->N,
                                                                     c->cfg.core_genes, c->d_avgdist);
     LAUNCH_CHECK(c);
     c->avgdist_valid = true;
@@ -347,6 +350,7 @@ int launch_acc_step(pansim_ctx *c, uint32_t gen)
         CU(c, cudaMemsetAsync(c->d_dump_gain, 0, (size_t)c->N * c->acc_stride_words * 4, c->stream));
     }
     c->acc_cur ^= 1;
+    c->fitness_valid = false;
     return 0;
 }
 
@@ -517,7 +521,8 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
         const double rate_hr = cfg->hr_mean / (double)c->L;
         c->p_mut_site = -std::expm1(-rate_mut);
         c->p_hr_site = -std::expm1(-rate_hr);
-        build_poisson_table(rate_mut * BLOCK_SITES, c->tab_mut);
+        // SNP slots: Poisson(4/3 x mean); a slot is void with probability 1/4 (core_step.cuh)
+        build_poisson_table(rate_mut * BLOCK_SITES * (4.0 / 3.0), c->tab_mut);
         build_poisson_table(rate_hr * BLOCK_SITES, c->tab_hr);
         for (HostPoissonTable *t : {&c->tab_mut, &c->tab_hr}) {
             CU(c, cudaMalloc(&t->d_thr, t->size * sizeof(uint32_t)));
@@ -673,6 +678,7 @@ int pansim_upload_acc(pansim_ctx *c, const uint8_t *bytes)
     }
     c->has_acc = true;
     c->avgdist_valid = false;
+    c->fitness_valid = false;
     return 0;
 }
 
@@ -763,6 +769,7 @@ int pansim_set_selection(pansim_ctx *c, const double *s)
     for (uint32_t j = 0; j < c->G; j++) lw[j] = std::log(1.0 + s[j] * 1.0);   // population.rs:306 with x = 1
     CU(c, cudaMemcpyAsync(c->d_lw, lw.data(), (size_t)c->G * 8, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
+    c->fitness_valid = false;
     return 0;
 }
 
@@ -883,6 +890,7 @@ int pansim_next_generation(pansim_ctx *c, const uint32_t *parents)
         acc_gather_kernel<<<div_up64(total, 256), 256, 0, c->stream>>>(c->acc[c->acc_cur], c->acc[c->acc_cur ^ 1], c->d_parents, c->N, c->acc_stride_words);
         LAUNCH_CHECK(c);
         c->acc_cur ^= 1;
+        c->fitness_valid = false;
     }
     if (int rc = launch_core_step(c, 0, false)) return rc;
     timing_end(c);
@@ -970,6 +978,7 @@ int pansim_step_replay(pansim_ctx *c, const pansim_events *ev)
         }
     }
     // accessory: flips (population.rs:504-508) then HGT sets (:745 with value 1)
+    c->fitness_valid = false;
     if (nf) {
         acc_apply_flips_kernel<<<div_up64(nf, 256), 256, 0, c->stream>>>(c->acc[c->acc_cur], f_row, f_gene, nf, c->acc_stride_words);
         LAUNCH_CHECK(c);

@@ -17,30 +17,58 @@ namespace pansim {
 // sum bit for bit (population.rs:303-317). A present gene with lw_j = -inf
 // (s_j = -1) sets l_i := 0.0 (population.rs:312-318).
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(64) fitness_kernel(const uint32_t *acc, uint32_t n_rows, uint32_t n_genes,
-                                                     uint32_t stride_words, const double *lw,
-                                                     double *logfit, int32_t *num_genes)
+constexpr int FIT_WARPS = 4;
+constexpr int FIT_CHUNK_WORDS = 32;               // 1024 genes per compaction round
+
+__global__ void __launch_bounds__(FIT_WARPS * 32) fitness_kernel(const uint32_t *acc, uint32_t n_rows,
+                                                                 uint32_t n_genes, uint32_t stride_words,
+                                                                 const double *lw, double *logfit,
+                                                                 int32_t *num_genes)
 {
-    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    // Terms of absent genes are ln(1 + s*0) = +0.0: adding them never changes the
+    // running sum, so only present genes are added -- in increasing column order,
+    // by a single sequential f64 chain per row (bit-exact vs population.rs:303-317).
+    // The warp first compacts the present genes' lw values into shared memory so
+    // the chain is not exposed to load latency.
+    __shared__ double list[FIT_WARPS][FIT_CHUNK_WORDS * 32];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t row = blockIdx.x * FIT_WARPS + warp;
     if (row >= n_rows) return;
     const uint32_t *r = acc + (uint64_t)row * stride_words;
     const uint32_t n_words = (n_genes + 31u) / 32u;
+    double *mine = list[warp];
     double sum = 0.0;
     bool neg_inf = false;
     int32_t cnt = 0;
-    for (uint32_t w = 0; w < n_words; w++) {
-        uint32_t bits = r[w];
-        cnt += __popc(bits);
+    for (uint32_t w0 = 0; w0 < n_words; w0 += FIT_CHUNK_WORDS) {
+        const uint32_t w = w0 + lane;
+        uint32_t bits = (w < n_words) ? r[w] : 0u;
+        const uint32_t c = __popc(bits);
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += v;
+        }
+        uint32_t off = incl - c;
+        const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+        cnt += (int32_t)tot;
         while (bits) {
             const uint32_t b = __ffs(bits) - 1;
             bits &= bits - 1;
             const double v = lw[w * 32u + b];
             neg_inf |= (v == -INFINITY);
-            sum += v;
+            mine[off++] = v;
         }
+        __syncwarp();
+        for (uint32_t t = 0; t < tot; t++) sum += mine[t];      // every lane runs the same chain
+        __syncwarp();
     }
-    logfit[row] = (n_genes > 0) ? (neg_inf ? 0.0 : sum) : 0.0;
-    num_genes[row] = cnt;
+    neg_inf = __any_sync(0xffffffffu, neg_inf);
+    if (lane == 0) {
+        logfit[row] = (n_genes > 0) ? (neg_inf ? 0.0 : sum) : 0.0;
+        num_genes[row] = cnt;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -86,25 +114,39 @@ __global__ void __launch_bounds__(256) acc_inter_kernel(const uint32_t *acc, uin
 
 // K2b: mean Jaccard distance of individual i to all j != i, summed in j order
 // exactly like get_distance + the fold of population.rs:770-771.
-__global__ void __launch_bounds__(128) avg_distance_kernel(const uint32_t *inter, const int32_t *num_genes,
-                                                           uint32_t n_rows, uint32_t core_genes,
-                                                           double *avgdist)
+constexpr int AVG_WARPS = 4;
+
+__global__ void __launch_bounds__(AVG_WARPS * 32) avg_distance_kernel(const uint32_t *inter,
+                                                                      const int32_t *num_genes, uint32_t n_rows,
+                                                                      uint32_t core_genes, double *avgdist)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    // One warp per individual: the 32 lanes evaluate 32 distances in parallel (the
+    // f64 division is the expensive part), then the values are added one by one in
+    // j order -- the same sequential chain as the fold of population.rs:770.
+    // Lanes with j == i or j >= N contribute +0.0, which never changes the sum.
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t i = blockIdx.x * AVG_WARPS + (threadIdx.x >> 5);
     if (i >= n_rows) return;
     const double cg = (double)core_genes;
     const uint32_t ki = (uint32_t)num_genes[i];
+    const uint32_t *irow = inter + (uint64_t)i * n_rows;
     double sum = 0.0;
-    for (uint32_t j = 0; j < n_rows; j++) {
-        if (j == i) continue;
-        const uint32_t in = inter[(uint64_t)j * n_rows + i];          // symmetric: coalesced read
-        const uint32_t un = ki + (uint32_t)num_genes[j] - in;
-        const double d = 1.0 - (((double)in + 0.0 + cg) / ((double)un + 0.0 + cg));   // :144-145
-        sum += d;
+    for (uint32_t j0 = 0; j0 < n_rows; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        double d = 0.0;
+        if (j < n_rows && j != i) {
+            const uint32_t in = irow[j];
+            const uint32_t un = ki + (uint32_t)num_genes[j] - in;
+            d = 1.0 - (((double)in + 0.0 + cg) / ((double)un + 0.0 + cg));   // :144-145
+        }
+#pragma unroll
+        for (int t = 0; t < 32; t++) sum += __shfl_sync(0xffffffffu, d, t);
     }
-    double fd = sum / (double)(n_rows - 1u);
-    if (fd == 0.0) fd = DBL_MIN;                                      // :774-776
-    avgdist[i] = fd;
+    if (lane == 0) {
+        double fd = sum / (double)(n_rows - 1u);
+        if (fd == 0.0) fd = DBL_MIN;                                  // :774-776
+        avgdist[i] = fd;
+    }
 }
 
 // ---------------------------------------------------------------------------
