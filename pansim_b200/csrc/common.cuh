@@ -121,22 +121,19 @@ struct BitStream {
 
 // Poisson by CDF inversion from one 32-bit uniform: k = #{j : T[j] <= u} with
 // T[j] = round(CDF(j) * 2^32) (built on the host in f64), padded with
-// 0xFFFFFFFF to a power of two. A mean above the table range is drawn as a sum
-// of n_sub independent Poisson(mean / n_sub) (exact by additivity).
-struct PoissonTable {
-    const uint32_t *thr;   // shared-memory pointer inside kernels
-    uint32_t size;         // power of two
-    uint32_t n_sub;        // 0 = rate is zero
-    uint32_t kmax;
-};
+// 0xFFFFFFFF. A 256-entry guide table indexed by the top byte of u gives the
+// count of thresholds <= (u & 0xFF000000); a short forward scan finishes. A mean
+// above the table range is drawn as a sum of n_sub independent Poisson(mean /
+// n_sub) (exact by additivity).
+// Shared-memory image of one table: [256 x u32 guide][size x u32 thresholds]
+constexpr uint32_t GUIDE_ENTRIES = 256;
 
-__device__ __forceinline__ uint32_t poisson_from_uniform(const uint32_t *thr, uint32_t size,
-                                                         uint32_t kmax, uint32_t u)
+__device__ __forceinline__ uint32_t poisson_from_uniform(const uint32_t *tab, uint32_t kmax, uint32_t u)
 {
-    uint32_t pos = 0;
-    for (uint32_t step = size >> 1; step > 0; step >>= 1)
-        if (thr[pos + step - 1] <= u) pos += step;
-    return pos < kmax ? pos : kmax;
+    uint32_t k = tab[u >> 24];
+    const uint32_t *thr = tab + GUIDE_ENTRIES;
+    while (k < kmax && thr[k] <= u) k++;
+    return k;
 }
 
 // ---------------------------------------------------------------------------

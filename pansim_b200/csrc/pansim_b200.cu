@@ -59,6 +59,20 @@ void build_poisson_table(double mean, HostPoissonTable &t)
     t.thr.resize(size, 0xFFFFFFFFu);
 }
 
+// device image: [256 guide entries][size thresholds]; guide[b] = #{j : T[j] <= b << 24}
+std::vector<uint32_t> poisson_table_image(const HostPoissonTable &t)
+{
+    std::vector<uint32_t> img(GUIDE_ENTRIES + t.size);
+    for (uint32_t b = 0; b < GUIDE_ENTRIES; b++) {
+        const uint32_t u = b << 24;
+        uint32_t k = 0;
+        while (k < t.kmax && t.thr[k] <= u) k++;
+        img[b] = k;
+    }
+    for (uint32_t j = 0; j < t.size; j++) img[GUIDE_ENTRIES + j] = t.thr[j];
+    return img;
+}
+
 struct EventPool {
     std::vector<cudaEvent_t> ev;
     size_t used = 0;
@@ -367,8 +381,8 @@ void fill_core_args(pansim_ctx *c, CoreStepArgs &a, uint32_t gen)
     a.site_limit = c->site_end;
     a.key = make_uint2((uint32_t)c->cfg.seed, (uint32_t)(c->cfg.seed >> 32));
     a.gen = gen;
-    a.mut_thr = c->tab_mut.d_thr; a.mut_size = c->tab_mut.size; a.mut_nsub = c->tab_mut.nsub; a.mut_kmax = c->tab_mut.kmax;
-    a.hr_thr = c->tab_hr.d_thr; a.hr_size = c->tab_hr.size; a.hr_nsub = c->tab_hr.nsub; a.hr_kmax = c->tab_hr.kmax;
+    a.mut_tab = c->tab_mut.d_thr; a.mut_size = c->tab_mut.size; a.mut_nsub = c->tab_mut.nsub; a.mut_kmax = c->tab_mut.kmax;
+    a.hr_tab = c->tab_hr.d_thr; a.hr_size = c->tab_hr.size; a.hr_nsub = c->tab_hr.nsub; a.hr_kmax = c->tab_hr.kmax;
     a.dump_counters = c->d_dump_counters;
     a.dump_cap = c->dump_cap;
     a.d_mut_row = c->d_mut_row; a.d_mut_site = c->d_mut_site; a.d_mut_seq = c->d_mut_seq; a.d_mut_allele = c->d_mut_allele;
@@ -521,12 +535,12 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
         const double rate_hr = cfg->hr_mean / (double)c->L;
         c->p_mut_site = -std::expm1(-rate_mut);
         c->p_hr_site = -std::expm1(-rate_hr);
-        // SNP slots: Poisson(4/3 x mean); a slot is void with probability 1/4 (core_step.cuh)
-        build_poisson_table(rate_mut * BLOCK_SITES * (4.0 / 3.0), c->tab_mut);
+        build_poisson_table(rate_mut * BLOCK_SITES, c->tab_mut);
         build_poisson_table(rate_hr * BLOCK_SITES, c->tab_hr);
         for (HostPoissonTable *t : {&c->tab_mut, &c->tab_hr}) {
-            CU(c, cudaMalloc(&t->d_thr, t->size * sizeof(uint32_t)));
-            CU(c, cudaMemcpy(t->d_thr, t->thr.data(), t->size * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            const std::vector<uint32_t> img = poisson_table_image(*t);
+            CU(c, cudaMalloc(&t->d_thr, img.size() * sizeof(uint32_t)));
+            CU(c, cudaMemcpy(t->d_thr, img.data(), img.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         }
         for (uint32_t k = 0; k < cfg->n_compartments; k++) {
             const double sites = (double)(cfg->comp_hi[k] - cfg->comp_lo[k]);
