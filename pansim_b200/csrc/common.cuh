@@ -1,5 +1,5 @@
 // common.cuh -- device-side building blocks shared by all kernels:
-// Philox4x32-10, a bit-stream reader over it, Poisson-by-inversion tables,
+// Philox4x32-10, Poisson-by-inversion tables,
 // and the sm_100a PTX wrappers (mbarrier, cp.async.bulk = TMA 1-D bulk copies).
 #pragma once
 #include <cstdint>
@@ -65,74 +65,25 @@ __host__ __device__ __forceinline__ uint4 make_ctr(uint32_t block, uint32_t row,
     return make_uint4(block, row, gen, stream << 16);
 }
 
-// 128-bit shift register over successive Philox outputs.
-struct BitStream {
-    uint32_t r0, r1, r2, r3;
-    int left;
-    uint4 ctr;
-    uint2 key;
-
-    __device__ __forceinline__ BitStream(uint4 c, uint2 k) : left(0), ctr(c), key(k) {}
-
-    __device__ __forceinline__ void refill()
-    {
-        const uint4 o = philox4x32_10(ctr, key);
-        ctr.w += 1;
-        r0 = o.x; r1 = o.y; r2 = o.z; r3 = o.w;
-        left = 128;
-    }
-    // n in [1,31]
-    __device__ __forceinline__ uint32_t take(int n)
-    {
-        if (left < n) refill();
-        const uint32_t v = r0 & ((1u << n) - 1u);
-        r0 = __funnelshift_r(r0, r1, n);
-        r1 = __funnelshift_r(r1, r2, n);
-        r2 = __funnelshift_r(r2, r3, n);
-        r3 >>= n;
-        left -= n;
-        return v;
-    }
-    __device__ __forceinline__ uint32_t take32()
-    {
-        if (left < 32) refill();
-        const uint32_t v = r0;
-        r0 = r1; r1 = r2; r2 = r3; r3 = 0;
-        left -= 32;
-        return v;
-    }
-    // exactly uniform on [0,n): Lemire multiply-shift with rejection
-    __device__ __forceinline__ uint32_t below(uint32_t n)
-    {
-        uint32_t x = take32();
-        uint64_t m = (uint64_t)x * n;
-        uint32_t l = (uint32_t)m;
-        if (l < n) {
-            const uint32_t t = (0u - n) % n;
-            while (l < t) {
-                x = take32();
-                m = (uint64_t)x * n;
-                l = (uint32_t)m;
-            }
-        }
-        return (uint32_t)(m >> 32);
-    }
-};
-
 // Poisson by CDF inversion from one 32-bit uniform: k = #{j : T[j] <= u} with
 // T[j] = round(CDF(j) * 2^32) (built on the host in f64), padded with
-// 0xFFFFFFFF. A 256-entry guide table indexed by the top byte of u gives the
-// count of thresholds <= (u & 0xFF000000); a short forward scan finishes. A mean
-// above the table range is drawn as a sum of n_sub independent Poisson(mean /
-// n_sub) (exact by additivity).
+// 0xFFFFFFFF. A 256-entry guide table indexed by the top 8 bits of u holds
+// 2*k0 + impure, where k0 = #{j : T[j] <= (u with the low 24 bits cleared)} and
+// `impure` says a threshold falls inside the bin (then a short forward scan
+// finishes). A mean above the table range is drawn as a sum of n_sub
+// independent Poisson(mean / n_sub) (exact by additivity).
 // Shared-memory image of one table: [256 x u32 guide][size x u32 thresholds]
 constexpr uint32_t GUIDE_ENTRIES = 256;
+constexpr uint32_t GUIDE_SHIFT = 24;
 
 __device__ __forceinline__ uint32_t poisson_from_uniform(const uint32_t *tab, uint32_t kmax, uint32_t u)
 {
-    uint32_t k = tab[u >> 24];
-    const uint32_t *thr = tab + GUIDE_ENTRIES;
-    while (k < kmax && thr[k] <= u) k++;
+    const uint32_t g = tab[u >> GUIDE_SHIFT];
+    uint32_t k = g >> 1;
+    if (g & 1u) {
+        const uint32_t *thr = tab + GUIDE_ENTRIES;
+        while (k < kmax && thr[k] <= u) k++;
+    }
     return k;
 }
 

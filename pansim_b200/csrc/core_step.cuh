@@ -47,11 +47,10 @@
 namespace pansim {
 
 constexpr int CS_WARPS = 8;
-constexpr int CS_STAGES = 3;
+constexpr int CS_STAGES = 2;
 constexpr int CS_THREADS = CS_WARPS * 32;
-constexpr int HRQ_CAP = 64;                       // HR queue entries per warp
+constexpr int HRQ_CAP = 32;                       // HR queue entries per warp
 constexpr uint32_t POISSON_TABLE_MAX = 1024;
-constexpr uint32_t SNP_GROUP = 20;                // SNP events per pair of Philox calls
 
 struct CoreStepArgs {
     const uint8_t *old_state;
@@ -87,10 +86,10 @@ static inline size_t core_step_smem_bytes(uint32_t mut_size, uint32_t hr_size)
 // Poisson count of a (block,row) stream. Draw 0 uses `first` (word x of Philox
 // call 0); a mean above the table range adds draws from dedicated count calls
 // (exact by additivity).
-__device__ __forceinline__ uint32_t stream_count(uint4 ctr, uint2 key, uint32_t first, const uint32_t *tab,
-                                                 uint32_t nsub, uint32_t kmax)
+__device__ __noinline__ uint32_t stream_count_extra(uint4 ctr, uint2 key, const uint32_t *tab, uint32_t nsub,
+                                                    uint32_t kmax)
 {
-    uint32_t k = poisson_from_uniform(tab, kmax, first);
+    uint32_t k = 0;
     for (uint32_t s = 1; s < nsub; s++) {
         uint4 c = ctr;
         c.w |= 0x8000u | ((s - 1) >> 2);
@@ -102,35 +101,50 @@ __device__ __forceinline__ uint32_t stream_count(uint4 ctr, uint2 key, uint32_t 
     return k;
 }
 
-// next base-3 digit of the 64-bit fraction hi:lo (digit = floor(3F), F <- frac(3F))
-__device__ __forceinline__ uint32_t next_trit(uint32_t &lo, uint32_t &hi)
+__device__ __forceinline__ uint32_t stream_count(uint4 ctr, uint2 key, uint32_t first, const uint32_t *tab,
+                                                 uint32_t nsub, uint32_t kmax)
 {
-    const uint64_t a = (uint64_t)lo * 3u;
-    const uint64_t b = (uint64_t)hi * 3u + (uint32_t)(a >> 32);
-    lo = (uint32_t)a;
-    hi = (uint32_t)b;
-    return (uint32_t)(b >> 32);
+    uint32_t k = poisson_from_uniform(tab, kmax, first);
+    if (nsub > 1) k += stream_count_extra(ctr, key, tab, nsub, kmax);
+    return k;
 }
 
-// SNP stream layout of (block,row), group g = events 20g .. 20g+19:
-//   call 2g   : x = Poisson count word (g == 0 only), y:z = allele digit source, w = positions 0..3
-//   call 2g+1 : x,y,z,w = positions 4..19
-struct SnpGroup {
-    uint32_t tlo, thi;
-    uint32_t p[5];
-};
+// SNP stream layout of (block,row); group g = events 28g .. 28g+27, calls 3g..3g+2:
+//   call 3g   : x = Poisson count word (g == 0 only), y = digit bytes, z = reserve digit bytes,
+//               w = positions 0..3
+//   call 3g+1 : x,y,z,w = positions 4..19
+//   call 3g+2 : x = digit bytes, y = reserve digit bytes, z,w = positions 20..27
+// Part 0 = events 0..19, part 1 = events 20..27. Part 1 is only generated when
+// some lane of the warp needs it, so the common case costs two Philox calls.
+//
+// Alleles: one digit byte v serves five consecutive events as its base-3 digits
+// (event i of the chunk gets floor(v / 3^i) mod 3). v must be uniform on
+// [0,243): a byte >= 243 is replaced by the reserve byte, and if that is >= 243
+// too (p = 0.26 %) by a dedicated Philox word scaled to [0,243) (bias 6e-8).
+constexpr uint32_t SNP_PART0 = 20, SNP_GROUP = 28;
 
-__device__ __forceinline__ SnpGroup snp_group(uint4 ctr, uint2 key, uint32_t g, const uint4 *first)
+__device__ __forceinline__ uint4 snp_call(uint4 ctr, uint2 key, uint32_t call)
 {
-    uint4 c0 = ctr, c1 = ctr;
-    c0.w += 2u * g;
-    c1.w += 2u * g + 1u;
-    const uint4 a = first ? *first : philox4x32_10(c0, key);
-    const uint4 b = philox4x32_10(c1, key);
-    SnpGroup r;
-    r.tlo = a.y; r.thi = a.z;
-    r.p[0] = a.w; r.p[1] = b.x; r.p[2] = b.y; r.p[3] = b.z; r.p[4] = b.w;
-    return r;
+    ctr.w += call;
+    return philox4x32_10(ctr, key);
+}
+
+__device__ __noinline__ uint32_t digit_byte_fallback(uint4 ctr, uint2 key, uint32_t tag)
+{
+    ctr.w |= 0x2000u;
+    ctr.x ^= 0x5bd1e995u * (tag + 1u);
+    return __umulhi(philox4x32_10(ctr, key).x, 243u);
+}
+
+__device__ __forceinline__ uint32_t digit_byte(uint32_t tp, uint32_t tr, uint32_t c, uint4 ctr, uint2 key,
+                                               uint32_t tag)
+{
+    uint32_t v = (tp >> (8u * c)) & 255u;
+    if (v >= 243u) {
+        v = (tr >> (8u * c)) & 255u;
+        if (v >= 243u) v = digit_byte_fallback(ctr, key, tag);
+    }
+    return v;
 }
 
 template <bool DUMP>
@@ -140,9 +154,11 @@ struct MutApply {
     uint64_t reg_site0;
     const CoreStepArgs *a;
 
-    __device__ __forceinline__ void slot(uint32_t pos, uint32_t digit, uint32_t idx) const
+    __device__ __forceinline__ void slot(uint32_t pos, uint32_t digit, uint32_t idx, uint32_t kk) const
     {
-        if (idx < k && pos < pos_lim) {
+        // positions beyond the end of a ragged last region are written too and
+        // cleared again by the padding fix-up at the end of the item
+        if (idx < kk) {
             const uint32_t addr = lane_base + ((pos & 0xF0u) << 3);      // word (pos>>4)*32 + lane
             const uint32_t one = 1u << ((pos & 15u) * 2u);
             uint32_t w;
@@ -150,43 +166,60 @@ struct MutApply {
             w = (w & ~(one * 3u)) | (one * digit + one);                 // code = digit + 1 in {C,G,T}
             asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(w) : "memory");
             if (DUMP) {
-                const uint32_t s = atomicAdd(&a->dump_counters[0], 1u);
-                if (s < a->dump_cap) {
-                    const uint32_t sir = (((pos >> 4) << 5) + lane) * 16u + (pos & 15u);
-                    a->d_mut_row[s] = row;
-                    a->d_mut_site[s] = (uint32_t)(reg_site0 + sir);
-                    a->d_mut_seq[s] = idx;
-                    a->d_mut_allele[s] = (uint8_t)(2u << digit);
+                if (pos < pos_lim) {
+                    const uint32_t s = atomicAdd(&a->dump_counters[0], 1u);
+                    if (s < a->dump_cap) {
+                        const uint32_t sir = (((pos >> 4) << 5) + lane) * 16u + (pos & 15u);
+                        a->d_mut_row[s] = row;
+                        a->d_mut_site[s] = (uint32_t)(reg_site0 + sir);
+                        a->d_mut_seq[s] = idx;
+                        a->d_mut_allele[s] = (uint8_t)(2u << digit);
+                    }
                 }
             }
         }
     }
 
-    __device__ __forceinline__ void group(SnpGroup g, uint32_t base) const
+    // apply the first n_ev events of one part (positions packed in p0..p4, 4 per word);
+    // `base` = index of its first event. Loop over chunks of 5 events = one digit byte.
+    __device__ __forceinline__ void part(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, uint32_t p4,
+                                         uint32_t n_ev, uint32_t tp, uint32_t tr, uint32_t base, uint4 ctr,
+                                         uint2 key, uint32_t tag0) const
     {
+        const uint32_t kk = min(k, base + n_ev);           // events of this part that exist for this lane
+#pragma unroll 1
+        for (uint32_t c = 0; 5u * c < n_ev; c++) {
+            uint32_t v = digit_byte(tp, tr, c, ctr, key, tag0 + c);
 #pragma unroll
-        for (int j = 0; j < 5; j++) {
-#pragma unroll
-            for (int b = 0; b < 4; b++) {
-                const uint32_t pos = (g.p[j] >> (8 * b)) & 255u;
-                const uint32_t digit = next_trit(g.tlo, g.thi);
-                slot(pos, digit, base + 4 * j + b);
+            for (int i = 0; i < 5; i++) {
+                const uint32_t q = (v * 171u) >> 9;        // v / 3 for v < 256
+                const uint32_t digit = v - 3u * q;
+                v = q;
+                const uint32_t pos = i < 4 ? ((p0 >> (8 * i)) & 255u) : (p1 & 255u);
+                slot(pos, digit, base + 5u * c + i, kk);
             }
+            // advance the position string by 5 bytes
+            p0 = __funnelshift_r(p1, p2, 8);
+            p1 = __funnelshift_r(p2, p3, 8);
+            p2 = __funnelshift_r(p3, p4, 8);
+            p3 = p4 >> 8;
+            p4 = 0;
         }
     }
 };
 
-// index (0..19) of the last of the first `n` position bytes equal to `pos`, or -1
-__device__ __forceinline__ int find_last_pos(const SnpGroup &g, uint32_t pos, uint32_t n)
+// index (within the part) of the last of its first `n` position bytes equal to `pos`, or -1
+template <int NW>
+__device__ __forceinline__ int find_last_pos(const uint32_t (&p)[NW], uint32_t pos, int n)
 {
     const uint32_t rep = pos * 0x01010101u;
     int last = -1;
 #pragma unroll
-    for (int j = 0; j < 5; j++) {
-        const uint32_t t = g.p[j] ^ rep;
+    for (int j = 0; j < NW; j++) {
+        const uint32_t t = p[j] ^ rep;
         // exact per-byte zero test: bit 7 of each byte of z set iff that byte of t is 0
         uint32_t z = ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u;
-        const int nv = (int)n - 4 * j;                    // valid bytes in this word
+        const int nv = n - 4 * j;                         // valid bytes in this word
         if (nv < 4) z &= nv <= 0 ? 0u : ((1u << (8 * nv)) - 1u);
         if (z) last = 4 * j + ((31 - __clz(z)) >> 3);
     }
@@ -199,20 +232,37 @@ __device__ __forceinline__ uint32_t snp_probe(uint32_t block, uint32_t d, uint32
                                               const uint32_t *tab_mut)
 {
     const uint4 ctr = make_ctr(block, d, a.gen, STREAM_CORE_MUT);
-    const uint4 g0 = philox4x32_10(ctr, a.key);
-    const uint32_t kd = stream_count(ctr, a.key, g0.x, tab_mut, a.mut_nsub, a.mut_kmax);
-    SnpGroup g = snp_group(ctr, a.key, 0, &g0);
-    int last = find_last_pos(g, pos, kd);
-    uint32_t lo = g.tlo, hi = g.thi;
-    for (uint32_t grp = 1; grp * SNP_GROUP < kd; grp++) {          // rare: more than 20 events
-        const SnpGroup h = snp_group(ctr, a.key, grp, nullptr);
-        const int l2 = find_last_pos(h, pos, kd - grp * SNP_GROUP);
-        if (l2 >= 0) { last = l2; lo = h.tlo; hi = h.thi; }
+    uint4 c0 = snp_call(ctr, a.key, 0);
+    const uint32_t kd = stream_count(ctr, a.key, c0.x, tab_mut, a.mut_nsub, a.mut_kmax);
+    int last = -1;
+    uint32_t tp = 0, tr = 0, tag = 0;
+#pragma unroll 1
+    for (uint32_t base = 0, g = 0; base < kd; base += SNP_GROUP, g++) {
+        if (g) c0 = snp_call(ctr, a.key, 3u * g);
+        const uint4 c1 = snp_call(ctr, a.key, 3u * g + 1u);
+        const uint32_t p0[5] = {c0.w, c1.x, c1.y, c1.z, c1.w};
+        const int l0 = find_last_pos<5>(p0, pos, (int)(kd - base));
+        if (l0 >= 0) { last = l0; tp = c0.y; tr = c0.z; tag = g * 8u; }
+        if (kd > base + SNP_PART0) {
+            const uint4 c2 = snp_call(ctr, a.key, 3u * g + 2u);
+            const uint32_t p1[2] = {c2.z, c2.w};
+            const int l1 = find_last_pos<2>(p1, pos, (int)(kd - base - SNP_PART0));
+            if (l1 >= 0) { last = l1; tp = c2.x; tr = c2.y; tag = g * 8u + 4u; }
+        }
     }
     if (last < 0) return 0u;
-    uint32_t digit = 0;
-    for (int i = 0; i <= last; i++) digit = next_trit(lo, hi);
-    return digit + 1u;
+    const uint32_t c = (uint32_t)last / 5u, i = (uint32_t)last % 5u;
+    uint32_t v = digit_byte(tp, tr, c, ctr, a.key, tag + c);
+    for (uint32_t t = 0; t < i; t++) v = (v * 171u) >> 9;
+    return v - 3u * ((v * 171u) >> 9) + 1u;
+}
+
+__device__ __noinline__ uint32_t hr_retry_word(uint4 c, uint2 key, uint32_t e)
+{
+    c.w |= 0x4000u;
+    c.y ^= 0x80000000u;
+    c.x += e * 0x9E3779B9u;
+    return philox4x32_10(c, key).x;
 }
 
 // HR event e of a (block,row) stream: position and donor. Call c = e/2 of the
@@ -230,19 +280,13 @@ __device__ __forceinline__ void hr_event(const uint4 g, bool first_call, uint32_
     const uint32_t l = (uint32_t)m;
     if (l < n_other) {
         const uint32_t t = (0u - n_other) % n_other;
-        if (l < t) {
-            uint4 c = hctr;
-            c.w |= 0x4000u;
-            c.y ^= 0x80000000u;
-            c.x += e * 0x9E3779B9u;
-            m = (uint64_t)philox4x32_10(c, key).x * n_other;
-        }
+        if (l < t) m = (uint64_t)hr_retry_word(hctr, key, e) * n_other;
     }
     donor_raw = (uint32_t)(m >> 32);
 }
 
 template <bool RNG, bool DUMP>
-__global__ void __launch_bounds__(CS_THREADS, 3) core_step_kernel(const CoreStepArgs a)
+__global__ void __launch_bounds__(CS_THREADS, 4) core_step_kernel(const CoreStepArgs a)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint64_t *bars_all = reinterpret_cast<uint64_t *>(smem_raw + (size_t)CS_WARPS * CS_STAGES * REGION_BYTES);
@@ -256,7 +300,9 @@ __global__ void __launch_bounds__(CS_THREADS, 3) core_step_kernel(const CoreStep
     uint2 *hrq = hrq_all + warp * HRQ_CAP;
 
     if (RNG) {
+#pragma unroll 1
         for (uint32_t i = threadIdx.x; i < GUIDE_ENTRIES + a.mut_size; i += CS_THREADS) tab_mut[i] = a.mut_tab[i];
+#pragma unroll 1
         for (uint32_t i = threadIdx.x; i < GUIDE_ENTRIES + a.hr_size; i += CS_THREADS) tab_hr[i] = a.hr_tab[i];
     }
     if (lane == 0) {
@@ -273,20 +319,23 @@ __global__ void __launch_bounds__(CS_THREADS, 3) core_step_kernel(const CoreStep
     // item t = gw + j*n_warps  ->  (row, reg), advanced incrementally
     const uint32_t d_row = n_warps / a.n_regions, d_reg = n_warps % a.n_regions;
 
-    // the load side runs CS_STAGES-1 items ahead with its own (row, reg) cursor
-    uint32_t l_row = gw / a.n_regions, l_reg = gw % a.n_regions;
-    auto issue_load = [&](uint32_t j) {      // lane 0 only; must be called for j = 0,1,2,... in order
-        const uint8_t *src = a.old_state + (uint64_t)a.parents[l_row] * a.row_stride + (uint64_t)l_reg * REGION_BYTES;
-        const uint32_t s = j % CS_STAGES;
-        mbar_arrive_expect_tx(&bars[s], REGION_BYTES);
-        bulk_g2s(stages + s * REGION_BYTES, src, REGION_BYTES, &bars[s]);
-        l_row += d_row; l_reg += d_reg;
-        if (l_reg >= a.n_regions) { l_reg -= a.n_regions; l_row++; }
-    };
+    // the load side runs CS_STAGES-1 items ahead with its own (row, reg) cursor (lane 0 only)
+    uint32_t l_row = gw / a.n_regions, l_reg = gw % a.n_regions, l_j = 0;
+#define PANSIM_ISSUE_LOAD()                                                                                  \
+    do {                                                                                                     \
+        const uint8_t *src_ = a.old_state + (uint64_t)a.parents[l_row] * a.row_stride +                      \
+                              (uint64_t)l_reg * REGION_BYTES;                                                \
+        const uint32_t s_ = l_j % CS_STAGES;                                                                 \
+        mbar_arrive_expect_tx(&bars[s_], REGION_BYTES);                                                      \
+        bulk_g2s(stages + s_ * REGION_BYTES, src_, REGION_BYTES, &bars[s_]);                                 \
+        l_j++; l_row += d_row; l_reg += d_reg;                                                               \
+        if (l_reg >= a.n_regions) { l_reg -= a.n_regions; l_row++; }                                         \
+    } while (0)
 
     if (lane == 0) {
         const uint32_t pre = n_my < (uint32_t)(CS_STAGES - 1) ? n_my : (uint32_t)(CS_STAGES - 1);
-        for (uint32_t j = 0; j < pre; j++) issue_load(j);
+#pragma unroll 1
+        for (uint32_t jj = 0; jj < pre; jj++) PANSIM_ISSUE_LOAD();
     }
 
     uint32_t row = gw / a.n_regions, reg = gw % a.n_regions;
@@ -300,24 +349,24 @@ __global__ void __launch_bounds__(CS_THREADS, 3) core_step_kernel(const CoreStep
         const uint64_t reg_site0 = (uint64_t)greg * REGION_SITES;
         // positions >= pos_lim fall beyond the end of the alignment (ragged last region):
         // site-in-region = (pos>>4)*512 + lane*16 + (pos&15) < lim  <=>  pos < pos_lim
-        uint32_t pos_lim = 256u;
+        uint32_t pos_lim = 256u, pos_lim_any = 256u;       // pos_lim_any < 256: ragged region (warp-uniform)
         {
             const uint64_t rem = a.site_limit - reg_site0;
             if (rem < REGION_SITES) {
+                pos_lim_any = 0u;
                 const int q = (int)rem - (int)(lane * 16u);
                 pos_lim = q <= 0 ? 0u : (uint32_t)(q >> 9) * 16u + min(16u, (uint32_t)(q & 511));
             }
         }
         const uint4 mctr = make_ctr(block_id, row, a.gen, STREAM_CORE_MUT);
         const uint4 hctr = make_ctr(block_id, row, a.gen, STREAM_CORE_HR);
-        uint4 hg0 = make_uint4(0, 0, 0, 0);
+        uint4 hg0 = make_uint4(0, 0, 0, 0), mc0 = make_uint4(0, 0, 0, 0), mc1 = make_uint4(0, 0, 0, 0);
         uint32_t k = 0, kh = 0;
-        SnpGroup mg;
         if (RNG) {
             if (a.mut_nsub) {
-                const uint4 mg0 = philox4x32_10(mctr, a.key);
-                k = stream_count(mctr, a.key, mg0.x, tab_mut, a.mut_nsub, a.mut_kmax);
-                mg = snp_group(mctr, a.key, 0, &mg0);
+                mc0 = snp_call(mctr, a.key, 0);
+                mc1 = snp_call(mctr, a.key, 1);
+                k = stream_count(mctr, a.key, mc0.x, tab_mut, a.mut_nsub, a.mut_kmax);
             }
             if (a.hr_nsub) {
                 hg0 = philox4x32_10(hctr, a.key);
@@ -331,9 +380,20 @@ __global__ void __launch_bounds__(CS_THREADS, 3) core_step_kernel(const CoreStep
             // ---- SNP mutation (population.rs:512-539) ----
             if (a.mut_nsub) {
                 const MutApply<DUMP> f{smem_u32(sw) + lane * 4u, lane, pos_lim, k, row, reg_site0, &a};
-                f.group(mg, 0u);
-                for (uint32_t grp = 1; grp * SNP_GROUP < k; grp++)       // rare: more than 20 events
-                    f.group(snp_group(mctr, a.key, grp, nullptr), grp * SNP_GROUP);
+                const uint32_t kw = __reduce_max_sync(0xffffffffu, k);      // warp-uniform trip counts
+#pragma unroll 1
+                for (uint32_t base = 0, g = 0; base < kw; base += SNP_GROUP, g++) {
+                    if (g) {
+                        mc0 = snp_call(mctr, a.key, 3u * g);
+                        mc1 = snp_call(mctr, a.key, 3u * g + 1u);
+                    }
+                    f.part(mc0.w, mc1.x, mc1.y, mc1.z, mc1.w, SNP_PART0, mc0.y, mc0.z, base, mctr, a.key, g * 8u);
+                    if (kw > base + SNP_PART0) {
+                        const uint4 mc2 = snp_call(mctr, a.key, 3u * g + 2u);
+                        f.part(mc2.z, mc2.w, 0u, 0u, 0u, SNP_GROUP - SNP_PART0, mc2.x, mc2.y, base + SNP_PART0,
+                               mctr, a.key, g * 8u + 4u);
+                    }
+                }
             }
 
             // ---- homologous recombination (population.rs:544-751, core) ----
@@ -423,6 +483,16 @@ __global__ void __launch_bounds__(CS_THREADS, 3) core_step_kernel(const CoreStep
                     __syncwarp();
                 }
             }
+            // ragged last region: clear whatever events wrote beyond the end of the alignment
+            if (pos_lim_any < 256u) {
+                const uint32_t lim = (uint32_t)(a.site_limit - reg_site0);
+#pragma unroll 1
+                for (uint32_t kk = 0; kk < WORDS_PER_LANE; kk++) {
+                    const uint32_t site0 = (kk * 32u + lane) * 16u;
+                    const uint32_t nv = site0 >= lim ? 0u : min(16u, lim - site0);
+                    if (nv < 16u) sw[kk * 32u + lane] &= (1u << (2u * nv)) - 1u;
+                }
+            }
             fence_proxy_async();     // generic-proxy writes -> visible to the bulk store
         }
         __syncwarp();
@@ -433,7 +503,7 @@ __global__ void __launch_bounds__(CS_THREADS, 3) core_step_kernel(const CoreStep
             bulk_commit();
             if (j + CS_STAGES - 1 < n_my) {
                 bulk_wait_read<1>();      // the store that last used stage (j-1)%S has left smem
-                issue_load(j + CS_STAGES - 1);
+                PANSIM_ISSUE_LOAD();
             }
         }
         __syncwarp();
@@ -441,6 +511,7 @@ __global__ void __launch_bounds__(CS_THREADS, 3) core_step_kernel(const CoreStep
         if (reg >= a.n_regions) { reg -= a.n_regions; row++; }
     }
     if (lane == 0) bulk_wait<0>();
+#undef PANSIM_ISSUE_LOAD
 }
 
 }  // namespace pansim

@@ -59,15 +59,18 @@ void build_poisson_table(double mean, HostPoissonTable &t)
     t.thr.resize(size, 0xFFFFFFFFu);
 }
 
-// device image: [256 guide entries][size thresholds]; guide[b] = #{j : T[j] <= b << 24}
+// device image: [GUIDE_ENTRIES guide words][size thresholds]; see common.cuh
 std::vector<uint32_t> poisson_table_image(const HostPoissonTable &t)
 {
     std::vector<uint32_t> img(GUIDE_ENTRIES + t.size);
     for (uint32_t b = 0; b < GUIDE_ENTRIES; b++) {
-        const uint32_t u = b << 24;
-        uint32_t k = 0;
-        while (k < t.kmax && t.thr[k] <= u) k++;
-        img[b] = k;
+        const uint32_t lo = b << GUIDE_SHIFT;
+        const uint32_t hi = lo | ((1u << GUIDE_SHIFT) - 1u);
+        uint32_t k0 = 0, k1 = 0;
+        while (k0 < t.kmax && t.thr[k0] <= lo) k0++;
+        k1 = k0;
+        while (k1 < t.kmax && t.thr[k1] <= hi) k1++;
+        img[b] = 2u * k0 + (k1 != k0 ? 1u : 0u);
     }
     for (uint32_t j = 0; j < t.size; j++) img[GUIDE_ENTRIES + j] = t.thr[j];
     return img;
