@@ -60,6 +60,7 @@ struct CoreStepArgs {
     uint32_t n_regions;       // regions per (local) row
     uint64_t row_stride;      // bytes
     uint32_t region0;         // global index of local region 0
+    uint32_t items_per_warp;  // (row, region) items per warp; a CTA covers CS_WARPS * items_per_warp consecutive items
     uint64_t site_limit;      // global site index one past the last valid site of this shard
     uint2 key;
     uint32_t gen;
@@ -311,13 +312,18 @@ __global__ void __launch_bounds__(CS_THREADS, 4) core_step_kernel(const CoreStep
     }
     __syncthreads();
 
+    // CTA b covers items [b*C, (b+1)*C), C = CS_WARPS*items_per_warp; warp w takes b*C + w + 8j.
+    // CTAs are short-lived on purpose: SM slots turn over every few tens of microseconds, so the
+    // (higher-priority) accessory/selection kernels of the next generation can slip in between.
     const uint32_t total = a.n_rows * a.n_regions;
-    const uint32_t n_warps = gridDim.x * CS_WARPS;
-    const uint32_t gw = blockIdx.x * CS_WARPS + warp;
-    if (gw >= total) return;
-    const uint32_t n_my = (total - gw + n_warps - 1) / n_warps;
-    // item t = gw + j*n_warps  ->  (row, reg), advanced incrementally
-    const uint32_t d_row = n_warps / a.n_regions, d_reg = n_warps % a.n_regions;
+    const uint32_t cta_items = CS_WARPS * a.items_per_warp;
+    const uint32_t cta_base = blockIdx.x * cta_items;
+    const uint32_t cta_end = min(total, cta_base + cta_items);
+    const uint32_t gw = cta_base + warp;
+    if (gw >= cta_end) return;
+    const uint32_t n_my = (cta_end - gw + CS_WARPS - 1) / CS_WARPS;
+    // item t = gw + j*CS_WARPS  ->  (row, reg), advanced incrementally
+    const uint32_t d_row = CS_WARPS / a.n_regions, d_reg = CS_WARPS % a.n_regions;
 
     // the load side runs CS_STAGES-1 items ahead with its own (row, reg) cursor (lane 0 only)
     uint32_t l_row = gw / a.n_regions, l_reg = gw % a.n_regions, l_j = 0;

@@ -104,7 +104,13 @@ enum TimeGroup { TG_SELECT = 0, TG_ACC, TG_CORE, TG_PAIR_CORE, TG_PAIR_ACC, TG_C
 struct pansim_ctx {
     pansim_config cfg;
     std::string err;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;        // accessory / selection chain, copies, distances
+    cudaStream_t stream_core = nullptr;   // fused core step (runs concurrently with the chain above)
+    cudaEvent_t ev_parents[3] = {nullptr, nullptr, nullptr};    // parents[i] written
+    cudaEvent_t ev_core_done[3] = {nullptr, nullptr, nullptr};  // core step that read parents[i] finished
+    bool core_done_valid[3] = {false, false, false};
+    uint32_t *d_parents_buf[3] = {nullptr, nullptr, nullptr};
+    int parents_idx = 0;
     int sm_count = 0;
 
     uint32_t N = 0, G = 0;
@@ -167,7 +173,7 @@ struct pansim_ctx {
     cudaEvent_t t_begin = nullptr, t_end = nullptr;
     uint32_t launches = 0;
 
-    uint32_t core_grid = 0;
+    uint32_t core_grid = 0, core_items_per_warp = 1;
     size_t core_smem = 0;
 };
 
@@ -203,19 +209,20 @@ inline uint32_t div_up64(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1)
 struct ScopedSpan {
     pansim_ctx *c;
     int group;
+    cudaStream_t st;
     cudaEvent_t a = nullptr;
-    ScopedSpan(pansim_ctx *ctx, int g) : c(ctx), group(g)
+    ScopedSpan(pansim_ctx *ctx, int g, cudaStream_t stream = nullptr) : c(ctx), group(g), st(stream ? stream : ctx->stream)
     {
         if (c->timing_enabled) {
             a = c->pool.get();
-            cudaEventRecord(a, c->stream);
+            cudaEventRecord(a, st);
         }
     }
     ~ScopedSpan()
     {
         if (c->timing_enabled) {
             cudaEvent_t b = c->pool.get();
-            cudaEventRecord(b, c->stream);
+            cudaEventRecord(b, st);
             c->spans.push_back({a, b, group});
         }
     }
@@ -381,6 +388,7 @@ void fill_core_args(pansim_ctx *c, CoreStepArgs &a, uint32_t gen)
     a.n_regions = c->n_regions;
     a.row_stride = c->core_stride;
     a.region0 = c->region0;
+    a.items_per_warp = c->core_items_per_warp;
     a.site_limit = c->site_end;
     a.key = make_uint2((uint32_t)c->cfg.seed, (uint32_t)(c->cfg.seed >> 32));
     a.gen = gen;
@@ -393,18 +401,18 @@ void fill_core_args(pansim_ctx *c, CoreStepArgs &a, uint32_t gen)
     a.d_hr_value = c->d_hr_value;
 }
 
-int launch_core_step(pansim_ctx *c, uint32_t gen, bool rng)
+int launch_core_step(pansim_ctx *c, uint32_t gen, bool rng, cudaStream_t st)
 {
     if (c->Ll == 0) return 0;
     CoreStepArgs a;
     fill_core_args(c, a, gen);
     const bool any_rng = rng && (a.mut_nsub || a.hr_nsub);
     if (!any_rng) {
-        core_step_kernel<false, false><<<c->core_grid, CS_THREADS, c->core_smem, c->stream>>>(a);
+        core_step_kernel<false, false><<<c->core_grid, CS_THREADS, c->core_smem, st>>>(a);
     } else if (c->dump_enabled) {
-        core_step_kernel<true, true><<<c->core_grid, CS_THREADS, c->core_smem, c->stream>>>(a);
+        core_step_kernel<true, true><<<c->core_grid, CS_THREADS, c->core_smem, st>>>(a);
     } else {
-        core_step_kernel<true, false><<<c->core_grid, CS_THREADS, c->core_smem, c->stream>>>(a);
+        core_step_kernel<true, false><<<c->core_grid, CS_THREADS, c->core_smem, st>>>(a);
     }
     LAUNCH_CHECK(c);
     c->core_cur ^= 1;
@@ -417,8 +425,49 @@ int require_state(pansim_ctx *c)
     return 0;
 }
 
+// Rotate to the next parents buffer. The buffer was last read by the core step
+// issued three generations ago: the selection chain must not overwrite it before
+// that kernel has finished.
+int next_parents_buffer(pansim_ctx *c)
+{
+    c->parents_idx = (c->parents_idx + 1) % 3;
+    const int i = c->parents_idx;
+    if (c->core_done_valid[i]) CU(c, cudaStreamWaitEvent(c->stream, c->ev_core_done[i], 0));
+    c->d_parents = c->d_parents_buf[i];
+    return 0;
+}
+
+// accessory step on the chain stream, fused core step on the core stream; both
+// read the current parents buffer, which must have been produced on c->stream.
+int launch_population_steps(pansim_ctx *c, uint32_t gen)
+{
+    const int i = c->parents_idx;
+    CU(c, cudaEventRecord(c->ev_parents[i], c->stream));
+    CU(c, cudaStreamWaitEvent(c->stream_core, c->ev_parents[i], 0));
+    {
+        ScopedSpan s(c, TG_CORE, c->stream_core);
+        if (int rc = launch_core_step(c, gen, true, c->stream_core)) return rc;
+    }
+    CU(c, cudaEventRecord(c->ev_core_done[i], c->stream_core));
+    c->core_done_valid[i] = true;
+    {
+        ScopedSpan s(c, TG_ACC);
+        if (int rc = launch_acc_step(c, gen)) return rc;
+    }
+    return 0;
+}
+
+// after a batch of generations: later work on c->stream must see the core state
+int join_core_stream(pansim_ctx *c)
+{
+    const int i = c->parents_idx;
+    if (c->core_done_valid[i]) CU(c, cudaStreamWaitEvent(c->stream, c->ev_core_done[i], 0));
+    return 0;
+}
+
 int step_device(pansim_ctx *c, uint32_t gen)
 {
+    if (int rc = next_parents_buffer(c)) return rc;
     {
         ScopedSpan s(c, TG_SELECT);
         bool use_avg = false;
@@ -428,14 +477,7 @@ int step_device(pansim_ctx *c, uint32_t gen)
         }
         if (int rc = launch_select(c, gen, use_avg)) return rc;
     }
-    {
-        ScopedSpan s(c, TG_ACC);
-        if (int rc = launch_acc_step(c, gen)) return rc;
-    }
-    {
-        ScopedSpan s(c, TG_CORE);
-        if (int rc = launch_core_step(c, gen, true)) return rc;
-    }
+    if (int rc = launch_population_steps(c, gen)) return rc;
     c->avgdist_valid = false;
     return 0;
 }
@@ -473,7 +515,8 @@ void pansim_destroy(pansim_ctx *c)
     if (!c) return;
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    void *ptrs[] = {c->core[0], c->core[1], c->acc[0], c->acc[1], c->d_parents, c->d_lw, c->d_logfit, c->d_avgdist,
+    if (c->stream_core) cudaStreamSynchronize(c->stream_core);
+    void *ptrs[] = {c->core[0], c->core[1], c->acc[0], c->acc[1], c->d_parents_buf[0], c->d_parents_buf[1], c->d_parents_buf[2], c->d_lw, c->d_logfit, c->d_avgdist,
                     c->d_num_genes, c->d_tmp_a, c->d_tmp_b, c->d_weights, c->d_cum, c->d_err, c->d_inter, c->d_rowK,
                     c->d_gain_thr, c->tab_mut.d_thr, c->tab_hr.d_thr, c->d_r1, c->d_r2, c->d_cd, c->d_in, c->d_un,
                     c->d_replay, c->d_hkeys, c->d_hvals, c->d_stage, c->d_dump_counters, c->d_mut_row, c->d_mut_site,
@@ -482,6 +525,11 @@ void pansim_destroy(pansim_ctx *c)
     for (void *p : ptrs)
         if (p) cudaFree(p);
     c->pool.destroy();
+    for (int i = 0; i < 3; i++) {
+        if (c->ev_parents[i]) cudaEventDestroy(c->ev_parents[i]);
+        if (c->ev_core_done[i]) cudaEventDestroy(c->ev_core_done[i]);
+    }
+    if (c->stream_core) cudaStreamDestroy(c->stream_core);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -531,7 +579,17 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
         CU(c, cudaGetDeviceProperties(&prop, cfg->device));
         if (prop.major < 10) FAIL(c, PANSIM_ERR_CUDA, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
         c->sm_count = prop.multiProcessorCount;
-        CU(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        {
+            // the accessory/selection chain is latency-critical and tiny: give it priority over the core step
+            int lo = 0, hi = 0;
+            CU(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CU(c, cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, hi));
+            CU(c, cudaStreamCreateWithPriority(&c->stream_core, cudaStreamNonBlocking, lo));
+        }
+        for (int i = 0; i < 3; i++) {
+            CU(c, cudaEventCreateWithFlags(&c->ev_parents[i], cudaEventDisableTiming));
+            CU(c, cudaEventCreateWithFlags(&c->ev_core_done[i], cudaEventDisableTiming));
+        }
 
         // per-cell rates
         const double rate_mut = cfg->core_mut_mean / (double)c->L;
@@ -568,7 +626,8 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
             CU(c, cudaMemset(c->acc[b], 0, acc_bytes));
         }
         const size_t n = c->N;
-        CU(c, cudaMalloc(&c->d_parents, n * 4));
+        for (int i = 0; i < 3; i++) CU(c, cudaMalloc(&c->d_parents_buf[i], n * 4));
+        c->d_parents = c->d_parents_buf[0];
         CU(c, cudaMalloc(&c->d_lw, (size_t)(c->G ? c->G : 1) * 8));
         CU(c, cudaMemset(c->d_lw, 0, (size_t)(c->G ? c->G : 1) * 8));
         CU(c, cudaMalloc(&c->d_logfit, n * 8));
@@ -593,12 +652,13 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
         int occ = 0;
         CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, core_step_kernel<true, false>, CS_THREADS, c->core_smem));
         if (occ < 1) FAIL(c, PANSIM_ERR_CUDA, "core_step_kernel does not fit on an SM (smem %zu)", c->core_smem);
+        // short-lived CTAs (3 items per warp, tuned on B200): many waves over the resident slots
         const uint64_t items = (uint64_t)c->N * c->n_regions;
-        uint64_t grid = (uint64_t)c->sm_count * occ;
-        const uint64_t need = (items + CS_WARPS - 1) / CS_WARPS;
-        if (grid > need) grid = need;
-        if (grid < 1) grid = 1;
-        c->core_grid = (uint32_t)grid;
+        c->core_items_per_warp = 3;
+        if (const char *e = getenv("PANSIM_CORE_ITEMS_PER_WARP")) c->core_items_per_warp = (uint32_t)std::max(1, atoi(e));
+        const uint64_t per_cta = (uint64_t)CS_WARPS * c->core_items_per_warp;
+        c->core_grid = (uint32_t)std::max<uint64_t>(1, (items + per_cta - 1) / per_cta);
+        (void)occ;
         return 0;
     };
     int rc = body();
@@ -812,6 +872,7 @@ int pansim_sample_indices(pansim_ctx *c, uint32_t gen, const double *avg, uint32
     if (!c) return PANSIM_ERR_INVALID;
     if (int rc = require_state(c)) return rc;
     CU(c, cudaSetDevice(c->cfg.device));
+    if (int rc = next_parents_buffer(c)) return rc;
     bool use_avg = false;
     if (avg) {
         CU(c, cudaMemcpyAsync(c->d_avgdist, avg, (size_t)c->N * 8, cudaMemcpyHostToDevice, c->stream));
@@ -863,17 +924,12 @@ int pansim_step_with_parents(pansim_ctx *c, uint32_t gen, const uint32_t *parent
     if (!c || !parents) return PANSIM_ERR_INVALID;
     if (int rc = require_state(c)) return rc;
     CU(c, cudaSetDevice(c->cfg.device));
+    if (int rc = next_parents_buffer(c)) return rc;
     if (int rc = upload_parents(c, parents)) return rc;
     if (c->dump_enabled) CU(c, cudaMemsetAsync(c->d_dump_counters, 0, 2 * sizeof(uint32_t), c->stream));
     timing_begin(c);
-    {
-        ScopedSpan s(c, TG_ACC);
-        if (int rc = launch_acc_step(c, gen)) return rc;
-    }
-    {
-        ScopedSpan s(c, TG_CORE);
-        if (int rc = launch_core_step(c, gen, true)) return rc;
-    }
+    if (int rc = launch_population_steps(c, gen)) return rc;
+    if (int rc = join_core_stream(c)) return rc;
     timing_end(c);
     c->avgdist_valid = false;
     CU(c, cudaStreamSynchronize(c->stream));
@@ -891,6 +947,7 @@ int pansim_run_generations(pansim_ctx *c, uint32_t gen0, uint32_t n)
     timing_begin(c);
     for (uint32_t g = 0; g < n; g++)
         if (int rc = step_device(c, gen0 + g)) return rc;
+    if (int rc = join_core_stream(c)) return rc;
     timing_end(c);
     return check_device_flag(c, PANSIM_ERR_WEIGHTS, "WeightedIndex::new would fail: a weight is negative/NaN or the total is not positive (population.rs:440)");
 }
@@ -900,6 +957,7 @@ int pansim_next_generation(pansim_ctx *c, const uint32_t *parents)
     if (!c || !parents) return PANSIM_ERR_INVALID;
     if (int rc = require_state(c)) return rc;
     CU(c, cudaSetDevice(c->cfg.device));
+    if (int rc = next_parents_buffer(c)) return rc;
     if (int rc = upload_parents(c, parents)) return rc;
     timing_begin(c);
     if (c->G) {
@@ -909,7 +967,7 @@ int pansim_next_generation(pansim_ctx *c, const uint32_t *parents)
         c->acc_cur ^= 1;
         c->fitness_valid = false;
     }
-    if (int rc = launch_core_step(c, 0, false)) return rc;
+    if (int rc = launch_core_step(c, 0, false, c->stream)) return rc;
     timing_end(c);
     c->avgdist_valid = false;
     CU(c, cudaStreamSynchronize(c->stream));
