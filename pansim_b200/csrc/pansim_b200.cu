@@ -554,8 +554,8 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
         c->site_end = cfg->site_end;
         if (c->site_begin == 0 && c->site_end == 0) c->site_end = c->L;
         if (c->site_end > c->L || c->site_begin > c->site_end) FAIL(c, PANSIM_ERR_INVALID, "bad column shard [%llu,%llu)", (unsigned long long)c->site_begin, (unsigned long long)c->site_end);
-        if (c->site_begin % PANSIM_SITE_ALIGN) FAIL(c, PANSIM_ERR_INVALID, "site_begin must be a multiple of %u", PANSIM_SITE_ALIGN);
-        if (c->site_end != c->L && c->site_end % PANSIM_SITE_ALIGN) FAIL(c, PANSIM_ERR_INVALID, "site_end must be core_size or a multiple of %u", PANSIM_SITE_ALIGN);
+        if (c->site_begin % PANSIM_SITE_ALIGN && c->site_begin != c->site_end) FAIL(c, PANSIM_ERR_INVALID, "site_begin must be a multiple of %u", PANSIM_SITE_ALIGN);
+        if (c->site_end != c->L && c->site_end % PANSIM_SITE_ALIGN && c->site_begin != c->site_end) FAIL(c, PANSIM_ERR_INVALID, "site_end must be core_size or a multiple of %u", PANSIM_SITE_ALIGN);
         c->Ll = c->site_end - c->site_begin;
         c->region0 = (uint32_t)(c->site_begin / REGION_SITES);
         c->n_regions = (uint32_t)((c->Ll + REGION_SITES - 1) / REGION_SITES);

@@ -55,7 +55,7 @@ def test_create_fails_loudly_without_gpu_or_bad_args():
         assert b"no CPU fallback" in _ffi.lib().pansim_last_error(None)
         with pytest.raises(pb.PansimError):
             pb.Pansim(cfg)
-    cfg.site_begin = 100        # not a multiple of PANSIM_SITE_ALIGN
+    cfg.site_begin = 10         # not a multiple of PANSIM_SITE_ALIGN
     cfg.site_end = 100
     rc = _ffi.lib().pansim_create(C.byref(cfg), C.byref(h))
     assert rc == -1 and b"site_begin" in _ffi.lib().pansim_last_error(None)
