@@ -63,8 +63,9 @@ class RunResult:
     stdout: list = field(default_factory=list)
 
 
-def run(p: Params, outpref: str | None = None, device: int = 0, out=sys.stdout) -> RunResult | None:
+def run(p: Params, outpref: str | None = None, device: int = 0, out=None) -> RunResult | None:
     """main.rs:15-564. Returns None where the reference prints a validation message and exits 0."""
+    out = out or sys.stdout
     msgs = validate(p)
     if msgs:
         for m in msgs:

@@ -1,0 +1,111 @@
+"""End-to-end tests: whole runs through the host driver (main.rs mirror) on the GPU.
+
+KS design (hard part 6): pairwise distances within one run share
+a genealogy, so the two-sample KS test is taken over PER-RUN summary scalars --
+20 GPU seeds vs 20 oracle seeds per scalar, p > 0.01 (north_star). Both sides are
+deterministic given their seeds, so the outcome of this test is reproducible.
+"""
+import os
+
+import numpy as np
+import pytest
+from scipy.stats import ks_2samp
+
+import pansim_b200 as pb
+from pansim_b200 import simulate
+from oracle import binding as ob
+
+pytestmark = pytest.mark.gpu
+
+SCALARS = ["mean_core", "mean_acc", "median_core", "median_acc", "std_core", "std_acc",
+           "mean_gene_freq", "frac_freq_lt_01", "frac_freq_gt_09"]
+
+CONFIGS = {
+    "neutral_defaults_scaled": dict(pop_size=64, core_size=20000, pan_genes=600, core_genes=200, n_gen=30,
+                                    max_distances=2000),
+    "selection_competition_high_recomb": dict(pop_size=48, core_size=12000, pan_genes=400, core_genes=100, n_gen=25,
+                                              max_distances=1500, prop_positive=0.1, competition_strength=0.5,
+                                              HR_rate=1.0, HGT_rate=1.0),
+}
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_ks_gpu_vs_oracle_over_20_seeds(name):
+    kw = CONFIGS[name]
+    gpu, cpu = {k: [] for k in SCALARS}, {k: [] for k in SCALARS}
+    for seed in range(20):
+        p = pb.Params(seed=seed, **kw)
+        d = pb.derive(p)
+        r = simulate.run(p, outpref=None)
+        s = simulate.summarize(r.core_distances, r.acc_distances, r.gene_freqs, d.pan_size)
+        o = ob.run(ob.default_params(seed=1000 + seed, threads=2, **kw))
+        for k in SCALARS:
+            gpu[k].append(s[k])
+            cpu[k].append(getattr(o, k))
+    report = {}
+    for k in SCALARS:
+        if np.ptp(gpu[k] + cpu[k]) == 0:           # degenerate scalar (e.g. no gene above 0.9)
+            report[k] = 1.0
+            continue
+        report[k] = ks_2samp(gpu[k], cpu[k]).pvalue
+    bad = {k: v for k, v in report.items() if not v > 0.01}
+    assert not bad, f"KS p <= 0.01 for {bad}; all: {report}"
+
+
+def test_output_files_have_reference_format(tmp_path):
+    p = pb.Params(pop_size=20, core_size=500, pan_genes=60, core_genes=20, n_gen=3, max_distances=50, seed=4,
+                  print_dist=True, print_matrices=True, print_selection=True, prop_positive=0.2, verbose=True)
+    d = pb.derive(p)
+    pref = str(tmp_path / "out")
+    lines = []
+
+    class Sink:
+        def write(self, s):
+            lines.append(s)
+
+    r = simulate.run(p, outpref=pref, out=Sink())
+    text = "".join(lines).splitlines()
+    assert text[0] == f"avg_gene_freq adjusted to {pb.fmt_f64(d.avg_gene_freq_adj)}"       # main.rs:270
+    assert text[1] == "Finished gen: 1" and text[2].startswith("avg_gene_freq: ")          # main.rs:523-525
+    # <outpref>.tsv: core \t acc, one line per sampled pair (main.rs:480-482)
+    rows = [l.split("\t") for l in open(pref + ".tsv").read().splitlines()]
+    assert len(rows) == 50 and all(len(x) == 2 for x in rows)
+    assert [float(x[0]) for x in rows] == r.core_distances.tolist()
+    assert all("e" not in x[0] and "e" not in x[1] for x in rows)                          # Rust `{}`: never scientific
+    # _freqs.txt: accessory genes first, then core_genes ones (population.rs:857-860)
+    fr = open(pref + "_freqs.txt").read().splitlines()
+    assert len(fr) == d.pan_size + p.core_genes and fr[-p.core_genes:] == ["1"] * p.core_genes
+    # _per_gen.tsv: avg_core, std_core, avg_acc, std_acc per generation (main.rs:546)
+    pg = [l.split("\t") for l in open(pref + "_per_gen.tsv").read().splitlines()]
+    assert len(pg) == 3 and all(len(x) == 4 for x in pg)
+    std_c, avg_c = pb.standard_deviation(r.core_distances)
+    assert pg[-1][0] == pb.fmt_f64(avg_c) and pg[-1][1] == pb.fmt_f64(std_c)
+    # _selection.tsv: one coefficient per accessory gene (main.rs:328-329)
+    assert len(open(pref + "_selection.tsv").read().splitlines()) == d.pan_size
+    # matrices (population.rs:865-897): core letters; pangenome = core ones then accessory bits
+    core = open(pref + "_core_genome.csv").read().splitlines()
+    assert len(core) == 20 and all(len(l.split(",")) == 500 and set(l.split(",")) <= set("ACGT") for l in core)
+    pan = [l.split(",") for l in open(pref + "_pangenome.csv").read().splitlines()]
+    assert len(pan) == 20 and all(len(x) == 60 and x[:20] == ["1"] * 20 for x in pan)
+
+
+def test_validation_failure_prints_and_returns_none(capsys):
+    assert simulate.run(pb.Params(core_genes=7000), outpref=None) is None
+    assert "core_genes must be less than or equal to pan_size" in capsys.readouterr().out
+
+
+def test_cli_runs(tmp_path):
+    from pansim_b200.__main__ import main
+    pref = str(tmp_path / "cli")
+    rc = main(["--pop_size", "1e1", "--core_size", "300", "--pan_genes", "40", "--core_genes", "10", "--n_gen", "2",
+               "--max_distances", "7", "--outpref", pref, "--HR_rate", "0.5", "--prop_positive", "-0.1"])
+    assert rc == 0 and len(open(pref + ".tsv").read().splitlines()) == 7
+
+
+def test_same_seed_same_result_and_device_runs_are_reproducible():
+    kw = dict(pop_size=32, core_size=9000, pan_genes=200, core_genes=50, n_gen=5, max_distances=100, seed=9,
+              prop_positive=0.1, competition_strength=0.2)
+    a = simulate.run(pb.Params(**kw))
+    b = simulate.run(pb.Params(**kw))
+    assert (a.core_distances == b.core_distances).all() and (a.acc_distances == b.acc_distances).all()
+    assert (a.gene_freqs == b.gene_freqs).all()
