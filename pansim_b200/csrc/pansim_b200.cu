@@ -140,6 +140,11 @@ struct pansim_ctx {
     double hgt_scale[2] = {0, 0};
     double p_mut_site = 0, p_hr_site = 0;
 
+    // pair plan (row-stationary groups), cached while the pair list is unchanged
+    std::vector<uint32_t> plan_r1, plan_r2;
+    PairGroup *d_groups = nullptr;
+    uint32_t *d_partner = nullptr, *d_orig = nullptr;
+    size_t plan_groups = 0, plan_cap_groups = 0, plan_cap_pairs = 0;
     // pair buffers
     uint32_t *d_r1 = nullptr, *d_r2 = nullptr, *d_cd = nullptr, *d_in = nullptr, *d_un = nullptr;
     size_t pair_cap = 0;
@@ -519,7 +524,7 @@ void pansim_destroy(pansim_ctx *c)
     void *ptrs[] = {c->core[0], c->core[1], c->acc[0], c->acc[1], c->d_parents_buf[0], c->d_parents_buf[1], c->d_parents_buf[2], c->d_lw, c->d_logfit, c->d_avgdist,
                     c->d_num_genes, c->d_tmp_a, c->d_tmp_b, c->d_weights, c->d_cum, c->d_err, c->d_inter, c->d_rowK,
                     c->d_gain_thr, c->tab_mut.d_thr, c->tab_hr.d_thr, c->d_r1, c->d_r2, c->d_cd, c->d_in, c->d_un,
-                    c->d_replay, c->d_hkeys, c->d_hvals, c->d_stage, c->d_dump_counters, c->d_mut_row, c->d_mut_site,
+                    c->d_replay, c->d_hkeys, c->d_hvals, c->d_stage, c->d_groups, c->d_partner, c->d_orig, c->d_dump_counters, c->d_mut_row, c->d_mut_site,
                     c->d_mut_seq, c->d_mut_allele, c->d_hr_rec, c->d_hr_locus, c->d_hr_donor, c->d_hr_seq,
                     c->d_hr_value, c->d_dump_flip, c->d_dump_gain};
     for (void *p : ptrs)
@@ -1080,12 +1085,58 @@ static int ensure_pairs(pansim_ctx *c, size_t n)
     return 0;
 }
 
+// Build (or reuse) the row-stationary plan for this pair list.
+static int ensure_pair_plan(pansim_ctx *c, const uint32_t *r1, const uint32_t *r2, size_t P)
+{
+    if (c->plan_r1.size() == P && c->plan_groups &&
+        memcmp(c->plan_r1.data(), r1, P * 4) == 0 && memcmp(c->plan_r2.data(), r2, P * 4) == 0)
+        return 0;
+    // counting sort by first row
+    std::vector<uint32_t> start(c->N + 1, 0);
+    for (size_t k = 0; k < P; k++) start[r1[k] + 1]++;
+    for (uint32_t i = 0; i < c->N; i++) start[i + 1] += start[i];
+    std::vector<uint32_t> partner(P), orig(P), cursor(start.begin(), start.end() - 1);
+    for (size_t k = 0; k < P; k++) {
+        const uint32_t pos = cursor[r1[k]]++;
+        partner[pos] = r2[k];
+        orig[pos] = (uint32_t)k;
+    }
+    std::vector<PairGroup> groups;
+    groups.reserve(P / PAIR_GROUP + c->N);
+    for (uint32_t i = 0; i < c->N; i++)
+        for (uint32_t f = start[i]; f < start[i + 1]; f += PAIR_GROUP)
+            groups.push_back(PairGroup{i, f, std::min<uint32_t>(PAIR_GROUP, start[i + 1] - f)});
+    if (groups.size() > c->plan_cap_groups) {
+        if (c->d_groups) cudaFree(c->d_groups);
+        c->d_groups = nullptr; c->plan_cap_groups = 0;
+        if (cudaMalloc(&c->d_groups, groups.size() * sizeof(PairGroup)) != cudaSuccess) FAIL(c, PANSIM_ERR_NOMEM, "cudaMalloc for the pair plan failed");
+        c->plan_cap_groups = groups.size();
+    }
+    if (P > c->plan_cap_pairs) {
+        if (c->d_partner) cudaFree(c->d_partner);
+        if (c->d_orig) cudaFree(c->d_orig);
+        c->d_partner = c->d_orig = nullptr; c->plan_cap_pairs = 0;
+        if (cudaMalloc(&c->d_partner, P * 4) != cudaSuccess || cudaMalloc(&c->d_orig, P * 4) != cudaSuccess) FAIL(c, PANSIM_ERR_NOMEM, "cudaMalloc for the pair plan failed");
+        c->plan_cap_pairs = P;
+    }
+    CU(c, cudaMemcpyAsync(c->d_groups, groups.data(), groups.size() * sizeof(PairGroup), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->d_partner, partner.data(), P * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(c->d_orig, orig.data(), P * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));      // the host vectors go out of scope
+    c->plan_groups = groups.size();
+    c->plan_r1.assign(r1, r1 + P);
+    c->plan_r2.assign(r2, r2 + P);
+    return 0;
+}
+
 static int pair_counts_impl(pansim_ctx *c, const uint32_t *r1, const uint32_t *r2, size_t P, uint32_t *d_cd,
                             uint32_t *d_in, uint32_t *d_un)
 {
     if (P > 0x7FFFFFFFull) FAIL(c, PANSIM_ERR_INVALID, "more than 2^31 pairs per call");
     for (size_t k = 0; k < P; k++)
         if (r1[k] >= c->N || r2[k] >= c->N) FAIL(c, PANSIM_ERR_INVALID, "pair %zu out of range", k);
+    if (d_cd && c->Ll)
+        if (int rc = ensure_pair_plan(c, r1, r2, P)) return rc;
     CU(c, cudaMemcpyAsync(c->d_r1, r1, P * 4, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemcpyAsync(c->d_r2, r2, P * 4, cudaMemcpyHostToDevice, c->stream));
     timing_begin(c);
@@ -1104,8 +1155,10 @@ static int pair_counts_impl(pansim_ctx *c, const uint32_t *r1, const uint32_t *r
             uint32_t n_chunks = (row_vec4 + chunk_vec4 - 1) / chunk_vec4;
             if (n_chunks > 65535) { n_chunks = 65535; chunk_vec4 = (row_vec4 + n_chunks - 1) / n_chunks; chunk_vec4 = ((chunk_vec4 + 255) / 256) * 256; n_chunks = (row_vec4 + chunk_vec4 - 1) / chunk_vec4; }
             if (n_chunks > 1) CU(c, cudaMemsetAsync(d_cd, 0, P * 4, c->stream));
-            const uint32_t gx = (uint32_t)std::min<size_t>(P, 1u << 20);
-            pair_core_kernel<<<dim3(gx, n_chunks), PAIR_THREADS, 0, c->stream>>>(c->core[c->core_cur], c->core_stride, chunk_vec4, row_vec4, c->d_r1, c->d_r2, (uint32_t)P, d_cd);
+            const uint32_t gx = (uint32_t)std::min<size_t>(c->plan_groups, 1u << 20);
+            pair_core_grouped_kernel<<<dim3(gx, n_chunks), PAIR_THREADS, 0, c->stream>>>(
+                c->core[c->core_cur], c->core_stride, chunk_vec4, row_vec4, c->d_groups, (uint32_t)c->plan_groups,
+                c->d_partner, c->d_orig, d_cd);
             LAUNCH_CHECK(c);
         }
     }
