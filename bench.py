@@ -203,16 +203,16 @@ def main():
     W = max(3, args.warmup)
     K = max(1, args.steps)
     # this rank's slab: columns [rank*L, (rank+1)*L) of a (world*L)-site alignment
+    from pansim_b200.sharding import SITE_ALIGN, column_shards
     L = CFG2["core_size"]
-    align = 8192
-    Lslab = L if world == 1 else ((L + align - 1) // align) * align     # shard starts must be region aligned
+    Lslab = L if world == 1 else ((L + SITE_ALIGN - 1) // SITE_ALIGN) * SITE_ALIGN   # whole regions per rank
     total_L = L if world == 1 else Lslab * world
     kw = dict(CFG2)
     kw["core_size"] = total_L
     # keep the per-site rates of cfg2: lambda scales with the alignment length (main.rs:275)
     p = pb.Params(**kw)
     d = pb.derive(p)
-    site_begin, site_end = (0, 0) if world == 1 else (rank * Lslab, min(total_L, (rank + 1) * Lslab))
+    site_begin, site_end = (0, 0) if world == 1 else column_shards(total_L, world)[rank]
     sim = pb.Pansim.from_params(p, device=local_rank, site_begin=site_begin, site_end=site_end)
     info = sim.info()
 
