@@ -155,27 +155,29 @@ struct MutApply {
     uint64_t reg_site0;
     const CoreStepArgs *a;
 
-    __device__ __forceinline__ void slot(uint32_t pos, uint32_t digit, uint32_t idx, uint32_t kk) const
+    // `code` = new 2-bit allele (1..3). Branch-free: the read-modify-write is computed for
+    // every slot and only the store is predicated on the slot being a real event, so the
+    // five slots of a chunk form one basic block the scheduler can interleave.
+    __device__ __forceinline__ void slot(uint32_t pos, uint32_t code, uint32_t idx, uint32_t kk) const
     {
         // positions beyond the end of a ragged last region are written too and
         // cleared again by the padding fix-up at the end of the item
-        if (idx < kk) {
-            const uint32_t addr = lane_base + ((pos & 0xF0u) << 3);      // word (pos>>4)*32 + lane
-            const uint32_t one = 1u << ((pos & 15u) * 2u);
-            uint32_t w;
-            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(addr));
-            w = (w & ~(one * 3u)) | (one * digit + one);                 // code = digit + 1 in {C,G,T}
-            asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(w) : "memory");
-            if (DUMP) {
-                if (pos < pos_lim) {
-                    const uint32_t s = atomicAdd(&a->dump_counters[0], 1u);
-                    if (s < a->dump_cap) {
-                        const uint32_t sir = (((pos >> 4) << 5) + lane) * 16u + (pos & 15u);
-                        a->d_mut_row[s] = row;
-                        a->d_mut_site[s] = (uint32_t)(reg_site0 + sir);
-                        a->d_mut_seq[s] = idx;
-                        a->d_mut_allele[s] = (uint8_t)(2u << digit);
-                    }
+        const uint32_t addr = lane_base + ((pos & 0xF0u) << 3);          // word (pos>>4)*32 + lane
+        const uint32_t sh = (pos & 15u) * 2u;
+        uint32_t w;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(addr));
+        w = (w & ~(3u << sh)) | (code << sh);
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.lt.u32 p, %2, %3;\n\t@p st.shared.u32 [%0], %1;\n\t}"
+                     ::"r"(addr), "r"(w), "r"(idx), "r"(kk) : "memory");
+        if (DUMP) {
+            if (idx < kk && pos < pos_lim) {
+                const uint32_t s = atomicAdd(&a->dump_counters[0], 1u);
+                if (s < a->dump_cap) {
+                    const uint32_t sir = (((pos >> 4) << 5) + lane) * 16u + (pos & 15u);
+                    a->d_mut_row[s] = row;
+                    a->d_mut_site[s] = (uint32_t)(reg_site0 + sir);
+                    a->d_mut_seq[s] = idx;
+                    a->d_mut_allele[s] = (uint8_t)(1u << code);
                 }
             }
         }
@@ -194,10 +196,10 @@ struct MutApply {
 #pragma unroll
             for (int i = 0; i < 5; i++) {
                 const uint32_t q = (v * 171u) >> 9;        // v / 3 for v < 256
-                const uint32_t digit = v - 3u * q;
+                const uint32_t code = v + 1u - 3u * q;     // base-3 digit + 1 = allele code of {C,G,T}
                 v = q;
                 const uint32_t pos = i < 4 ? ((p0 >> (8 * i)) & 255u) : (p1 & 255u);
-                slot(pos, digit, base + 5u * c + i, kk);
+                slot(pos, code, base + 5u * c + i, kk);
             }
             // advance the position string by 5 bytes
             p0 = __funnelshift_r(p1, p2, 8);
