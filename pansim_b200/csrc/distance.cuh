@@ -127,9 +127,130 @@ __global__ void __launch_bounds__(PAIR_THREADS) pair_core_grouped_kernel(
             uint32_t t = 0;
             for (int w = 0; w < PAIR_THREADS / 32; w++) t += wsum[w][threadIdx.x];
             const uint32_t out = orig_index[grp.first + threadIdx.x];
-            if (gridDim.y == 1) core_diff[out] = t; else atomicAdd(&core_diff[out], t);
+            atomicAdd(&core_diff[out], t);
         }
         __syncthreads();
+    }
+}
+
+// v2: shared-memory row tiles. The host plan (cached) buckets the pairs by the pair of
+// 32-row blocks their endpoints fall in. A CTA takes one batch (<= 256 pairs of one
+// block pair), stages the <= 64 rows it needs, 512 B per row per stage, with cp.async
+// (LDGSTS, 16 B per thread, 3-stage ring; 64 separate 512 B TMA bulk copies per stage were
+// measured slower), and walks the whole column range. Each warp owns up to 16 consecutive pairs of the batch (sorted by
+// first endpoint so the first row is re-read only when it changes) and keeps their counts
+// in registers until the end: every staged byte is reused by all pairs of the batch that
+// touch its row, which cuts the L2 traffic of the streaming kernels ~3-6x.
+constexpr int TILE_ROWS = 64;          // 2 blocks of 32 rows
+constexpr int TILE_BYTES = 512;        // per row per stage
+constexpr int TILE_STAGES = 3;
+constexpr int TILE_WARPS = 16;
+constexpr int TILE_THREADS = TILE_WARPS * 32;
+constexpr int TILE_PPW = 16;           // pairs per warp
+constexpr int TILE_BATCH = TILE_WARPS * TILE_PPW;   // 256
+
+struct TileBatch {
+    uint32_t block_a, block_b;         // 32-row blocks (block_a <= block_b)
+    uint32_t first, count;             // range in the tile pair arrays
+    uint32_t col_begin, col_end;       // column range in units of TILE_BYTES
+};
+
+static inline size_t tile_smem_bytes()
+{
+    return (size_t)TILE_STAGES * TILE_ROWS * TILE_BYTES + TILE_BATCH * sizeof(uint32_t);
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(TILE_THREADS, 2) pair_core_tile_kernel(
+    const uint8_t *state, uint64_t row_stride, uint32_t n_rows, const TileBatch *batches,
+    const uint16_t *tile_slots, const uint32_t *tile_orig, uint32_t *core_diff)
+{
+    extern __shared__ __align__(128) uint8_t tsm[];
+    uint32_t *meta = reinterpret_cast<uint32_t *>(tsm + (size_t)TILE_STAGES * TILE_ROWS * TILE_BYTES);
+    const TileBatch bt = batches[blockIdx.x];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    for (uint32_t i = threadIdx.x; i < TILE_BATCH; i += TILE_THREADS)
+        meta[i] = i < bt.count ? tile_slots[bt.first + i] : 0xFFFFu;
+
+    // staging: a stage is TILE_ROWS x 512 B = 2048 pieces of 16 B, 4 per thread. Piece p of a
+    // chunk belongs to row slot p/32 (slots 0..31 -> block_a, 32..63 -> block_b), byte (p%32)*16.
+    constexpr int PIECES = TILE_ROWS * TILE_BYTES / 16 / TILE_THREADS;      // 4
+    const uint8_t *src[PIECES];
+    uint32_t dst_off[PIECES];
+#pragma unroll
+    for (int k = 0; k < PIECES; k++) {
+        const uint32_t p = threadIdx.x + k * TILE_THREADS;
+        const uint32_t slot = p >> 5;
+        const uint32_t row = slot < 32 ? bt.block_a * 32 + slot : bt.block_b * 32 + (slot - 32);
+        const bool ok = row < n_rows && (slot < 32 || bt.block_b != bt.block_a);
+        src[k] = ok ? state + (uint64_t)row * row_stride + (uint64_t)bt.col_begin * TILE_BYTES + (p & 31u) * 16u : nullptr;
+        dst_off[k] = slot * TILE_BYTES + (p & 31u) * 16u;
+    }
+    const uint32_t n_chunks = bt.col_end - bt.col_begin;
+    auto issue = [&](uint32_t c) {
+        uint8_t *stage = tsm + (size_t)(c % TILE_STAGES) * TILE_ROWS * TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < PIECES; k++)
+            if (src[k]) cp_async16(stage + dst_off[k], src[k] + (uint64_t)c * TILE_BYTES);
+        cp_async_commit();
+    };
+    issue(0);
+    if (n_chunks > 1) issue(1); else cp_async_commit();
+
+    uint32_t acc[TILE_PPW];
+#pragma unroll
+    for (int q = 0; q < TILE_PPW; q++) acc[q] = 0;
+    __syncthreads();                                   // meta[] is complete
+    // per-warp pair metadata hoisted out of the column loop: byte offsets of both rows inside
+    // a stage (packed a | b << 16), number of real pairs, and which pairs start a new first row
+    uint32_t offs[TILE_PPW];
+    uint32_t nq = 0, reload = 0;
+    {
+        uint32_t prev = 0xFFFFFFFFu;
+#pragma unroll
+        for (int q = 0; q < TILE_PPW; q++) {
+            const uint32_t m = meta[warp * TILE_PPW + q];
+            const uint32_t sa = m & 0xFFu, sb = (m >> 8) & 0xFFu;
+            offs[q] = (sa * TILE_BYTES) | ((sb * TILE_BYTES) << 16);
+            if (m != 0xFFFFu) {
+                nq = q + 1;
+                if (sa != prev) reload |= 1u << q;
+                prev = sa;
+            }
+        }
+    }
+
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        if (c + 2 < n_chunks) issue(c + 2); else cp_async_commit();     // keep the group count uniform
+        cp_async_wait<2>();                                              // chunk c has landed (this thread)
+        __syncthreads();                                                 // ... and everybody else's pieces
+        const uint8_t *base = tsm + (size_t)(c % TILE_STAGES) * TILE_ROWS * TILE_BYTES + lane * 16;
+        uint4 a = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int q = 0; q < TILE_PPW; q++) {
+            if (q < (int)nq) {                       // warp-uniform
+                if ((reload >> q) & 1u) a = *reinterpret_cast<const uint4 *>(base + (offs[q] & 0xFFFFu));
+                const uint4 b = *reinterpret_cast<const uint4 *>(base + (offs[q] >> 16));
+                acc[q] += diff_sites4(a, b);
+            }
+        }
+        __syncthreads();                              // stage c%3 may be overwritten by chunk c+3 next iteration
+    }
+#pragma unroll
+    for (int q = 0; q < TILE_PPW; q++) {
+        uint32_t v = acc[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        const uint32_t idx = warp * TILE_PPW + q;
+        if (lane == 0 && idx < bt.count) atomicAdd(&core_diff[tile_orig[bt.first + idx]], v);
     }
 }
 

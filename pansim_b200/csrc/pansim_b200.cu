@@ -3,6 +3,7 @@
 // launch configuration and error mapping. There is no CPU fallback.
 #include "../../include/pansim_b200.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -145,6 +146,10 @@ struct pansim_ctx {
     PairGroup *d_groups = nullptr;
     uint32_t *d_partner = nullptr, *d_orig = nullptr;
     size_t plan_groups = 0, plan_cap_groups = 0, plan_cap_pairs = 0;
+    TileBatch *d_batches = nullptr;
+    uint16_t *d_tile_slots = nullptr;
+    uint32_t *d_tile_orig = nullptr;
+    size_t plan_batches = 0, plan_cap_batches = 0, plan_cap_tile_pairs = 0;
     // pair buffers
     uint32_t *d_r1 = nullptr, *d_r2 = nullptr, *d_cd = nullptr, *d_in = nullptr, *d_un = nullptr;
     size_t pair_cap = 0;
@@ -524,7 +529,7 @@ void pansim_destroy(pansim_ctx *c)
     void *ptrs[] = {c->core[0], c->core[1], c->acc[0], c->acc[1], c->d_parents_buf[0], c->d_parents_buf[1], c->d_parents_buf[2], c->d_lw, c->d_logfit, c->d_avgdist,
                     c->d_num_genes, c->d_tmp_a, c->d_tmp_b, c->d_weights, c->d_cum, c->d_err, c->d_inter, c->d_rowK,
                     c->d_gain_thr, c->tab_mut.d_thr, c->tab_hr.d_thr, c->d_r1, c->d_r2, c->d_cd, c->d_in, c->d_un,
-                    c->d_replay, c->d_hkeys, c->d_hvals, c->d_stage, c->d_groups, c->d_partner, c->d_orig, c->d_dump_counters, c->d_mut_row, c->d_mut_site,
+                    c->d_replay, c->d_hkeys, c->d_hvals, c->d_stage, c->d_groups, c->d_partner, c->d_orig, c->d_batches, c->d_tile_slots, c->d_tile_orig, c->d_dump_counters, c->d_mut_row, c->d_mut_site,
                     c->d_mut_seq, c->d_mut_allele, c->d_hr_rec, c->d_hr_locus, c->d_hr_donor, c->d_hr_seq,
                     c->d_hr_value, c->d_dump_flip, c->d_dump_gain};
     for (void *p : ptrs)
@@ -651,6 +656,7 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
 
         // launch shape of the fused core kernel: persistent, grid = SMs x resident CTAs
         c->core_smem = core_step_smem_bytes(c->tab_mut.size, c->tab_hr.size);
+        CU(c, cudaFuncSetAttribute(pair_core_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes()));
         CU(c, cudaFuncSetAttribute(core_step_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->core_smem));
         CU(c, cudaFuncSetAttribute(core_step_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->core_smem));
         CU(c, cudaFuncSetAttribute(core_step_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->core_smem));
@@ -1085,45 +1091,122 @@ static int ensure_pairs(pansim_ctx *c, size_t n)
     return 0;
 }
 
-// Build (or reuse) the row-stationary plan for this pair list.
+// Build (or reuse) the plan for this pair list: pairs whose 32-row block pair holds enough
+// pairs go to the shared-memory tile kernel, the rest to the row-stationary group kernel.
 static int ensure_pair_plan(pansim_ctx *c, const uint32_t *r1, const uint32_t *r2, size_t P)
 {
-    if (c->plan_r1.size() == P && c->plan_groups &&
+    if (c->plan_r1.size() == P && (c->plan_groups || c->plan_batches) &&
         memcmp(c->plan_r1.data(), r1, P * 4) == 0 && memcmp(c->plan_r2.data(), r2, P * 4) == 0)
         return 0;
-    // counting sort by first row
+    const uint32_t NB = (c->N + 31) / 32;
+    const size_t n_keys = (size_t)NB * NB;
+    std::vector<uint32_t> key(P);
+    std::vector<uint32_t> kcount;
+    // the shared-memory tile kernel is correct but measured slower than the row-stationary
+    // group kernel on B200 at cfg2 (3.1-3.5 ms vs 2.3 ms per 10^5 pairs): opt-in only
+    const bool use_tiles = getenv("PANSIM_TILES") != nullptr && n_keys <= (1u << 24);
+    if (use_tiles) {
+        kcount.assign(n_keys + 1, 0);
+        for (size_t k = 0; k < P; k++) {
+            const uint32_t bi = r1[k] >> 5, bj = r2[k] >> 5;
+            key[k] = std::min(bi, bj) * NB + std::max(bi, bj);
+            kcount[key[k] + 1]++;
+        }
+    }
+    const uint32_t dense_min = 24;     // below this a tile would stage rows it barely uses
+    // ---- dense part: tile batches ----
+    std::vector<TileBatch> batches;
+    std::vector<uint16_t> tslots;
+    std::vector<uint32_t> torig;
+    std::vector<uint8_t> is_dense(P, 0);
+    if (use_tiles) {
+        std::vector<uint32_t> kstart(kcount);
+        for (size_t i = 0; i < n_keys; i++) kstart[i + 1] += kstart[i];
+        std::vector<uint32_t> order(P), cur(kstart.begin(), kstart.end() - 1);
+        for (size_t k = 0; k < P; k++) order[cur[key[k]]++] = (uint32_t)k;
+        const uint32_t cols = (uint32_t)(c->core_stride / TILE_BYTES);
+        size_t n_dense_batches = 0;
+        for (size_t kk = 0; kk < n_keys; kk++) {
+            const uint32_t cnt = kstart[kk + 1] - kstart[kk];
+            if (cnt >= dense_min) n_dense_batches += (cnt + TILE_BATCH - 1) / TILE_BATCH;
+        }
+        // split the column range so that there are a few waves of CTAs
+        uint32_t col_split = 1;
+        const size_t want = (size_t)c->sm_count * 2 * 3;
+        while (n_dense_batches && n_dense_batches * col_split < want && col_split < 8 && cols / (col_split * 2) >= 16) col_split *= 2;
+        for (size_t kk = 0; kk < n_keys; kk++) {
+            const uint32_t cnt = kstart[kk + 1] - kstart[kk];
+            if (cnt < dense_min) continue;
+            const uint32_t ba = (uint32_t)(kk / NB), bb = (uint32_t)(kk % NB);
+            // slots of each pair, sorted by first slot (row-stationary reuse inside a warp)
+            std::vector<std::pair<uint32_t, uint32_t>> v;      // (slot_a << 8 | slot_b, orig)
+            v.reserve(cnt);
+            for (uint32_t t = kstart[kk]; t < kstart[kk + 1]; t++) {
+                const uint32_t k = order[t];
+                is_dense[k] = 1;
+                auto slot = [&](uint32_t row) { return (row >> 5) == ba ? (row & 31u) : 32u + (row & 31u); };
+                v.push_back({(slot(r1[k]) << 8) | slot(r2[k]), k});
+            }
+            std::sort(v.begin(), v.end());
+            for (uint32_t f = 0; f < cnt; f += TILE_BATCH) {
+                const uint32_t n = std::min<uint32_t>(TILE_BATCH, cnt - f);
+                for (uint32_t sp = 0; sp < col_split; sp++) {
+                    TileBatch b;
+                    b.block_a = ba; b.block_b = bb; b.first = (uint32_t)tslots.size(); b.count = n;
+                    b.col_begin = (uint32_t)((uint64_t)cols * sp / col_split);
+                    b.col_end = (uint32_t)((uint64_t)cols * (sp + 1) / col_split);
+                    batches.push_back(b);
+                }
+                for (uint32_t t = f; t < f + n; t++) {
+                    tslots.push_back((uint16_t)((v[t].first >> 8) | ((v[t].first & 0xFFu) << 8)));   // low = slot_a
+                    torig.push_back(v[t].second);
+                }
+            }
+        }
+    }
+    // ---- sparse part: row-stationary groups (counting sort by first row) ----
     std::vector<uint32_t> start(c->N + 1, 0);
-    for (size_t k = 0; k < P; k++) start[r1[k] + 1]++;
+    for (size_t k = 0; k < P; k++) if (!is_dense[k]) start[r1[k] + 1]++;
     for (uint32_t i = 0; i < c->N; i++) start[i + 1] += start[i];
-    std::vector<uint32_t> partner(P), orig(P), cursor(start.begin(), start.end() - 1);
+    const size_t n_sparse = start[c->N];
+    std::vector<uint32_t> partner(n_sparse), orig(n_sparse), cursor(start.begin(), start.end() - 1);
     for (size_t k = 0; k < P; k++) {
+        if (is_dense[k]) continue;
         const uint32_t pos = cursor[r1[k]]++;
         partner[pos] = r2[k];
         orig[pos] = (uint32_t)k;
     }
     std::vector<PairGroup> groups;
-    groups.reserve(P / PAIR_GROUP + c->N);
     for (uint32_t i = 0; i < c->N; i++)
         for (uint32_t f = start[i]; f < start[i + 1]; f += PAIR_GROUP)
             groups.push_back(PairGroup{i, f, std::min<uint32_t>(PAIR_GROUP, start[i + 1] - f)});
-    if (groups.size() > c->plan_cap_groups) {
-        if (c->d_groups) cudaFree(c->d_groups);
-        c->d_groups = nullptr; c->plan_cap_groups = 0;
-        if (cudaMalloc(&c->d_groups, groups.size() * sizeof(PairGroup)) != cudaSuccess) FAIL(c, PANSIM_ERR_NOMEM, "cudaMalloc for the pair plan failed");
-        c->plan_cap_groups = groups.size();
-    }
-    if (P > c->plan_cap_pairs) {
-        if (c->d_partner) cudaFree(c->d_partner);
-        if (c->d_orig) cudaFree(c->d_orig);
-        c->d_partner = c->d_orig = nullptr; c->plan_cap_pairs = 0;
-        if (cudaMalloc(&c->d_partner, P * 4) != cudaSuccess || cudaMalloc(&c->d_orig, P * 4) != cudaSuccess) FAIL(c, PANSIM_ERR_NOMEM, "cudaMalloc for the pair plan failed");
-        c->plan_cap_pairs = P;
-    }
-    CU(c, cudaMemcpyAsync(c->d_groups, groups.data(), groups.size() * sizeof(PairGroup), cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaMemcpyAsync(c->d_partner, partner.data(), P * 4, cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaMemcpyAsync(c->d_orig, orig.data(), P * 4, cudaMemcpyHostToDevice, c->stream));
+
+    auto grow = [&](void **ptr, size_t &cap, size_t need, size_t elem) -> int {
+        if (need <= cap) return 0;
+        if (*ptr) cudaFree(*ptr);
+        *ptr = nullptr; cap = 0;
+        if (cudaMalloc(ptr, need * elem) != cudaSuccess) return -1;
+        cap = need;
+        return 0;
+    };
+    size_t cap_tp2 = c->plan_cap_tile_pairs, cap_p2 = c->plan_cap_pairs;
+    if (grow((void **)&c->d_groups, c->plan_cap_groups, groups.size(), sizeof(PairGroup)) ||
+        grow((void **)&c->d_partner, c->plan_cap_pairs, n_sparse, 4) || grow((void **)&c->d_orig, cap_p2, n_sparse, 4) ||
+        grow((void **)&c->d_batches, c->plan_cap_batches, batches.size(), sizeof(TileBatch)) ||
+        grow((void **)&c->d_tile_slots, c->plan_cap_tile_pairs, tslots.size(), 2) ||
+        grow((void **)&c->d_tile_orig, cap_tp2, torig.size(), 4))
+        FAIL(c, PANSIM_ERR_NOMEM, "cudaMalloc for the pair plan failed");
+    auto up = [&](void *dst, const void *src, size_t bytes) { if (bytes) cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream); };
+    up(c->d_groups, groups.data(), groups.size() * sizeof(PairGroup));
+    up(c->d_partner, partner.data(), n_sparse * 4);
+    up(c->d_orig, orig.data(), n_sparse * 4);
+    up(c->d_batches, batches.data(), batches.size() * sizeof(TileBatch));
+    up(c->d_tile_slots, tslots.data(), tslots.size() * 2);
+    up(c->d_tile_orig, torig.data(), torig.size() * 4);
     CU(c, cudaStreamSynchronize(c->stream));      // the host vectors go out of scope
+    CU(c, cudaGetLastError());
     c->plan_groups = groups.size();
+    c->plan_batches = batches.size();
     c->plan_r1.assign(r1, r1 + P);
     c->plan_r2.assign(r2, r2 + P);
     return 0;
@@ -1154,12 +1237,19 @@ static int pair_counts_impl(pansim_ctx *c, const uint32_t *r1, const uint32_t *r
             uint32_t chunk_vec4 = (uint32_t)(chunk_bytes / 16);
             uint32_t n_chunks = (row_vec4 + chunk_vec4 - 1) / chunk_vec4;
             if (n_chunks > 65535) { n_chunks = 65535; chunk_vec4 = (row_vec4 + n_chunks - 1) / n_chunks; chunk_vec4 = ((chunk_vec4 + 255) / 256) * 256; n_chunks = (row_vec4 + chunk_vec4 - 1) / chunk_vec4; }
-            if (n_chunks > 1) CU(c, cudaMemsetAsync(d_cd, 0, P * 4, c->stream));
-            const uint32_t gx = (uint32_t)std::min<size_t>(c->plan_groups, 1u << 20);
-            pair_core_grouped_kernel<<<dim3(gx, n_chunks), PAIR_THREADS, 0, c->stream>>>(
-                c->core[c->core_cur], c->core_stride, chunk_vec4, row_vec4, c->d_groups, (uint32_t)c->plan_groups,
-                c->d_partner, c->d_orig, d_cd);
-            LAUNCH_CHECK(c);
+            CU(c, cudaMemsetAsync(d_cd, 0, P * 4, c->stream));      // both kernels accumulate with integer atomics
+            if (c->plan_batches) {
+                pair_core_tile_kernel<<<(uint32_t)c->plan_batches, TILE_THREADS, tile_smem_bytes(), c->stream>>>(
+                    c->core[c->core_cur], c->core_stride, c->N, c->d_batches, c->d_tile_slots, c->d_tile_orig, d_cd);
+                LAUNCH_CHECK(c);
+            }
+            if (c->plan_groups) {
+                const uint32_t gx = (uint32_t)std::min<size_t>(c->plan_groups, 1u << 20);
+                pair_core_grouped_kernel<<<dim3(gx, n_chunks), PAIR_THREADS, 0, c->stream>>>(
+                    c->core[c->core_cur], c->core_stride, chunk_vec4, row_vec4, c->d_groups, (uint32_t)c->plan_groups,
+                    c->d_partner, c->d_orig, d_cd);
+                LAUNCH_CHECK(c);
+            }
         }
     }
     if (d_in || d_un) {
