@@ -49,7 +49,7 @@ namespace pansim {
 constexpr int CS_WARPS = 8;
 constexpr int CS_STAGES = 2;
 constexpr int CS_THREADS = CS_WARPS * 32;
-constexpr int HRQ_CAP = 32;                       // HR queue entries per warp
+constexpr int HRQ_CAP = 64;                       // HR queue entries per warp
 constexpr uint32_t POISSON_TABLE_MAX = 1024;
 
 struct CoreStepArgs {
@@ -61,6 +61,8 @@ struct CoreStepArgs {
     uint64_t row_stride;      // bytes
     uint32_t region0;         // global index of local region 0
     uint32_t items_per_warp;  // (row, region) items per warp; a CTA covers CS_WARPS * items_per_warp consecutive items
+    uint32_t snapshot_pass;   // 1 = second pass of the two-pass mode: old_state already holds the gathered and
+                              // mutated rows (identity gather, no SNPs; HR donors are read from it directly)
     uint64_t site_limit;      // global site index one past the last valid site of this shard
     uint2 key;
     uint32_t gen;
@@ -331,7 +333,7 @@ __global__ void __launch_bounds__(CS_THREADS, 4) core_step_kernel(const CoreStep
     uint32_t l_row = gw / a.n_regions, l_reg = gw % a.n_regions, l_j = 0;
 #define PANSIM_ISSUE_LOAD()                                                                                  \
     do {                                                                                                     \
-        const uint8_t *src_ = a.old_state + (uint64_t)a.parents[l_row] * a.row_stride +                      \
+        const uint8_t *src_ = a.old_state + (uint64_t)(a.snapshot_pass ? l_row : a.parents[l_row]) * a.row_stride + \
                               (uint64_t)l_reg * REGION_BYTES;                                                \
         const uint32_t s_ = l_j % CS_STAGES;                                                                 \
         mbar_arrive_expect_tx(&bars[s_], REGION_BYTES);                                                      \
@@ -371,7 +373,7 @@ __global__ void __launch_bounds__(CS_THREADS, 4) core_step_kernel(const CoreStep
         uint4 hg0 = make_uint4(0, 0, 0, 0), mc0 = make_uint4(0, 0, 0, 0), mc1 = make_uint4(0, 0, 0, 0);
         uint32_t k = 0, kh = 0;
         if (RNG) {
-            if (a.mut_nsub) {
+            if (a.mut_nsub && !a.snapshot_pass) {
                 mc0 = snp_call(mctr, a.key, 0);
                 mc1 = snp_call(mctr, a.key, 1);
                 k = stream_count(mctr, a.key, mc0.x, tab_mut, a.mut_nsub, a.mut_kmax);
@@ -386,7 +388,7 @@ __global__ void __launch_bounds__(CS_THREADS, 4) core_step_kernel(const CoreStep
 
         if (RNG) {
             // ---- SNP mutation (population.rs:512-539) ----
-            if (a.mut_nsub) {
+            if (a.mut_nsub && !a.snapshot_pass) {
                 const MutApply<DUMP> f{smem_u32(sw) + lane * 4u, lane, pos_lim, k, row, reg_site0, &a};
                 const uint32_t kw = __reduce_max_sync(0xffffffffu, k);      // warp-uniform trip counts
 #pragma unroll 1
@@ -419,12 +421,12 @@ __global__ void __launch_bounds__(CS_THREADS, 4) core_step_kernel(const CoreStep
                 for (uint32_t win = 0; win < tot; win += HRQ_CAP) {
                     // 1) owners enqueue their events that fall in [win, win + HRQ_CAP)
                     if (kh && pre + kh > win && pre < win + HRQ_CAP) {
+                        const uint32_t e_lo = pre >= win ? 0u : win - pre;
+                        const uint32_t e_hi = min(kh, win + HRQ_CAP - pre);
                         uint4 g = hg0;
                         uint32_t have_call = 0;
-                        for (uint32_t e = 0; e < kh; e++) {
+                        for (uint32_t e = e_lo; e < e_hi; e++) {
                             const uint32_t gi = pre + e;
-                            if (gi < win) continue;
-                            if (gi >= win + HRQ_CAP) break;
                             const uint32_t call = e >> 1;
                             if (call != have_call) {
                                 uint4 c = hctr;
@@ -452,9 +454,9 @@ __global__ void __launch_bounds__(CS_THREADS, 4) core_step_kernel(const CoreStep
                                 const uint32_t widx = ((pos >> 4) << 5) + owner;
                                 const uint32_t sh = (pos & 15u) * 2u;
                                 const uint32_t *dsrc = reinterpret_cast<const uint32_t *>(
-                                    a.old_state + (uint64_t)a.parents[d] * a.row_stride + (uint64_t)reg * REGION_BYTES);
+                                    a.old_state + (uint64_t)(a.snapshot_pass ? d : a.parents[d]) * a.row_stride + (uint64_t)reg * REGION_BYTES);
                                 uint32_t val = (__ldg(dsrc + widx) >> sh) & 3u;
-                                if (a.mut_nsub) {
+                                if (a.mut_nsub && !a.snapshot_pass) {
                                     const uint32_t m = snp_probe(greg * 32u + owner, d, pos, a, tab_mut);
                                     if (m) val = m;
                                 }

@@ -121,6 +121,8 @@ struct pansim_ctx {
     uint32_t acc_stride_words = 0, acc_words = 0;
 
     uint8_t *core[2] = {nullptr, nullptr};
+    uint8_t *core_snap = nullptr;    // two-pass mode: gathered + mutated rows, before recombination
+    bool two_pass_hr = false;
     uint32_t *acc[2] = {nullptr, nullptr};
     int core_cur = 0, acc_cur = 0;
     bool has_core = false, has_acc = false;
@@ -411,12 +413,8 @@ void fill_core_args(pansim_ctx *c, CoreStepArgs &a, uint32_t gen)
     a.d_hr_value = c->d_hr_value;
 }
 
-int launch_core_step(pansim_ctx *c, uint32_t gen, bool rng, cudaStream_t st)
+int launch_core_kernel(pansim_ctx *c, const CoreStepArgs &a, bool any_rng, cudaStream_t st)
 {
-    if (c->Ll == 0) return 0;
-    CoreStepArgs a;
-    fill_core_args(c, a, gen);
-    const bool any_rng = rng && (a.mut_nsub || a.hr_nsub);
     if (!any_rng) {
         core_step_kernel<false, false><<<c->core_grid, CS_THREADS, c->core_smem, st>>>(a);
     } else if (c->dump_enabled) {
@@ -425,6 +423,31 @@ int launch_core_step(pansim_ctx *c, uint32_t gen, bool rng, cudaStream_t st)
         core_step_kernel<true, false><<<c->core_grid, CS_THREADS, c->core_smem, st>>>(a);
     }
     LAUNCH_CHECK(c);
+    return 0;
+}
+
+int launch_core_step(pansim_ctx *c, uint32_t gen, bool rng, cudaStream_t st)
+{
+    if (c->Ll == 0) return 0;
+    CoreStepArgs a;
+    fill_core_args(c, a, gen);
+    const bool any_rng = rng && (a.mut_nsub || a.hr_nsub);
+    if (any_rng && c->two_pass_hr && a.hr_nsub) {
+        // Heavy recombination: recomputing the donor's SNPs for every HR event would dominate.
+        // Pass 1 writes the gathered + mutated rows (the snapshot of population.rs:693-695) to a
+        // third buffer, pass 2 streams it into the new state applying the HR events, reading
+        // donor alleles straight from the snapshot. Same events (same counters) as the fused pass.
+        CoreStepArgs p1 = a;
+        p1.new_state = c->core_snap;
+        p1.hr_nsub = 0;
+        if (int rc = launch_core_kernel(c, p1, true, st)) return rc;
+        CoreStepArgs p2 = a;
+        p2.old_state = c->core_snap;
+        p2.snapshot_pass = 1;
+        if (int rc = launch_core_kernel(c, p2, true, st)) return rc;
+    } else {
+        if (int rc = launch_core_kernel(c, a, any_rng, st)) return rc;
+    }
     c->core_cur ^= 1;
     return 0;
 }
@@ -526,7 +549,7 @@ void pansim_destroy(pansim_ctx *c)
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->stream_core) cudaStreamSynchronize(c->stream_core);
-    void *ptrs[] = {c->core[0], c->core[1], c->acc[0], c->acc[1], c->d_parents_buf[0], c->d_parents_buf[1], c->d_parents_buf[2], c->d_lw, c->d_logfit, c->d_avgdist,
+    void *ptrs[] = {c->core[0], c->core[1], c->core_snap, c->acc[0], c->acc[1], c->d_parents_buf[0], c->d_parents_buf[1], c->d_parents_buf[2], c->d_lw, c->d_logfit, c->d_avgdist,
                     c->d_num_genes, c->d_tmp_a, c->d_tmp_b, c->d_weights, c->d_cum, c->d_err, c->d_inter, c->d_rowK,
                     c->d_gain_thr, c->tab_mut.d_thr, c->tab_hr.d_thr, c->d_r1, c->d_r2, c->d_cd, c->d_in, c->d_un,
                     c->d_replay, c->d_hkeys, c->d_hvals, c->d_stage, c->d_groups, c->d_partner, c->d_orig, c->d_batches, c->d_tile_slots, c->d_tile_orig, c->d_dump_counters, c->d_mut_row, c->d_mut_site,
@@ -634,6 +657,13 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
             }
             CU(c, cudaMalloc(&c->acc[b], acc_bytes));
             CU(c, cudaMemset(c->acc[b], 0, acc_bytes));
+        }
+        // two-pass recombination when a site block expects more than ~2 HR events per generation
+        c->two_pass_hr = rate_hr * BLOCK_SITES > 2.0;
+        if (const char *e = getenv("PANSIM_TWO_PASS_HR")) c->two_pass_hr = atoi(e) != 0;
+        if (c->two_pass_hr && core_bytes) {
+            if (cudaMalloc(&c->core_snap, core_bytes) != cudaSuccess) FAIL(c, PANSIM_ERR_NOMEM, "cudaMalloc of %zu bytes (core snapshot) failed", core_bytes);
+            CU(c, cudaMemset(c->core_snap, 0, core_bytes));
         }
         const size_t n = c->N;
         for (int i = 0; i < 3; i++) CU(c, cudaMalloc(&c->d_parents_buf[i], n * 4));

@@ -479,3 +479,21 @@ def test_state_required_and_error_codes():
         assert e.value.code == -5
     with pytest.raises(pb.PansimError):
         make(pb.Params(pop_size=1, core_size=1000, pan_genes=10, core_genes=0, HR_rate=1.0))   # HR needs N >= 2
+
+
+def test_two_pass_recombination_equals_fused(monkeypatch):
+    """Heavy-HR two-pass mode (snapshot buffer + direct donor reads) draws the same events and
+    must give the same state as the fused single pass with snapshot recomputation."""
+    p = small_params(HR_rate=1.0, core_mu=0.2, core_size=8192 * 2 + 999, n_gen=3)
+    d = pb.derive(p)
+    rng = np.random.default_rng(21)
+    core, acc = random_state(rng, p.pop_size, p.core_size, d.pan_size)
+    states = []
+    for mode in ("0", "1"):
+        monkeypatch.setenv("PANSIM_TWO_PASS_HR", mode)
+        with make(p) as sim:
+            sim.upload(core, acc)
+            sim.run_generations(0, p.n_gen)
+            states.append((sim.download_core(), sim.download_acc()))
+    assert (states[0][0] == states[1][0]).all() and (states[0][1] == states[1][1]).all()
+    assert (states[0][0] != core).any()
