@@ -31,9 +31,8 @@
 // its first 20 SNP events (a lane that drew more handles the excess in a short
 // tail), positions are extracted with compile-time byte selects, the snapshot
 // probe compares four position bytes per instruction, and the HR events of all
-// 32 lanes are compacted into a
-// shared-memory queue so that the expensive snapshot recomputation runs with
-// all lanes busy.
+// 32 lanes are renumbered lane-major and handled one per lane, so that the
+// expensive snapshot recomputation runs with all lanes busy.
 //
 // Data movement: warp-private TMA pipelines. Each warp owns CS_STAGES 2 KiB
 // shared-memory buffers; lane 0 issues cp.async.bulk global->shared for the
@@ -49,7 +48,6 @@ namespace pansim {
 constexpr int CS_WARPS = 8;
 constexpr int CS_STAGES = 2;
 constexpr int CS_THREADS = CS_WARPS * 32;
-constexpr int HRQ_CAP = 64;                       // HR queue entries per warp
 constexpr uint32_t POISSON_TABLE_MAX = 1024;
 
 struct CoreStepArgs {
@@ -82,7 +80,6 @@ struct CoreStepArgs {
 static inline size_t core_step_smem_bytes(uint32_t mut_size, uint32_t hr_size)
 {
     return (size_t)CS_WARPS * CS_STAGES * REGION_BYTES + (size_t)CS_WARPS * CS_STAGES * sizeof(uint64_t) +
-           (size_t)CS_WARPS * HRQ_CAP * sizeof(uint2) +
            (size_t)(2 * GUIDE_ENTRIES + mut_size + hr_size) * sizeof(uint32_t);
 }
 
@@ -188,12 +185,13 @@ struct MutApply {
     // apply the first n_ev events of one part (positions packed in p0..p4, 4 per word);
     // `base` = index of its first event. Loop over chunks of 5 events = one digit byte.
     __device__ __forceinline__ void part(uint32_t p0, uint32_t p1, uint32_t p2, uint32_t p3, uint32_t p4,
-                                         uint32_t n_ev, uint32_t tp, uint32_t tr, uint32_t base, uint4 ctr,
-                                         uint2 key, uint32_t tag0) const
+                                         uint32_t n_ev, uint32_t kw, uint32_t tp, uint32_t tr, uint32_t base,
+                                         uint4 ctr, uint2 key, uint32_t tag0) const
     {
         const uint32_t kk = min(k, base + n_ev);           // events of this part that exist for this lane
+        const uint32_t n_run = min(n_ev, kw - base);       // ... and for the busiest lane of the warp
 #pragma unroll 1
-        for (uint32_t c = 0; 5u * c < n_ev; c++) {
+        for (uint32_t c = 0; 5u * c < n_run; c++) {
             uint32_t v = digit_byte(tp, tr, c, ctr, key, tag0 + c);
 #pragma unroll
             for (int i = 0; i < 5; i++) {
@@ -295,14 +293,12 @@ __global__ void __launch_bounds__(CS_THREADS, 4) core_step_kernel(const CoreStep
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     uint64_t *bars_all = reinterpret_cast<uint64_t *>(smem_raw + (size_t)CS_WARPS * CS_STAGES * REGION_BYTES);
-    uint2 *hrq_all = reinterpret_cast<uint2 *>(bars_all + CS_WARPS * CS_STAGES);
-    uint32_t *tab_mut = reinterpret_cast<uint32_t *>(hrq_all + CS_WARPS * HRQ_CAP);
+    uint32_t *tab_mut = reinterpret_cast<uint32_t *>(bars_all + CS_WARPS * CS_STAGES);
     uint32_t *tab_hr = tab_mut + GUIDE_ENTRIES + a.mut_size;
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t *stages = smem_raw + (size_t)warp * CS_STAGES * REGION_BYTES;
     uint64_t *bars = bars_all + warp * CS_STAGES;
-    uint2 *hrq = hrq_all + warp * HRQ_CAP;
 
     if (RNG) {
 #pragma unroll 1
@@ -397,18 +393,21 @@ __global__ void __launch_bounds__(CS_THREADS, 4) core_step_kernel(const CoreStep
                         mc0 = snp_call(mctr, a.key, 3u * g);
                         mc1 = snp_call(mctr, a.key, 3u * g + 1u);
                     }
-                    f.part(mc0.w, mc1.x, mc1.y, mc1.z, mc1.w, SNP_PART0, mc0.y, mc0.z, base, mctr, a.key, g * 8u);
+                    f.part(mc0.w, mc1.x, mc1.y, mc1.z, mc1.w, SNP_PART0, kw, mc0.y, mc0.z, base, mctr, a.key, g * 8u);
                     if (kw > base + SNP_PART0) {
                         const uint4 mc2 = snp_call(mctr, a.key, 3u * g + 2u);
-                        f.part(mc2.z, mc2.w, 0u, 0u, 0u, SNP_GROUP - SNP_PART0, mc2.x, mc2.y, base + SNP_PART0,
+                        f.part(mc2.z, mc2.w, 0u, 0u, 0u, SNP_GROUP - SNP_PART0, kw, mc2.x, mc2.y, base + SNP_PART0,
                                mctr, a.key, g * 8u + 4u);
                     }
                 }
             }
 
             // ---- homologous recombination (population.rs:544-751, core) ----
+            // The warp's events are numbered lane-major (owner lane, then draw order) and handled
+            // 32 at a time, one event per lane, so the snapshot recomputation runs with all lanes
+            // busy. Events of one owner stay in draw order: within a window they are applied in
+            // rounds of increasing rank, and windows are processed in order (later wins, :745).
             if (a.hr_nsub) {
-                // exclusive prefix of event counts over the warp -> global event index
                 uint32_t incl = kh;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
@@ -418,62 +417,57 @@ __global__ void __launch_bounds__(CS_THREADS, 4) core_step_kernel(const CoreStep
                 const uint32_t pre = incl - kh;
                 const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
                 const uint32_t n_other = a.n_rows - 1u;
-                for (uint32_t win = 0; win < tot; win += HRQ_CAP) {
-                    // 1) owners enqueue their events that fall in [win, win + HRQ_CAP)
-                    if (kh && pre + kh > win && pre < win + HRQ_CAP) {
-                        const uint32_t e_lo = pre >= win ? 0u : win - pre;
-                        const uint32_t e_hi = min(kh, win + HRQ_CAP - pre);
-                        uint4 g = hg0;
-                        uint32_t have_call = 0;
-                        for (uint32_t e = e_lo; e < e_hi; e++) {
-                            const uint32_t gi = pre + e;
-                            const uint32_t call = e >> 1;
-                            if (call != have_call) {
-                                uint4 c = hctr;
-                                c.w += call;
-                                g = philox4x32_10(c, a.key);
-                                have_call = call;
+#pragma unroll 1
+                for (uint32_t win = 0; win < tot; win += 32) {
+                    const uint32_t q = win + lane;
+                    const bool active = q < tot;
+                    // owner = first lane whose inclusive count exceeds q
+                    uint32_t owner = 0;
+#pragma unroll
+                    for (int step = 16; step > 0; step >>= 1) {
+                        const uint32_t v = __shfl_sync(0xffffffffu, incl, (owner + step - 1) & 31u);
+                        if (v <= q && owner + step <= 31u) owner += step;
+                    }
+                    const uint32_t o_pre = __shfl_sync(0xffffffffu, pre, owner);
+                    const uint32_t o_lim = __shfl_sync(0xffffffffu, pos_lim, owner);
+                    uint4 g;
+                    g.x = 0;
+                    g.y = __shfl_sync(0xffffffffu, hg0.y, owner);
+                    g.z = __shfl_sync(0xffffffffu, hg0.z, owner);
+                    g.w = __shfl_sync(0xffffffffu, hg0.w, owner);
+                    const uint32_t e = q - o_pre;                       // draw index within the owner's stream
+                    const uint32_t rank = q - max(o_pre, win);          // order among the owner's events of this window
+                    uint32_t pos = 0, d = 0, val = 0;
+                    bool ok = false;
+                    if (active) {
+                        const uint4 octr = make_ctr(greg * 32u + owner, row, a.gen, STREAM_CORE_HR);
+                        const uint32_t call = e >> 1;
+                        if (call) {                                      // third and later events: rare
+                            uint4 c = octr;
+                            c.w += call;
+                            g = philox4x32_10(c, a.key);
+                        }
+                        hr_event(g, call == 0, e & 1u, n_other, octr, a.key, e, pos, d);
+                        d += (d >= row) ? 1u : 0u;                       // population.rs:616-619
+                        ok = pos < o_lim;
+                        if (ok) {
+                            // donor's allele after gather and SNPs, before any HR (snapshot, :693-695)
+                            const uint32_t widx = ((pos >> 4) << 5) + owner;
+                            const uint32_t *dsrc = reinterpret_cast<const uint32_t *>(
+                                a.old_state + (uint64_t)(a.snapshot_pass ? d : a.parents[d]) * a.row_stride +
+                                (uint64_t)reg * REGION_BYTES);
+                            val = (__ldg(dsrc + widx) >> ((pos & 15u) * 2u)) & 3u;
+                            if (a.mut_nsub && !a.snapshot_pass) {
+                                const uint32_t m = snp_probe(greg * 32u + owner, d, pos, a, tab_mut);
+                                if (m) val = m;
                             }
-                            uint32_t pos, d;
-                            hr_event(g, call == 0, e & 1u, n_other, hctr, a.key, e, pos, d);
-                            d += (d >= row) ? 1u : 0u;                  // population.rs:616-619
-                            const uint32_t ok = pos < pos_lim ? 1u : 0u;
-                            hrq[gi - win] = make_uint2(d, pos | (lane << 8) | (ok << 13));
                         }
                     }
-                    __syncwarp();
-                    // 2) all lanes: snapshot value of queue entries (donor after SNPs, before HR)
-                    const uint32_t n_q = min((uint32_t)HRQ_CAP, tot - win);
-                    for (uint32_t q0 = 0; q0 < n_q; q0 += 32) {
-                        const uint32_t q = q0 + lane;
-                        if (q < n_q) {
-                            const uint2 ent = hrq[q];
-                            if ((ent.y >> 13) & 1u) {
-                                const uint32_t pos = ent.y & 255u, owner = (ent.y >> 8) & 31u;
-                                const uint32_t d = ent.x;
-                                const uint32_t widx = ((pos >> 4) << 5) + owner;
-                                const uint32_t sh = (pos & 15u) * 2u;
-                                const uint32_t *dsrc = reinterpret_cast<const uint32_t *>(
-                                    a.old_state + (uint64_t)(a.snapshot_pass ? d : a.parents[d]) * a.row_stride + (uint64_t)reg * REGION_BYTES);
-                                uint32_t val = (__ldg(dsrc + widx) >> sh) & 3u;
-                                if (a.mut_nsub && !a.snapshot_pass) {
-                                    const uint32_t m = snp_probe(greg * 32u + owner, d, pos, a, tab_mut);
-                                    if (m) val = m;
-                                }
-                                hrq[q].y = ent.y | (val << 30);        // value parked in bits 30..31
-                            }
-                        }
-                    }
-                    __syncwarp();
-                    // 3) owners apply their events of this window in draw order (later wins)
-                    if (kh && pre + kh > win && pre < win + HRQ_CAP) {
-                        const uint32_t e_lo = pre >= win ? 0u : win - pre;
-                        const uint32_t e_hi = min(kh, win + HRQ_CAP - pre);
-                        for (uint32_t e = e_lo; e < e_hi; e++) {
-                            const uint2 ent = hrq[pre + e - win];
-                            if (!((ent.y >> 13) & 1u)) continue;
-                            const uint32_t pos = ent.y & 255u, val = ent.y >> 30;
-                            const uint32_t widx = ((pos >> 4) << 5) + lane;
+                    const uint32_t rmax = __reduce_max_sync(0xffffffffu, ok ? rank : 0u);
+#pragma unroll 1
+                    for (uint32_t r = 0; r <= rmax; r++) {
+                        if (ok && rank == r) {
+                            const uint32_t widx = ((pos >> 4) << 5) + owner;
                             const uint32_t sh = (pos & 15u) * 2u;
                             uint32_t w = sw[widx];
                             w = (w & ~(3u << sh)) | (val << sh);
@@ -483,15 +477,16 @@ __global__ void __launch_bounds__(CS_THREADS, 4) core_step_kernel(const CoreStep
                                 if (slot < a.dump_cap) {
                                     a.d_hr_rec[slot] = row;
                                     a.d_hr_locus[slot] = (uint32_t)(reg_site0 + widx * 16u + (pos & 15u));
-                                    a.d_hr_donor[slot] = ent.x;
+                                    a.d_hr_donor[slot] = d;
                                     a.d_hr_seq[slot] = e;
                                     a.d_hr_value[slot] = (uint8_t)(1u << val);
                                 }
                             }
                         }
+                        __syncwarp();
                     }
-                    __syncwarp();
                 }
+                __syncwarp();
             }
             // ragged last region: clear whatever events wrote beyond the end of the alignment
             if (pos_lim_any < 256u) {
