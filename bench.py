@@ -37,7 +37,8 @@ CFG2 = dict(pop_size=1000, core_size=1_200_000, pan_genes=6000, core_genes=2000,
 PEAK_FALLBACK_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
 # dram__bytes_read.sum + dram__bytes_write.sum of core_step_kernel from the committed
 # ncu --set full capture (profiles/), per launch at this workload; None until captured
-NCU_CORE_STEP_DRAM_BYTES = None
+NCU_CORE_STEP_DRAM_BYTES = 277.0e6   # 25.1 MB read + 251.9 MB written (profiles/r01_core_step_ncu_summary.txt, v6):
+# children of the same parent re-read that parent's row from L2, so DRAM reads stay far below N*L/4
 
 
 def selection_coefficients(rng, n, prop_positive, pos_lambda=10.0, neg_lambda=10.0):
@@ -123,7 +124,11 @@ def cpu_baseline_sample(n_gen: int, with_distances: bool, pairs: int):
     """Times the oracle port (CPU restatement of the reference, threads where the
     reference uses rayon) on a bounded sample of the same workload."""
     from oracle import binding as ob
-    threads = ob.lib().ora_max_threads()
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1, so ask the OS)
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        threads = os.cpu_count() or 1
     kw = dict(CFG2)
     kw["max_distances"] = pairs
     p = ob.default_params(threads=threads, **kw)
