@@ -46,7 +46,7 @@
 namespace pansim {
 
 constexpr int CS_WARPS = 8;
-constexpr int CS_STAGES = 2;
+constexpr int CS_STAGES = 3;
 constexpr int CS_THREADS = CS_WARPS * 32;
 constexpr uint32_t POISSON_TABLE_MAX = 1024;
 
