@@ -277,6 +277,24 @@ class Pansim:
         cd, it, un = self.pair_counts(range1, range2)
         return self.distances_from_counts(cd, it, un)
 
+    def iter_all_pairs(self, chunk_pairs: int = 4_000_000):
+        """Exact all-pairs mode (extension; the reference only samples pairs with replacement,
+        main.rs:413-427): yields (i, j, core_diff, inter, union) arrays covering every unordered
+        pair i < j exactly once, in chunks of about `chunk_pairs` pairs."""
+        N = self.N
+        i0 = 0
+        while i0 < N - 1:
+            # rows i0..i1-1 against all j > i
+            i1, n = i0, 0
+            while i1 < N - 1 and (n == 0 or n + (N - 1 - i1) <= chunk_pairs):
+                n += N - 1 - i1
+                i1 += 1
+            ii = np.repeat(np.arange(i0, i1, dtype=np.uint32), [N - 1 - i for i in range(i0, i1)])
+            jj = np.concatenate([np.arange(i + 1, N, dtype=np.uint32) for i in range(i0, i1)])
+            cd, it, un = self.pair_counts(ii, jj)
+            yield ii, jj, cd, it, un
+            i0 = i1
+
     def gene_counts(self) -> np.ndarray:
         out = np.empty(self.G, np.uint32)
         self._check(self._lib.pansim_gene_counts(self._h, _ptr(out)))

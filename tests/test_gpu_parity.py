@@ -497,3 +497,20 @@ def test_two_pass_recombination_equals_fused(monkeypatch):
             states.append((sim.download_core(), sim.download_acc()))
     assert (states[0][0] == states[1][0]).all() and (states[0][1] == states[1][1]).all()
     assert (states[0][0] != core).any()
+
+
+def test_all_pairs_mode_matches_oracle():
+    rng = np.random.default_rng(23)
+    N, L, G = 37, 5000, 90
+    core, acc = random_state(rng, N, L, G)
+    ocore, opan = ob.Population(core, True, 4), ob.Population(acc, False, 4)
+    seen = 0
+    with make(pb.Params(pop_size=N, core_size=L, pan_genes=G + 4, core_genes=4)) as sim:
+        sim.upload(core, acc)
+        for ii, jj, cd, it, un in sim.iter_all_pairs(chunk_pairs=200):
+            assert (ii < jj).all()
+            assert (cd == ocore.pair_counts(ii, jj)).all()
+            oi, ou = opan.pair_counts(ii, jj)
+            assert (it == oi).all() and (un == ou).all()
+            seen += len(ii)
+    assert seen == N * (N - 1) // 2
