@@ -514,3 +514,43 @@ def test_all_pairs_mode_matches_oracle():
             assert (it == oi).all() and (un == ou).all()
             seen += len(ii)
     assert seen == N * (N - 1) // 2
+
+
+def test_no_accessory_genome_and_tiny_shapes():
+    """pan_genes == core_genes -> zero accessory columns (population.rs:296 skips the fitness
+    term); single-site / single-gene shapes; one pair."""
+    p = pb.Params(pop_size=6, core_size=40, pan_genes=5, core_genes=5, n_gen=2, HGT_rate=0.0, core_mu=0.5, HR_rate=1.0)
+    assert pb.derive(p).pan_size == 0
+    rng = np.random.default_rng(3)
+    core = (1 << rng.integers(0, 4, (6, 40))).astype(np.uint8)
+    with make(p) as sim:
+        sim.upload(core, np.zeros((6, 0), np.uint8))
+        sim.run_generations(0, 3)
+        parents = sim.parents()
+        assert parents.max() < 6
+        out = sim.download_core()
+        assert set(np.unique(out)) <= {1, 2, 4, 8} and out.shape == (6, 40)
+        cd, it, un = sim.pair_counts([0], [1])
+        assert it[0] == 0 and un[0] == 0 and cd[0] == (out[0] != out[1]).sum()
+        assert sim.gene_frequencies().tolist() == [1.0] * 5
+    p1 = pb.Params(pop_size=2, core_size=1, pan_genes=2, core_genes=1, HR_rate=0.0, HGT_rate=0.0)
+    with make(p1) as sim:
+        sim.upload(np.array([[1], [8]], np.uint8), np.array([[1], [0]], np.uint8))
+        cd, it, un = sim.pair_counts([0, 1], [1, 0])
+        assert cd.tolist() == [1, 1] and it.tolist() == [0, 0] and un.tolist() == [1, 1]
+        sim.run_generations(0, 2)
+        assert sim.download_core().shape == (2, 1)
+
+
+def test_empty_pair_list_and_large_pair_batch():
+    rng = np.random.default_rng(4)
+    core, acc = random_state(rng, 50, 3000, 64)
+    with make(pb.Params(pop_size=50, core_size=3000, pan_genes=64, core_genes=0)) as sim:
+        sim.upload(core, acc)
+        cd, it, un = sim.pair_counts(np.zeros(0, np.uint32), np.zeros(0, np.uint32))
+        assert len(cd) == 0
+        r1, r2 = sample_pairs(rng, 50, 30000)        # many repeats of the same pairs
+        cd, it, un = sim.pair_counts(r1, r2)
+        assert (cd == ob.Population(core, True).pair_counts(r1, r2)).all()
+        with pytest.raises(pb.PansimError):
+            sim.pair_counts([0], [50])
