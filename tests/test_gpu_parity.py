@@ -481,16 +481,19 @@ def test_state_required_and_error_codes():
         make(pb.Params(pop_size=1, core_size=1000, pan_genes=10, core_genes=0, HR_rate=1.0))   # HR needs N >= 2
 
 
-def test_two_pass_recombination_equals_fused(monkeypatch):
-    """Heavy-HR two-pass mode (snapshot buffer + direct donor reads) draws the same events and
-    must give the same state as the fused single pass with snapshot recomputation."""
-    p = small_params(HR_rate=1.0, core_mu=0.2, core_size=8192 * 2 + 999, n_gen=3)
+@pytest.mark.parametrize("kw", [dict(HR_rate=1.0, core_mu=0.2), dict(HR_rate=0.05, core_mu=0.05),
+                                dict(HR_rate=0.3, core_mu=0.6)])
+def test_two_pass_recombination_equals_fused(monkeypatch, kw):
+    """The two ways the core step can schedule recombination draw the same events and must give
+    the same state: fused single pass (snapshot recomputed per event) and, for heavy HR, snapshot
+    buffer + second streaming pass with direct donor reads."""
+    p = small_params(core_size=8192 * 2 + 999, n_gen=3, pop_size=40, **kw)
     d = pb.derive(p)
     rng = np.random.default_rng(21)
     core, acc = random_state(rng, p.pop_size, p.core_size, d.pan_size)
     states = []
-    for mode in ("0", "1"):
-        monkeypatch.setenv("PANSIM_TWO_PASS_HR", mode)
+    for two_pass in ("0", "1"):
+        monkeypatch.setenv("PANSIM_TWO_PASS_HR", two_pass)
         with make(p) as sim:
             sim.upload(core, acc)
             sim.run_generations(0, p.n_gen)
