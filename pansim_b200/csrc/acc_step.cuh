@@ -27,13 +27,14 @@ struct AccArgs {
     uint32_t n_rows, n_genes, stride_words;
     uint2 key;
     uint32_t gen;
-    uint32_t n_comp;
-    uint32_t comp_lo[2], comp_hi[2];
-    uint32_t flip_thr[2];        // round(p_c * 2^32)
-    double hgt_scale[2];         // lambda_c / (N-1)
-    uint32_t *rowK;              // [2][n_rows] genes of compartment c present (post-mutation)
-    uint32_t *gain_thr;          // [n_genes]
-    uint32_t *dump_flip;         // optional [n_rows * stride_words]
+    // gene compartments (main.rs:341-367): scalars, not arrays, so that the kernels never index
+    // the parameter block dynamically (that would force a per-thread local copy of it)
+    uint32_t lo0, hi0, lo1, hi1;   // genes with weight 1.0 in compartment 0 / 1 (empty: lo == hi)
+    uint32_t flip_thr0, flip_thr1; // round(p_c * 2^32)
+    double hgt_scale0, hgt_scale1; // lambda_c / (N-1); 0 = off
+    double *rowInvK;               // [2][n_rows] 1 / (genes of compartment c present, post-mutation); 0 if none
+    uint32_t *gain_thr;            // [n_genes]
+    uint32_t *dump_flip;           // optional [n_rows * stride_words]
     uint32_t *dump_gain;
 };
 
@@ -49,36 +50,56 @@ __device__ __forceinline__ uint32_t comp_mask_for_word(uint32_t w, uint32_t lo, 
     return upto_b & ~upto_a;
 }
 
-// 32 Bernoulli bits for word w of row `row`: bit b set iff u_b < thr(gene 32w+b).
-// thr comes from per-gene thresholds `per_gene` (HGT) or per-compartment `ct` (flips).
+// Bernoulli(thr / 2^32) from a 16-bit uniform `u16` as the HIGH half of a 32-bit uniform; the low
+// half is only drawn (dedicated Philox call) in the 2^-16 case where the high halves tie, so the
+// decision is exactly `u32 < thr`.
+__device__ __noinline__ uint32_t bernoulli_low_half(uint32_t w, uint32_t row, uint32_t gen, uint32_t stream,
+                                                    uint2 key, uint32_t b)
+{
+    uint4 ctr = make_ctr(w, row, gen, stream);
+    ctr.w |= 0x100u + b;
+    return philox4x32_10(ctr, key).x & 0xFFFFu;
+}
+
+__device__ __forceinline__ bool bernoulli16(uint32_t u16, uint32_t thr, uint32_t w, uint32_t row, uint32_t gen,
+                                            uint32_t stream, uint2 key, uint32_t b)
+{
+    const uint32_t t_hi = thr >> 16, t_lo = thr & 0xFFFFu;
+    if (u16 != t_hi) return u16 < t_hi;
+    if (t_lo == 0) return false;
+    return bernoulli_low_half(w, row, gen, stream, key, b) < t_lo;
+}
+
+// 32 Bernoulli bits for word w of row `row`: bit b set iff uniform_b < thr(gene 32w+b). Four
+// Philox calls give the 32 high halves. thr: per-gene table (HGT) or per-compartment (flips).
 template <bool PER_GENE>
-__device__ __forceinline__ uint32_t bernoulli_word(const AccArgs &a, uint32_t stream, uint32_t row,
-                                                   uint32_t w, uint32_t active, const uint32_t *per_gene)
+__device__ __forceinline__ uint32_t bernoulli_word(const AccArgs &a, uint32_t stream, uint32_t row, uint32_t w,
+                                                   uint32_t active, uint32_t mask0, const uint32_t *per_gene)
 {
     uint32_t out = 0;
     if (!active) return 0;
-    const uint32_t m0 = PER_GENE ? 0u : comp_mask_for_word(w, a.comp_lo[0], a.comp_hi[0]);
 #pragma unroll 1
-    for (uint32_t q = 0; q < 8; q++) {
-        if (((active >> (4 * q)) & 0xFu) == 0) continue;
+    for (uint32_t q = 0; q < 4; q++) {
+        if (((active >> (8 * q)) & 0xFFu) == 0) continue;
         uint4 ctr = make_ctr(w, row, a.gen, stream);
         ctr.w |= q;
         const uint4 r = philox4x32_10(ctr, a.key);
         const uint32_t u[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-        for (uint32_t c = 0; c < 4; c++) {
-            const uint32_t b = 4 * q + c;
+        for (uint32_t c = 0; c < 8; c++) {
+            const uint32_t b = 8 * q + c;
+            const uint32_t u16 = (u[c >> 1] >> (16 * (c & 1))) & 0xFFFFu;
             uint32_t thr;
             if (PER_GENE) {
                 const uint32_t g = w * 32u + b;
                 thr = g < a.n_genes ? per_gene[g] : 0u;
             } else {
-                thr = ((m0 >> b) & 1u) ? a.flip_thr[0] : a.flip_thr[1];
+                thr = ((mask0 >> b) & 1u) ? a.flip_thr0 : a.flip_thr1;
             }
-            if (u[c] < thr) out |= 1u << b;
+            if (((active >> b) & 1u) && bernoulli16(u16, thr, w, row, a.gen, stream, a.key, b)) out |= 1u << b;
         }
     }
-    return out & active;
+    return out;
 }
 
 // gather + flips + per-row compartment popcounts. One warp per row.
@@ -92,17 +113,17 @@ __global__ void __launch_bounds__(256) acc_gather_flip_kernel(const AccArgs a)
     uint32_t *dst = a.new_state + (uint64_t)row * a.stride_words;
     uint32_t k0 = 0, k1 = 0;
     for (uint32_t w = lane; w < a.stride_words; w += 32) {
-        uint32_t m[2] = {0u, 0u};
-        for (uint32_t c = 0; c < a.n_comp; c++) m[c] = comp_mask_for_word(w, a.comp_lo[c], a.comp_hi[c]);
+        const uint32_t m0 = comp_mask_for_word(w, a.lo0, a.hi0);
+        const uint32_t m1 = comp_mask_for_word(w, a.lo1, a.hi1);
         uint32_t active = 0;
-        if (a.flip_thr[0]) active |= m[0];
-        if (a.flip_thr[1]) active |= m[1];
-        const uint32_t flips = bernoulli_word<false>(a, STREAM_ACC_FLIP, row, w, active, nullptr);
+        if (a.flip_thr0) active |= m0;
+        if (a.flip_thr1) active |= m1;
+        const uint32_t flips = bernoulli_word<false>(a, STREAM_ACC_FLIP, row, w, active, m0, nullptr);
         const uint32_t v = src[w] ^ flips;
         dst[w] = v;
         if (DUMP) a.dump_flip[(uint64_t)row * a.stride_words + w] = flips;
-        k0 += __popc(v & m[0]);
-        k1 += __popc(v & m[1]);
+        k0 += __popc(v & m0);
+        k1 += __popc(v & m1);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -110,39 +131,39 @@ __global__ void __launch_bounds__(256) acc_gather_flip_kernel(const AccArgs a)
         k1 += __shfl_xor_sync(0xffffffffu, k1, o);
     }
     if (lane == 0) {
-        a.rowK[row] = k0;
-        a.rowK[a.n_rows + row] = k1;
+        a.rowInvK[row] = k0 ? 1.0 / (double)k0 : 0.0;
+        a.rowInvK[a.n_rows + row] = k1 ? 1.0 / (double)k1 : 0.0;
     }
 }
 
-// per-gene HGT gain threshold from the post-mutation snapshot. One CTA (8 warps)
-// per 32-gene word; warp q sums donors q, q+8, ... in order, then the eight
-// partial sums are added in warp order: deterministic.
-__global__ void __launch_bounds__(256) acc_gain_threshold_kernel(const AccArgs a)
+// per-gene HGT gain threshold from the post-mutation snapshot. One CTA (32 warps) per 32-gene
+// word; warp q sums donors q, q+32, ... in order, then the 32 partial sums are added in warp
+// order: deterministic.
+constexpr int GAIN_WARPS = 32;
+
+__global__ void __launch_bounds__(GAIN_WARPS * 32) acc_gain_threshold_kernel(const AccArgs a)
 {
-    __shared__ double part[8][32];
+    __shared__ double part[GAIN_WARPS][32];
     const uint32_t w = blockIdx.x;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t g = w * 32u + lane;
     int c = -1;
-    for (uint32_t k = 0; k < a.n_comp; k++)
-        if (g >= a.comp_lo[k] && g < a.comp_hi[k] && a.hgt_scale[k] > 0.0) c = (int)k;
+    if (g >= a.lo0 && g < a.hi0 && a.hgt_scale0 > 0.0) c = 0;
+    if (g >= a.lo1 && g < a.hi1 && a.hgt_scale1 > 0.0) c = 1;
+    const double *invK = a.rowInvK + (c == 1 ? a.n_rows : 0u);
     double s = 0.0;
-    for (uint32_t d = warp; d < a.n_rows; d += 8) {
+    for (uint32_t d = warp; d < a.n_rows; d += GAIN_WARPS) {
         const uint32_t word = a.new_state[(uint64_t)d * a.stride_words + w];
-        if (c >= 0 && ((word >> lane) & 1u)) {
-            const uint32_t K = a.rowK[(uint32_t)c * a.n_rows + d];
-            s += 1.0 / (double)K;          // K >= 1 because the donor carries g
-        }
+        if (c >= 0 && ((word >> lane) & 1u)) s += invK[d];
     }
     part[warp][lane] = s;
     __syncthreads();
     if (warp == 0 && g < a.n_genes) {
         double S = 0.0;
-        for (int q = 0; q < 8; q++) S += part[q][lane];
+        for (int q = 0; q < GAIN_WARPS; q++) S += part[q][lane];
         uint32_t thr = 0;
         if (c >= 0 && S > 0.0) {
-            const double p = -expm1(-a.hgt_scale[c] * S);
+            const double p = -expm1(-(c == 1 ? a.hgt_scale1 : a.hgt_scale0) * S);
             const double t = rint(p * 4294967296.0);
             thr = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
         }
@@ -159,11 +180,11 @@ __global__ void __launch_bounds__(256) acc_hgt_apply_kernel(const AccArgs a)
     if (idx >= total) return;
     const uint32_t row = (uint32_t)(idx / a.stride_words), w = (uint32_t)(idx % a.stride_words);
     uint32_t valid = 0;
-    for (uint32_t c = 0; c < a.n_comp; c++)
-        if (a.hgt_scale[c] > 0.0) valid |= comp_mask_for_word(w, a.comp_lo[c], a.comp_hi[c]);
+    if (a.hgt_scale0 > 0.0) valid |= comp_mask_for_word(w, a.lo0, a.hi0);
+    if (a.hgt_scale1 > 0.0) valid |= comp_mask_for_word(w, a.lo1, a.hi1);
     const uint32_t cur = a.new_state[idx];
     const uint32_t active = valid & ~cur;      // a hit on a present gene writes 1 over 1
-    const uint32_t gain = bernoulli_word<true>(a, STREAM_ACC_HGT, row, w, active, a.gain_thr);
+    const uint32_t gain = bernoulli_word<true>(a, STREAM_ACC_HGT, row, w, active, 0u, a.gain_thr);
     if (gain) a.new_state[idx] = cur | gain;
     if (DUMP) a.dump_gain[idx] = gain;
 }

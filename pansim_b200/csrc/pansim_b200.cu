@@ -133,7 +133,8 @@ struct pansim_ctx {
     double *d_tmp_a = nullptr, *d_tmp_b = nullptr, *d_weights = nullptr, *d_cum = nullptr;
     int *d_err = nullptr;
     uint32_t *d_inter = nullptr;
-    uint32_t *d_rowK = nullptr, *d_gain_thr = nullptr;
+    double *d_rowInvK = nullptr;
+    uint32_t *d_gain_thr = nullptr;
     bool avgdist_valid = false;
     bool fitness_valid = false;   // d_logfit / d_num_genes match the current accessory state
 
@@ -348,14 +349,11 @@ void fill_acc_args(pansim_ctx *c, AccArgs &a, uint32_t gen)
     a.stride_words = c->acc_stride_words;
     a.key = make_uint2((uint32_t)c->cfg.seed, (uint32_t)(c->cfg.seed >> 32));
     a.gen = gen;
-    a.n_comp = c->cfg.n_compartments;
-    for (int k = 0; k < 2; k++) {
-        a.comp_lo[k] = c->cfg.comp_lo[k];
-        a.comp_hi[k] = c->cfg.comp_hi[k];
-        a.flip_thr[k] = c->flip_thr[k];
-        a.hgt_scale[k] = c->hgt_scale[k];
-    }
-    a.rowK = c->d_rowK;
+    if (c->cfg.n_compartments > 0) { a.lo0 = c->cfg.comp_lo[0]; a.hi0 = c->cfg.comp_hi[0]; }
+    if (c->cfg.n_compartments > 1) { a.lo1 = c->cfg.comp_lo[1]; a.hi1 = c->cfg.comp_hi[1]; }
+    a.flip_thr0 = c->flip_thr[0]; a.flip_thr1 = c->flip_thr[1];
+    a.hgt_scale0 = c->hgt_scale[0]; a.hgt_scale1 = c->hgt_scale[1];
+    a.rowInvK = c->d_rowInvK;
     a.gain_thr = c->d_gain_thr;
     a.dump_flip = c->d_dump_flip;
     a.dump_gain = c->d_dump_gain;
@@ -372,9 +370,9 @@ int launch_acc_step(pansim_ctx *c, uint32_t gen)
     else
         acc_gather_flip_kernel<false><<<div_up64(c->N, rows_per_cta), 256, 0, c->stream>>>(a);
     LAUNCH_CHECK(c);
-    const bool hgt = (a.hgt_scale[0] > 0.0 || a.hgt_scale[1] > 0.0);
+    const bool hgt = (a.hgt_scale0 > 0.0 || a.hgt_scale1 > 0.0);
     if (hgt) {
-        acc_gain_threshold_kernel<<<c->acc_words, 256, 0, c->stream>>>(a);
+        acc_gain_threshold_kernel<<<c->acc_words, GAIN_WARPS * 32, 0, c->stream>>>(a);
         LAUNCH_CHECK(c);
         const uint64_t total = (uint64_t)c->N * c->acc_stride_words;
         if (c->dump_enabled)
@@ -550,7 +548,7 @@ void pansim_destroy(pansim_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->stream_core) cudaStreamSynchronize(c->stream_core);
     void *ptrs[] = {c->core[0], c->core[1], c->core_snap, c->acc[0], c->acc[1], c->d_parents_buf[0], c->d_parents_buf[1], c->d_parents_buf[2], c->d_lw, c->d_logfit, c->d_avgdist,
-                    c->d_num_genes, c->d_tmp_a, c->d_tmp_b, c->d_weights, c->d_cum, c->d_err, c->d_inter, c->d_rowK,
+                    c->d_num_genes, c->d_tmp_a, c->d_tmp_b, c->d_weights, c->d_cum, c->d_err, c->d_inter, c->d_rowInvK,
                     c->d_gain_thr, c->tab_mut.d_thr, c->tab_hr.d_thr, c->d_r1, c->d_r2, c->d_cd, c->d_in, c->d_un,
                     c->d_replay, c->d_hkeys, c->d_hvals, c->d_stage, c->d_groups, c->d_partner, c->d_orig, c->d_batches, c->d_tile_slots, c->d_tile_orig, c->d_dump_counters, c->d_mut_row, c->d_mut_site,
                     c->d_mut_seq, c->d_mut_allele, c->d_hr_rec, c->d_hr_locus, c->d_hr_donor, c->d_hr_seq,
@@ -679,7 +677,7 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
         CU(c, cudaMalloc(&c->d_cum, n * 8));
         CU(c, cudaMalloc(&c->d_err, sizeof(int)));
         CU(c, cudaMemset(c->d_err, 0, sizeof(int)));
-        CU(c, cudaMalloc(&c->d_rowK, 2 * n * 4));
+        CU(c, cudaMalloc(&c->d_rowInvK, 2 * n * 8));
         CU(c, cudaMalloc(&c->d_gain_thr, (size_t)(c->G ? c->G : 1) * 4));
         CU(c, cudaMalloc(&c->d_dump_counters, 2 * sizeof(uint32_t)));
         CU(c, cudaMemset(c->d_dump_counters, 0, 2 * sizeof(uint32_t)));

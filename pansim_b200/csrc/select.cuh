@@ -61,7 +61,14 @@ __global__ void __launch_bounds__(FIT_WARPS * 32) fitness_kernel(const uint32_t 
             mine[off++] = v;
         }
         __syncwarp();
-        for (uint32_t t = 0; t < tot; t++) sum += mine[t];      // every lane runs the same chain
+        // every lane runs the same chain; loads are batched so the chain only waits on the adds
+        uint32_t t = 0;
+        for (; t + 8 <= tot; t += 8) {
+            const double v0 = mine[t], v1 = mine[t + 1], v2 = mine[t + 2], v3 = mine[t + 3];
+            const double v4 = mine[t + 4], v5 = mine[t + 5], v6 = mine[t + 6], v7 = mine[t + 7];
+            sum += v0; sum += v1; sum += v2; sum += v3; sum += v4; sum += v5; sum += v6; sum += v7;
+        }
+        for (; t < tot; t++) sum += mine[t];
         __syncwarp();
     }
     neg_inf = __any_sync(0xffffffffu, neg_inf);
