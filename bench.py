@@ -183,6 +183,10 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # clocks / throttle reasons are sampled (every 100 ms) from here to the end of the end-to-end
+    # loop: nvidia-smi needs ~1 s to start and the K-step region itself lasts tens of milliseconds
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+
     import torch
     import torch.distributed as dist
     import pansim_b200 as pb
@@ -228,10 +232,6 @@ def main():
     r1, r2 = sample_pairs(rng, p.pop_size, p.max_distances)
     sim.set_initial(core_row, acc_row)
     sim.set_selection(sel)
-
-    # clocks / throttle reasons are sampled from the warm-up to the end of the end-to-end loop
-    # (nvidia-smi needs ~1 s to start; the K-step region itself lasts tens of milliseconds)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
 
     # ---- warm-up (also diversifies the clonal start) -------------------------
     gen = 0
