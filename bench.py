@@ -75,7 +75,9 @@ def measured_peak():
 
 
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampler (100 ms). stop(t0, t1) keeps the samples taken while the GPU was under
+    load, i.e. between the wall-clock times t0 (start of warm-up) and t1 (end of the e2e loop)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -88,7 +90,8 @@ class ClockSampler:
         except Exception:
             self.p = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
@@ -99,24 +102,25 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.f.read().splitlines():
             parts = [x.strip() for x in line.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(parts[1]), float(parts[2]),
+                             [n for n, v in zip(names, parts[4:8]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for n, v in zip(names, parts[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
         os.unlink(self.f.name)
-        if sm:
-            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                   "samples": len(sm)}
+        load = [r for r in rows if t0 is not None and t0 - 0.15 <= r[0] <= t1 + 0.15]
+        use = load or rows
+        if use:
+            out = {"sm_mhz": float(np.median([r[1] for r in use])), "sm_max_mhz": float(max(r[2] for r in use)),
+                   "reasons": sorted({n for r in use for n in r[3]}), "samples": len(use),
+                   "window": "warm-up .. end of e2e loop" if load else "whole run (no sample fell in the load window)"}
         return out
 
 
@@ -234,6 +238,7 @@ def main():
     sim.set_selection(sel)
 
     # ---- warm-up (also diversifies the clonal start) -------------------------
+    t_load0 = time.time()
     gen = 0
     sim.run_generations(gen, W)
     gen += W
@@ -296,7 +301,7 @@ def main():
     for _ in range(3):
         cd, it, un = sim.pair_counts(r1, r2)               # h2d 2 x P u32, d2h 3 x P u32
     e2e_pair_ms = 1e3 * (time.perf_counter() - t0) / 3
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop(t_load0, time.time()) if sampler else None
 
     if rank != 0:
         if world > 1:
