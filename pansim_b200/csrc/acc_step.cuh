@@ -33,7 +33,7 @@ struct AccArgs {
     uint32_t flip_thr0, flip_thr1; // round(p_c * 2^32)
     double hgt_scale0, hgt_scale1; // lambda_c / (N-1); 0 = off
     double *rowInvK;               // [2][n_rows] 1 / (genes of compartment c present, post-mutation); 0 if none
-    uint32_t *gain_thr;            // [n_genes]
+    uint32_t *gain_planes;         // [gene words][32]: plane j = binary digit j (MSB first) of the 32 genes' gain thresholds
     uint32_t *dump_flip;           // optional [n_rows * stride_words]
     uint32_t *dump_gain;
 };
@@ -50,56 +50,44 @@ __device__ __forceinline__ uint32_t comp_mask_for_word(uint32_t w, uint32_t lo, 
     return upto_b & ~upto_a;
 }
 
-// Bernoulli(thr / 2^32) from a 16-bit uniform `u16` as the HIGH half of a 32-bit uniform; the low
-// half is only drawn (dedicated Philox call) in the 2^-16 case where the high halves tie, so the
-// decision is exactly `u32 < thr`.
-__device__ __noinline__ uint32_t bernoulli_low_half(uint32_t w, uint32_t row, uint32_t gen, uint32_t stream,
-                                                    uint2 key, uint32_t b)
-{
-    uint4 ctr = make_ctr(w, row, gen, stream);
-    ctr.w |= 0x100u + b;
-    return philox4x32_10(ctr, key).x & 0xFFFFu;
-}
+// 32 Bernoulli bits at once, bit-sliced and lazy: gene b gets result bit 1 iff U_b < thr_b, where
+// U_b is a 32-bit uniform whose binary digits are bit b of successive Philox words (most
+// significant digit first) and thr_b is given as 32 bit-planes (plane j = digit j of every gene's
+// threshold). A gene is decided at the first digit where U_b and thr_b differ, so on average
+// log2(32) + 1.3 ~ 6-7 random words settle all 32 genes (instead of one 32-bit uniform per gene);
+// the comparison is exact (all 32 digits are used if needed; equality means "not less").
+struct PlanesConst {            // per-compartment constant thresholds (gene gain/loss flips)
+    uint32_t thr0, thr1, m0, m1;
+    __device__ __forceinline__ uint32_t operator()(uint32_t j) const
+    {
+        return (((thr0 >> (31u - j)) & 1u) ? m0 : 0u) | (((thr1 >> (31u - j)) & 1u) ? m1 : 0u);
+    }
+};
+struct PlanesTable {            // per-gene thresholds (HGT), bit-planes precomputed per gene word
+    const uint32_t *p;
+    __device__ __forceinline__ uint32_t operator()(uint32_t j) const { return p[j]; }
+};
 
-__device__ __forceinline__ bool bernoulli16(uint32_t u16, uint32_t thr, uint32_t w, uint32_t row, uint32_t gen,
-                                            uint32_t stream, uint2 key, uint32_t b)
+template <typename Planes>
+__device__ __forceinline__ uint32_t bernoulli_word(uint2 key, uint32_t gen, uint32_t stream, uint32_t row,
+                                                   uint32_t w, uint32_t active, const Planes planes)
 {
-    const uint32_t t_hi = thr >> 16, t_lo = thr & 0xFFFFu;
-    if (u16 != t_hi) return u16 < t_hi;
-    if (t_lo == 0) return false;
-    return bernoulli_low_half(w, row, gen, stream, key, b) < t_lo;
-}
-
-// 32 Bernoulli bits for word w of row `row`: bit b set iff uniform_b < thr(gene 32w+b). Four
-// Philox calls give the 32 high halves. thr: per-gene table (HGT) or per-compartment (flips).
-template <bool PER_GENE>
-__device__ __forceinline__ uint32_t bernoulli_word(const AccArgs &a, uint32_t stream, uint32_t row, uint32_t w,
-                                                   uint32_t active, uint32_t mask0, const uint32_t *per_gene)
-{
-    uint32_t out = 0;
-    if (!active) return 0;
+    uint32_t und = active, res = 0;
 #pragma unroll 1
-    for (uint32_t q = 0; q < 4; q++) {
-        if (((active >> (8 * q)) & 0xFFu) == 0) continue;
-        uint4 ctr = make_ctr(w, row, a.gen, stream);
+    for (uint32_t q = 0; q < 8 && und; q++) {
+        uint4 ctr = make_ctr(w, row, gen, stream);
         ctr.w |= q;
-        const uint4 r = philox4x32_10(ctr, a.key);
-        const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+        const uint4 r4 = philox4x32_10(ctr, key);
+        const uint32_t r[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
-        for (uint32_t c = 0; c < 8; c++) {
-            const uint32_t b = 8 * q + c;
-            const uint32_t u16 = (u[c >> 1] >> (16 * (c & 1))) & 0xFFFFu;
-            uint32_t thr;
-            if (PER_GENE) {
-                const uint32_t g = w * 32u + b;
-                thr = g < a.n_genes ? per_gene[g] : 0u;
-            } else {
-                thr = ((mask0 >> b) & 1u) ? a.flip_thr0 : a.flip_thr1;
-            }
-            if (((active >> b) & 1u) && bernoulli16(u16, thr, w, row, a.gen, stream, a.key, b)) out |= 1u << b;
+        for (uint32_t c = 0; c < 4; c++) {
+            const uint32_t t = planes(4u * q + c);
+            const uint32_t lt = ~r[c] & t, gt = r[c] & ~t;
+            res |= und & lt;
+            und &= ~(lt | gt);
         }
     }
-    return out;
+    return res;
 }
 
 // gather + flips + per-row compartment popcounts. One warp per row.
@@ -118,7 +106,8 @@ __global__ void __launch_bounds__(256) acc_gather_flip_kernel(const AccArgs a)
         uint32_t active = 0;
         if (a.flip_thr0) active |= m0;
         if (a.flip_thr1) active |= m1;
-        const uint32_t flips = bernoulli_word<false>(a, STREAM_ACC_FLIP, row, w, active, m0, nullptr);
+        const uint32_t flips = bernoulli_word(a.key, a.gen, STREAM_ACC_FLIP, row, w, active,
+                                              PlanesConst{a.flip_thr0, a.flip_thr1, m0, m1});
         const uint32_t v = src[w] ^ flips;
         dst[w] = v;
         if (DUMP) a.dump_flip[(uint64_t)row * a.stride_words + w] = flips;
@@ -158,16 +147,23 @@ __global__ void __launch_bounds__(GAIN_WARPS * 32) acc_gain_threshold_kernel(con
     }
     part[warp][lane] = s;
     __syncthreads();
-    if (warp == 0 && g < a.n_genes) {
+    if (warp == 0) {
         double S = 0.0;
         for (int q = 0; q < GAIN_WARPS; q++) S += part[q][lane];
         uint32_t thr = 0;
-        if (c >= 0 && S > 0.0) {
+        if (g < a.n_genes && c >= 0 && S > 0.0) {
             const double p = -expm1(-(c == 1 ? a.hgt_scale1 : a.hgt_scale0) * S);
             const double t = rint(p * 4294967296.0);
             thr = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
         }
-        a.gain_thr[g] = thr;
+        // transpose the 32 thresholds into bit-planes: lane j keeps plane j
+        uint32_t plane = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < 32; j++) {
+            const uint32_t bal = __ballot_sync(0xffffffffu, (thr >> (31u - j)) & 1u);
+            if (lane == j) plane = bal;
+        }
+        a.gain_planes[(uint64_t)w * 32u + lane] = plane;
     }
 }
 
@@ -184,7 +180,8 @@ __global__ void __launch_bounds__(256) acc_hgt_apply_kernel(const AccArgs a)
     if (a.hgt_scale1 > 0.0) valid |= comp_mask_for_word(w, a.lo1, a.hi1);
     const uint32_t cur = a.new_state[idx];
     const uint32_t active = valid & ~cur;      // a hit on a present gene writes 1 over 1
-    const uint32_t gain = bernoulli_word<true>(a, STREAM_ACC_HGT, row, w, active, 0u, a.gain_thr);
+    const uint32_t gain = bernoulli_word(a.key, a.gen, STREAM_ACC_HGT, row, w, active,
+                                         PlanesTable{a.gain_planes + (uint64_t)w * 32u});
     if (gain) a.new_state[idx] = cur | gain;
     if (DUMP) a.dump_gain[idx] = gain;
 }

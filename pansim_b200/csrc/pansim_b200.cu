@@ -134,7 +134,8 @@ struct pansim_ctx {
     int *d_err = nullptr;
     uint32_t *d_inter = nullptr;
     double *d_rowInvK = nullptr;
-    uint32_t *d_gain_thr = nullptr;
+    uint32_t *d_gain_thr = nullptr;      // scratch (gene counts)
+    uint32_t *d_gain_planes = nullptr;   // [gene words][32] bit-planes of the HGT gain thresholds
     bool avgdist_valid = false;
     bool fitness_valid = false;   // d_logfit / d_num_genes match the current accessory state
 
@@ -354,7 +355,7 @@ void fill_acc_args(pansim_ctx *c, AccArgs &a, uint32_t gen)
     a.flip_thr0 = c->flip_thr[0]; a.flip_thr1 = c->flip_thr[1];
     a.hgt_scale0 = c->hgt_scale[0]; a.hgt_scale1 = c->hgt_scale[1];
     a.rowInvK = c->d_rowInvK;
-    a.gain_thr = c->d_gain_thr;
+    a.gain_planes = c->d_gain_planes;
     a.dump_flip = c->d_dump_flip;
     a.dump_gain = c->d_dump_gain;
 }
@@ -548,7 +549,7 @@ void pansim_destroy(pansim_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->stream_core) cudaStreamSynchronize(c->stream_core);
     void *ptrs[] = {c->core[0], c->core[1], c->core_snap, c->acc[0], c->acc[1], c->d_parents_buf[0], c->d_parents_buf[1], c->d_parents_buf[2], c->d_lw, c->d_logfit, c->d_avgdist,
-                    c->d_num_genes, c->d_tmp_a, c->d_tmp_b, c->d_weights, c->d_cum, c->d_err, c->d_inter, c->d_rowInvK,
+                    c->d_num_genes, c->d_tmp_a, c->d_tmp_b, c->d_weights, c->d_cum, c->d_err, c->d_inter, c->d_rowInvK, c->d_gain_planes,
                     c->d_gain_thr, c->tab_mut.d_thr, c->tab_hr.d_thr, c->d_r1, c->d_r2, c->d_cd, c->d_in, c->d_un,
                     c->d_replay, c->d_hkeys, c->d_hvals, c->d_stage, c->d_groups, c->d_partner, c->d_orig, c->d_batches, c->d_tile_slots, c->d_tile_orig, c->d_dump_counters, c->d_mut_row, c->d_mut_site,
                     c->d_mut_seq, c->d_mut_allele, c->d_hr_rec, c->d_hr_locus, c->d_hr_donor, c->d_hr_seq,
@@ -679,6 +680,7 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
         CU(c, cudaMemset(c->d_err, 0, sizeof(int)));
         CU(c, cudaMalloc(&c->d_rowInvK, 2 * n * 8));
         CU(c, cudaMalloc(&c->d_gain_thr, (size_t)(c->G ? c->G : 1) * 4));
+        CU(c, cudaMalloc(&c->d_gain_planes, (size_t)(c->acc_words ? c->acc_words : 1) * 32 * 4));
         CU(c, cudaMalloc(&c->d_dump_counters, 2 * sizeof(uint32_t)));
         CU(c, cudaMemset(c->d_dump_counters, 0, 2 * sizeof(uint32_t)));
 
