@@ -138,6 +138,7 @@ struct pansim_ctx {
     uint32_t *d_gain_planes = nullptr;   // [gene words][32] bit-planes of the HGT gain thresholds
     bool avgdist_valid = false;
     bool fitness_valid = false;   // d_logfit / d_num_genes match the current accessory state
+    bool fitness_blocked = false; // large shapes: blocked (fixed-association) fitness sum instead of the sequential chain
 
     HostPoissonTable tab_mut, tab_hr;
     uint32_t flip_thr[2] = {0, 0};
@@ -290,8 +291,12 @@ int launch_fitness(pansim_ctx *c)
 {
     if (c->fitness_valid) return 0;
     const uint32_t *acc = c->acc[c->acc_cur];
-    fitness_kernel<<<div_up64(c->N, FIT_WARPS), FIT_WARPS * 32, 0, c->stream>>>(acc, c->N, c->G, c->acc_stride_words, c->d_lw,
-                                                             c->d_logfit, c->d_num_genes);
+    if (c->fitness_blocked)
+        fitness_blocked_kernel<<<div_up64(c->N, FIT_WARPS), FIT_WARPS * 32, 0, c->stream>>>(acc, c->N, c->G, c->acc_stride_words,
+                                                                                       c->d_lw, c->d_logfit, c->d_num_genes);
+    else
+        fitness_kernel<<<div_up64(c->N, FIT_WARPS), FIT_WARPS * 32, 0, c->stream>>>(acc, c->N, c->G, c->acc_stride_words,
+                                                                               c->d_lw, c->d_logfit, c->d_num_genes);
     LAUNCH_CHECK(c);
     c->fitness_valid = true;
     return 0;
@@ -657,6 +662,9 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
             CU(c, cudaMalloc(&c->acc[b], acc_bytes));
             CU(c, cudaMemset(c->acc[b], 0, acc_bytes));
         }
+        // the bit-exact sequential fitness chain is kept up to 2^25 accessory cells (cfg1-3: 4e6)
+        c->fitness_blocked = (uint64_t)c->N * c->G > (1ull << 25);
+        if (const char *e = getenv("PANSIM_FITNESS_BLOCKED")) c->fitness_blocked = atoi(e) != 0;
         // two-pass recombination when a site block expects more than ~2 HR events per generation
         c->two_pass_hr = rate_hr * BLOCK_SITES > 2.0;
         if (const char *e = getenv("PANSIM_TWO_PASS_HR")) c->two_pass_hr = atoi(e) != 0;

@@ -78,6 +78,52 @@ __global__ void __launch_bounds__(FIT_WARPS * 32) fitness_kernel(const uint32_t 
     }
 }
 
+// Large shapes (N x G above FITNESS_EXACT_CELLS): the strictly sequential chain above costs one
+// issue slot per addition per row and dominates the accessory/selection chain (0.6 ms at
+// N = 10 000, G = 18 000). The blocked variant adds, per row, the present genes of each 32-gene
+// word in column order (one lane per word), then the word sums of each 1024-gene chunk in word
+// order, then the chunk sums in chunk order: a fixed association, independent of grid shape and
+// GPU count, within a few ulp (|rel| < 1e-13) of the reference's flat left-to-right sum.
+__global__ void __launch_bounds__(FIT_WARPS * 32) fitness_blocked_kernel(const uint32_t *acc, uint32_t n_rows,
+                                                                         uint32_t n_genes, uint32_t stride_words,
+                                                                         const double *lw, double *logfit,
+                                                                         int32_t *num_genes)
+{
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t row = blockIdx.x * FIT_WARPS + warp;
+    if (row >= n_rows) return;
+    const uint32_t *r = acc + (uint64_t)row * stride_words;
+    const uint32_t n_words = (n_genes + 31u) / 32u;
+    double sum = 0.0;
+    bool neg_inf = false;
+    int32_t cnt = 0;
+    for (uint32_t w0 = 0; w0 < n_words; w0 += 32) {
+        const uint32_t w = w0 + lane;
+        uint32_t bits = (w < n_words) ? r[w] : 0u;
+        cnt += __popc(bits);
+        double ws = 0.0;
+        const double *lww = lw + (uint64_t)w * 32u;
+        while (bits) {
+            const uint32_t b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const double v = lww[b];
+            neg_inf |= (v == -INFINITY);
+            ws += v;
+        }
+        double cs = 0.0;
+#pragma unroll
+        for (int t = 0; t < 32; t++) cs += __shfl_sync(0xffffffffu, ws, t);      // word order
+        sum += cs;                                                               // chunk order
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    neg_inf = __any_sync(0xffffffffu, neg_inf);
+    if (lane == 0) {
+        logfit[row] = (n_genes > 0) ? (neg_inf ? 0.0 : sum) : 0.0;
+        num_genes[row] = cnt;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // K2a: all-vs-all intersection counts I[i][j] = popc(row_i & row_j), 32x32 tiles,
 // upper triangle computed, mirrored on store.

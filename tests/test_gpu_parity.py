@@ -557,3 +557,25 @@ def test_empty_pair_list_and_large_pair_batch():
         assert (cd == ob.Population(core, True).pair_counts(r1, r2)).all()
         with pytest.raises(pb.PansimError):
             sim.pair_counts([0], [50])
+
+
+def test_blocked_fitness_sum_for_large_shapes(monkeypatch):
+    """Above 2^25 accessory cells the fitness sum uses a fixed blocked association instead of the
+    strictly sequential chain: same gene counts, log-fitness within 1e-12 (relative) of the oracle."""
+    monkeypatch.setenv("PANSIM_FITNESS_BLOCKED", "1")
+    rng = np.random.default_rng(31)
+    N, G = 70, 2500
+    core, acc = random_state(rng, N, 40, G, 0.25)
+    sel = rng.normal(0, 0.1, G)
+    sel[7] = -1.0
+    p = pb.Params(pop_size=N, core_size=40, pan_genes=G, core_genes=0)
+    with make(p) as sim:
+        sim.upload(core, acc)
+        sim.set_selection(sel)
+        sim.sample_indices(0)
+        w, ng, lf = sim.weights()
+    ow, ong, olf = ob.Population(acc, False, 0).selection_weights(pb.derive(p).avg_gene_num, np.ones(N), sel)
+    assert (ng == ong).all()
+    np.testing.assert_allclose(lf, olf, rtol=1e-12, atol=1e-12)
+    assert (lf[acc[:, 7] == 1] == 0.0).all()
+    np.testing.assert_allclose(w / w.sum(), ow / ow.sum(), rtol=1e-10)
