@@ -65,7 +65,17 @@ struct PlanesConst {            // per-compartment constant thresholds (gene gai
 };
 struct PlanesTable {            // per-gene thresholds (HGT), bit-planes precomputed per gene word
     const uint32_t *p;
-    __device__ __forceinline__ uint32_t operator()(uint32_t j) const { return p[j]; }
+    uint4 a, b;                 // planes 0..7 prefetched: they settle almost every gene
+    __device__ __forceinline__ explicit PlanesTable(const uint32_t *ptr)
+        : p(ptr), a(*reinterpret_cast<const uint4 *>(ptr)), b(*reinterpret_cast<const uint4 *>(ptr + 4)) {}
+    __device__ __forceinline__ uint32_t operator()(uint32_t j) const
+    {
+        switch (j) {
+        case 0: return a.x; case 1: return a.y; case 2: return a.z; case 3: return a.w;
+        case 4: return b.x; case 5: return b.y; case 6: return b.z; case 7: return b.w;
+        default: return p[j];
+        }
+    }
 };
 
 template <typename Planes>
@@ -141,7 +151,21 @@ __global__ void __launch_bounds__(GAIN_WARPS * 32) acc_gain_threshold_kernel(con
     if (g >= a.lo1 && g < a.hi1 && a.hgt_scale1 > 0.0) c = 1;
     const double *invK = a.rowInvK + (c == 1 ? a.n_rows : 0u);
     double s = 0.0;
-    for (uint32_t d = warp; d < a.n_rows; d += GAIN_WARPS) {
+    uint32_t d = warp;
+    for (; d + 3 * GAIN_WARPS < a.n_rows; d += 4 * GAIN_WARPS) {      // four loads in flight, adds in row order
+        const uint32_t w0 = a.new_state[(uint64_t)d * a.stride_words + w];
+        const uint32_t w1 = a.new_state[(uint64_t)(d + GAIN_WARPS) * a.stride_words + w];
+        const uint32_t w2 = a.new_state[(uint64_t)(d + 2 * GAIN_WARPS) * a.stride_words + w];
+        const uint32_t w3 = a.new_state[(uint64_t)(d + 3 * GAIN_WARPS) * a.stride_words + w];
+        const double k0 = invK[d], k1 = invK[d + GAIN_WARPS], k2 = invK[d + 2 * GAIN_WARPS], k3 = invK[d + 3 * GAIN_WARPS];
+        if (c >= 0) {
+            if ((w0 >> lane) & 1u) s += k0;
+            if ((w1 >> lane) & 1u) s += k1;
+            if ((w2 >> lane) & 1u) s += k2;
+            if ((w3 >> lane) & 1u) s += k3;
+        }
+    }
+    for (; d < a.n_rows; d += GAIN_WARPS) {
         const uint32_t word = a.new_state[(uint64_t)d * a.stride_words + w];
         if (c >= 0 && ((word >> lane) & 1u)) s += invK[d];
     }
@@ -181,7 +205,7 @@ __global__ void __launch_bounds__(256) acc_hgt_apply_kernel(const AccArgs a)
     const uint32_t cur = a.new_state[idx];
     const uint32_t active = valid & ~cur;      // a hit on a present gene writes 1 over 1
     const uint32_t gain = bernoulli_word(a.key, a.gen, STREAM_ACC_HGT, row, w, active,
-                                         PlanesTable{a.gain_planes + (uint64_t)w * 32u});
+                                         PlanesTable(a.gain_planes + (uint64_t)w * 32u));
     if (gain) a.new_state[idx] = cur | gain;
     if (DUMP) a.dump_gain[idx] = gain;
 }

@@ -89,20 +89,27 @@ __global__ void __launch_bounds__(FIT_WARPS * 32) fitness_blocked_kernel(const u
                                                                          const double *lw, double *logfit,
                                                                          int32_t *num_genes)
 {
+    __shared__ double lwc[1024];                       // lw of the current 1024-gene chunk (shared by the CTA's rows)
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t row = blockIdx.x * FIT_WARPS + warp;
-    if (row >= n_rows) return;
-    const uint32_t *r = acc + (uint64_t)row * stride_words;
+    const bool live = row < n_rows;
+    const uint32_t *r = acc + (uint64_t)(live ? row : 0) * stride_words;
     const uint32_t n_words = (n_genes + 31u) / 32u;
     double sum = 0.0;
     bool neg_inf = false;
     int32_t cnt = 0;
     for (uint32_t w0 = 0; w0 < n_words; w0 += 32) {
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < 1024; i += FIT_WARPS * 32) {
+            const uint32_t g = w0 * 32u + i;
+            lwc[i] = g < n_genes ? lw[g] : 0.0;
+        }
+        __syncthreads();
         const uint32_t w = w0 + lane;
-        uint32_t bits = (w < n_words) ? r[w] : 0u;
+        uint32_t bits = (live && w < n_words) ? r[w] : 0u;
         cnt += __popc(bits);
         double ws = 0.0;
-        const double *lww = lw + (uint64_t)w * 32u;
+        const double *lww = lwc + lane * 32u;
         while (bits) {
             const uint32_t b = __ffs(bits) - 1;
             bits &= bits - 1;
@@ -118,7 +125,7 @@ __global__ void __launch_bounds__(FIT_WARPS * 32) fitness_blocked_kernel(const u
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     neg_inf = __any_sync(0xffffffffu, neg_inf);
-    if (lane == 0) {
+    if (lane == 0 && live) {
         logfit[row] = (n_genes > 0) ? (neg_inf ? 0.0 : sum) : 0.0;
         num_genes[row] = cnt;
     }
