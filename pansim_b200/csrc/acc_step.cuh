@@ -135,39 +135,49 @@ __global__ void __launch_bounds__(256) acc_gather_flip_kernel(const AccArgs a)
     }
 }
 
-// per-gene HGT gain threshold from the post-mutation snapshot. One CTA (32 warps) per 32-gene
-// word; warp q sums donors q, q+32, ... in order, then the 32 partial sums are added in warp
-// order: deterministic.
+// per-gene HGT gain threshold from the post-mutation snapshot: S_g = sum over donors d carrying g of
+// 1/K_dc, a bit-matrix x vector product. One CTA (32 warps) per 32-gene word. A warp takes 32 donor
+// rows at a time (one row's word per lane), transposes the 32x32 bit tile with five shuffle stages
+// so that each lane holds ONE gene's mask over the 32 donors, and adds 1/K only for the set bits
+// (ascending donor order). Warp q handles row groups q, q+32, ...; the 32 partial sums are added in
+// warp order: deterministic.
 constexpr int GAIN_WARPS = 32;
+
+// in: lane l holds the word of row (31 - l); out: lane l holds, for gene (31 - l), bit r = row r
+__device__ __forceinline__ uint32_t warp_transpose32_rev(uint32_t x, uint32_t lane)
+{
+    uint32_t m = 0x0000FFFFu;
+#pragma unroll
+    for (uint32_t j = 16; j != 0; j >>= 1) {
+        const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+        if ((lane & j) == 0) x ^= (x ^ (y >> j)) & m;
+        else x ^= ((y ^ (x >> j)) & m) << j;
+        m ^= m << (j >> 1);
+    }
+    return x;
+}
 
 __global__ void __launch_bounds__(GAIN_WARPS * 32) acc_gain_threshold_kernel(const AccArgs a)
 {
     __shared__ double part[GAIN_WARPS][32];
     const uint32_t w = blockIdx.x;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t g = w * 32u + lane;
+    const uint32_t g = w * 32u + (31u - lane);            // the gene this lane accumulates
     int c = -1;
     if (g >= a.lo0 && g < a.hi0 && a.hgt_scale0 > 0.0) c = 0;
     if (g >= a.lo1 && g < a.hi1 && a.hgt_scale1 > 0.0) c = 1;
     const double *invK = a.rowInvK + (c == 1 ? a.n_rows : 0u);
     double s = 0.0;
-    uint32_t d = warp;
-    for (; d + 3 * GAIN_WARPS < a.n_rows; d += 4 * GAIN_WARPS) {      // four loads in flight, adds in row order
-        const uint32_t w0 = a.new_state[(uint64_t)d * a.stride_words + w];
-        const uint32_t w1 = a.new_state[(uint64_t)(d + GAIN_WARPS) * a.stride_words + w];
-        const uint32_t w2 = a.new_state[(uint64_t)(d + 2 * GAIN_WARPS) * a.stride_words + w];
-        const uint32_t w3 = a.new_state[(uint64_t)(d + 3 * GAIN_WARPS) * a.stride_words + w];
-        const double k0 = invK[d], k1 = invK[d + GAIN_WARPS], k2 = invK[d + 2 * GAIN_WARPS], k3 = invK[d + 3 * GAIN_WARPS];
-        if (c >= 0) {
-            if ((w0 >> lane) & 1u) s += k0;
-            if ((w1 >> lane) & 1u) s += k1;
-            if ((w2 >> lane) & 1u) s += k2;
-            if ((w3 >> lane) & 1u) s += k3;
+    for (uint32_t d0 = warp * 32u; d0 < a.n_rows; d0 += GAIN_WARPS * 32u) {
+        const uint32_t d = d0 + (31u - lane);
+        const uint32_t word = d < a.n_rows ? a.new_state[(uint64_t)d * a.stride_words + w] : 0u;
+        uint32_t mask = warp_transpose32_rev(word, lane);  // bit r = donor d0 + r carries gene g
+        if (c < 0) mask = 0;
+        while (mask) {
+            const uint32_t r = __ffs(mask) - 1;
+            mask &= mask - 1;
+            s += invK[d0 + r];
         }
-    }
-    for (; d < a.n_rows; d += GAIN_WARPS) {
-        const uint32_t word = a.new_state[(uint64_t)d * a.stride_words + w];
-        if (c >= 0 && ((word >> lane) & 1u)) s += invK[d];
     }
     part[warp][lane] = s;
     __syncthreads();
@@ -180,11 +190,12 @@ __global__ void __launch_bounds__(GAIN_WARPS * 32) acc_gain_threshold_kernel(con
             const double t = rint(p * 4294967296.0);
             thr = t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
         }
-        // transpose the 32 thresholds into bit-planes: lane j keeps plane j
+        // transpose the 32 thresholds into bit-planes (lane l holds gene 31 - l, hence the bit
+        // reversal): lane j keeps plane j
         uint32_t plane = 0;
 #pragma unroll
         for (uint32_t j = 0; j < 32; j++) {
-            const uint32_t bal = __ballot_sync(0xffffffffu, (thr >> (31u - j)) & 1u);
+            const uint32_t bal = __brev(__ballot_sync(0xffffffffu, (thr >> (31u - j)) & 1u));
             if (lane == j) plane = bal;
         }
         a.gain_planes[(uint64_t)w * 32u + lane] = plane;
