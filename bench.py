@@ -35,10 +35,9 @@ sys.path.insert(0, ROOT)
 CFG2 = dict(pop_size=1000, core_size=1_200_000, pan_genes=6000, core_genes=2000, n_gen=100,
             max_distances=100_000, prop_positive=0.1, competition_strength=0.5, seed=0)
 PEAK_FALLBACK_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
-# dram__bytes_read.sum + dram__bytes_write.sum of core_step_kernel from the committed
+# dram__bytes_read.sum + dram__bytes_write.sum of core_mut_kernel from the committed
 # ncu --set full capture (profiles/), per launch at this workload; None until captured
-NCU_CORE_STEP_DRAM_BYTES = 277.0e6   # 25.1 MB read + 251.9 MB written (profiles/r01_core_step_ncu_summary.txt, v6):
-# children of the same parent re-read that parent's row from L2, so DRAM reads stay far below N*L/4
+NCU_CORE_STEP_DRAM_BYTES = None
 
 
 def selection_coefficients(rng, n, prop_positive, pos_lambda=10.0, neg_lambda=10.0):
@@ -253,7 +252,9 @@ def main():
     wall_ms = 1e3 * (time.perf_counter() - t0)
     gen += K
     dev_ms = max_over_ranks(float(tm.total_ms))
-    core_ms = float(tm.core_step_ms) / K
+    core_ms = float(tm.core_step_ms) / K            # gather+SNP kernel and the recombination pass
+    hr_ms = float(tm.core_hr_ms) / K                # recombination pass alone (collect + apply)
+    mut_ms = core_ms - hr_ms                        # core_mut_kernel: the kernel that moves the state
     launches = int(tm.launches)
 
     # ---- distance pass (device time of the kernels; pairs resident) ----------
@@ -311,7 +312,7 @@ def main():
     peak, peak_src = measured_peak()
     N, P = p.pop_size, p.max_distances
     core_bytes = 2 * N * ((info.local_sites + 3) // 4)              # read + write of the packed slab
-    achieved = core_bytes / (core_ms * 1e-3) / 1e9 if core_ms > 0 else 0.0
+    achieved = core_bytes / (mut_ms * 1e-3) / 1e9 if mut_ms > 0 else 0.0
     gen_bytes = int(info.algorithmic_bytes_per_generation)
     ms_per_step = dev_ms / K
     value = world * K / (dev_ms * 1e-3)
@@ -331,14 +332,16 @@ def main():
         "wall_ms_per_step": wall_ms / K,
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"kernel": "core_step_kernel<RNG> (fused gather + SNP + HR, TMA bulk pipeline)",
+        "roofline": {"kernel": "core_mut_kernel<RNG> (gather-by-parent + SNP mutation, TMA bulk pipeline)",
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": NCU_CORE_STEP_DRAM_BYTES, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": core_bytes, "launch_ms": core_ms,
+                     "algorithmic_bytes_per_launch": core_bytes, "launch_ms": mut_ms,
+                     "core_genome_frac": core_bytes / (core_ms * 1e-3) / 1e9 / peak if core_ms > 0 else None,
                      "step_algorithmic_bytes": gen_bytes,
                      "step_frac": gen_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
-                     "kernel_share_of_step": core_ms / ms_per_step if ms_per_step > 0 else None,
-                     "breakdown_ms": {"select": tm.select_ms / K, "acc_step": tm.acc_step_ms / K, "core_step": core_ms}},
+                     "kernel_share_of_step": mut_ms / ms_per_step if ms_per_step > 0 else None,
+                     "breakdown_ms": {"select": tm.select_ms / K, "acc_step": tm.acc_step_ms / K, "core_step": core_ms,
+                                      "core_mut": mut_ms, "core_hr": hr_ms}},
         "distances": {"value": pairs_per_s, "unit": "pairs/s", "ms_per_pass": pair_ms, "pairs": P,
                       "core_ms": pair_core_ms / n_dist, "acc_ms": pair_acc_ms / n_dist,
                       "streaming_GBps": pair_bytes * P / (pair_ms * 1e-3) / 1e9,

@@ -197,11 +197,12 @@ int pansim_get_info(pansim_ctx *ctx, pansim_info *out);
  * pansim_pair_counts* call, split by kernel group. */
 typedef struct {
     float total_ms;
-    float core_step_ms;       /* fused gather+SNP+HR kernel (sum over generations) */
+    float core_step_ms;       /* core genome: gather+SNP kernel and the recombination pass (sum over generations) */
     float acc_step_ms;
     float select_ms;          /* competition + fitness + parent draw               */
     float pair_core_ms, pair_acc_ms;
     uint32_t launches;        /* kernels launched by that call                     */
+    float core_hr_ms;         /* the recombination pass alone (part of core_step_ms) */
 } pansim_timing;
 int pansim_get_timing(pansim_ctx *ctx, pansim_timing *out);
 /* enable/disable per-kernel event timing (off = no extra events; default on) */

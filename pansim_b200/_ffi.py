@@ -65,7 +65,7 @@ class Timing(C.Structure):
     _fields_ = [
         ("total_ms", C.c_float), ("core_step_ms", C.c_float), ("acc_step_ms", C.c_float),
         ("select_ms", C.c_float), ("pair_core_ms", C.c_float), ("pair_acc_ms", C.c_float),
-        ("launches", C.c_uint32),
+        ("launches", C.c_uint32), ("core_hr_ms", C.c_float),
     ]
 
 

@@ -75,6 +75,7 @@ __host__ __device__ __forceinline__ uint4 make_ctr(uint32_t block, uint32_t row,
 // Shared-memory image of one table: [256 x u32 guide][size x u32 thresholds]
 constexpr uint32_t GUIDE_ENTRIES = 256;
 constexpr uint32_t GUIDE_SHIFT = 24;
+constexpr uint32_t POISSON_TABLE_MAX = 1024;
 
 __device__ __forceinline__ uint32_t poisson_from_uniform(const uint32_t *tab, uint32_t kmax, uint32_t u)
 {
@@ -84,6 +85,32 @@ __device__ __forceinline__ uint32_t poisson_from_uniform(const uint32_t *tab, ui
         const uint32_t *thr = tab + GUIDE_ENTRIES;
         while (k < kmax && thr[k] <= u) k++;
     }
+    return k;
+}
+
+// Poisson count of a stream. Draw 0 uses `first` (word x of Philox call 0); a
+// mean above the table range adds draws from dedicated count calls (exact by
+// additivity).
+__device__ __noinline__ uint32_t stream_count_extra(uint4 ctr, uint2 key, const uint32_t *tab, uint32_t nsub,
+                                                    uint32_t kmax)
+{
+    uint32_t k = 0;
+    for (uint32_t s = 1; s < nsub; s++) {
+        uint4 c = ctr;
+        c.w |= 0x8000u | ((s - 1) >> 2);
+        const uint4 r = philox4x32_10(c, key);
+        const uint32_t sel = (s - 1) & 3u;
+        const uint32_t u = sel == 0 ? r.x : sel == 1 ? r.y : sel == 2 ? r.z : r.w;
+        k += poisson_from_uniform(tab, kmax, u);
+    }
+    return k;
+}
+
+__device__ __forceinline__ uint32_t stream_count(uint4 ctr, uint2 key, uint32_t first, const uint32_t *tab,
+                                                 uint32_t nsub, uint32_t kmax)
+{
+    uint32_t k = poisson_from_uniform(tab, kmax, first);
+    if (nsub > 1) k += stream_count_extra(ctr, key, tab, nsub, kmax);
     return k;
 }
 

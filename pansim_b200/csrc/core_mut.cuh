@@ -1,0 +1,311 @@
+// core_mut.cuh -- K4a: gather-by-parent fused with SNP mutation (core genome).
+//
+// One pass over the 2-bit packed core alignment does, per output row i:
+//   gather-by-parent   next[i,:] = pop[parents[i],:]      (population.rs:450-465)
+//   SNP mutation       population.rs:512-539
+// Homologous recombination (population.rs:544-751) follows as the sparse pass
+// of core_hr.cuh on the finished rows (which ARE the snapshot of :693-695).
+//
+// Every output cell is a pure function of (old state, parents, Philox key):
+// no races, no atomics, independent of grid size and of the column sharding.
+//
+// Exact thinning instead of the reference's per-row event loop (SURVEY.md 8a
+// row M): per row the reference draws n ~ Poisson(lambda) events at uniform
+// sites, each writing U{C,G,T} (core_vec[1 >> value] is always core_vec[0],
+// population.rs:531). Restricted to a 256-site block that is a
+// Poisson(256*lambda/L) number of events at uniform positions, one byte of
+// Philox output each; later events overwrite earlier ones.
+//
+// The kernel is instruction-issue bound, not HBM bound,
+// so the event loop is written for instruction count:
+//   * a position byte b addresses word (b & 15) of the lane's 16 words and
+//     cell (b >> 4) of that word; the shared-memory address is one shift and
+//     one LOP3 ((p >> k) & 0x780 | lane/stage base, stages 2 KiB aligned), the
+//     cell mask one wrap-mode shift of a pre-masked copy of the position word;
+//   * alleles: a uniform byte v < 243 carries base-3 digits; a 243-entry table
+//     in shared memory maps v to four words, word j holding allele code
+//     (digit j) + 1 replicated into all 16 cells, so the read-modify-write is
+//     LDS, SHF, LOP3 (bit select), predicated STS;
+//   * the five chunks (4 events each) of the first two Philox calls are
+//     unrolled behind warp-uniform guards, positions are compile-time shifts.
+//
+// Data movement: warp-private TMA pipelines (cp.async.bulk global->shared with
+// mbarrier completion from the PARENT's row, cp.async.bulk shared->global into
+// the child's row), three 2 KiB stages per warp, no CTA-wide barrier in the
+// steady state.
+#pragma once
+#include "common.cuh"
+
+namespace pansim {
+
+constexpr int CM_WARPS = 8;
+constexpr int CM_STAGES = 3;
+constexpr int CM_THREADS = CM_WARPS * 32;
+constexpr uint32_t CM_GUIDE = 512;            // u16 guide entries (= 256 words)
+constexpr uint32_t CM_GUIDE_SHIFT = 23;
+constexpr uint32_t CM_GUIDE_WORDS = CM_GUIDE / 2;
+constexpr uint32_t CM_LUT_ENTRIES = 243;
+constexpr uint32_t CM_LUT_BYTES = 3904;       // 243 x 16, rounded up to 64
+constexpr uint32_t CM_GROUP0 = 20;            // events carried by Philox calls 0 and 1
+constexpr uint32_t CM_TAIL = 8;               // events carried by each later call
+
+struct CoreMutArgs {
+    const uint8_t *old_state;
+    uint8_t *new_state;
+    const uint32_t *parents;  // nullptr = identity gather
+    uint32_t n_rows;
+    uint32_t n_regions;       // regions per (local) row
+    uint64_t row_stride;      // bytes
+    uint32_t region0;         // global index of local region 0
+    uint32_t items_per_warp;
+    uint64_t site_limit;      // global site index one past the last valid site of this shard
+    uint2 key;
+    uint32_t gen;
+    const uint32_t *mut_img;  // device image [CM_GUIDE u16 guide][mut_size thresholds]
+    uint32_t mut_size, mut_nsub, mut_kmax;
+    // optional event dump (parity instrumentation)
+    uint32_t *dump_counters;  // [0] = SNP events
+    uint32_t dump_cap;
+    uint32_t *d_mut_row, *d_mut_site, *d_mut_seq;
+    uint8_t *d_mut_allele;
+};
+
+static inline size_t core_mut_smem_bytes(uint32_t mut_size)
+{
+    return 2048 /* alignment slack */ + (size_t)CM_WARPS * CM_STAGES * REGION_BYTES + CM_LUT_BYTES +
+           (size_t)(CM_GUIDE_WORDS + mut_size) * sizeof(uint32_t) + (size_t)CM_WARPS * CM_STAGES * sizeof(uint64_t);
+}
+
+// Poisson by CDF inversion (see common.cuh) with a 512-bin u16 guide: entry =
+// 2*k0 + many, k0 = #{j : T[j] <= bin start}. A bin holding at most one
+// threshold needs exactly one comparison; `many` marks the few tail bins that
+// hold more and finish with a scan.
+__device__ __forceinline__ uint32_t poisson_fast(const uint32_t *tab, uint32_t kmax, uint32_t u)
+{
+    const uint32_t g = reinterpret_cast<const uint16_t *>(tab)[u >> CM_GUIDE_SHIFT];
+    const uint32_t *thr = tab + CM_GUIDE_WORDS;
+    uint32_t k = g >> 1;
+    k += thr[k] <= u ? 1u : 0u;
+    if (g & 1u) {
+        while (k < kmax && thr[k] <= u) k++;
+    }
+    return k;
+}
+
+// means above the table range: extra draws from dedicated count calls (exact by additivity)
+__device__ __noinline__ uint32_t mut_count_extra(uint4 ctr, uint2 key, const uint32_t *tab, uint32_t nsub, uint32_t kmax)
+{
+    uint32_t k = 0;
+    for (uint32_t s = 1; s < nsub; s++) {
+        uint4 c = ctr;
+        c.w |= 0x8000u | ((s - 1) >> 2);
+        const uint4 r = philox4x32_10(c, key);
+        const uint32_t sel = (s - 1) & 3u;
+        const uint32_t u = sel == 0 ? r.x : sel == 1 ? r.y : sel == 2 ? r.z : r.w;
+        k += poisson_fast(tab, kmax, u);
+    }
+    return k;
+}
+
+// digit byte and its reserves were all >= 243 (p = 1e-4 per chunk): dedicated Philox word, bias 6e-8
+__device__ __noinline__ uint32_t mut_digit_fallback(uint4 ctr, uint2 key, uint32_t tag)
+{
+    ctr.w |= 0x2000u;
+    ctr.x ^= 0x5bd1e995u * (tag + 1u);
+    return __umulhi(philox4x32_10(ctr, key).x, 243u);
+}
+
+template <bool DUMP>
+struct MutChunk {
+    uint32_t base_s;          // shared-space address of the stage | lane * 4
+    uint32_t lut_s;           // shared-space address of the digit table
+    uint32_t k, lane, row, lim;
+    uint64_t reg_site0;
+    uint4 ctr;
+    uint2 key;
+    const CoreMutArgs *a;
+
+    // events ev0 .. ev0+3 of this lane's stream: digit byte d (0..255), position bytes in p.
+    // `res` = reserve digit bytes (consumed from the low end, 0xFF shifted in).
+    __device__ __forceinline__ void run(uint32_t ev0, uint32_t d, uint32_t p, uint32_t &res) const
+    {
+        const bool rej = d >= 243u;
+        uint32_t v = rej ? (res & 255u) : d;
+        res = rej ? __funnelshift_r(res, 0xFFFFFFFFu, 8) : res;
+        if (v >= 243u) v = mut_digit_fallback(ctr, key, ev0 >> 2);
+        uint32_t c0, c1, c2, c3;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(c0), "=r"(c1), "=r"(c2), "=r"(c3) : "r"(lut_s + v * 16u));
+        const uint32_t cc[4] = {c0, c1, c2, c3};
+        const uint32_t psh = (p >> 3) & 0x1E1E1E1Eu;     // byte j: 2 * cell of event j (bit 0 clear)
+        const int rem = (int)k - (int)ev0;               // events of this chunk that exist for this lane
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t fa = j == 0 ? (p << 7) : (p >> (8 * j - 7));
+            const uint32_t addr = (fa & 0x780u) | base_s;                 // word (b & 15) * 32 + lane
+            const uint32_t m = __funnelshift_l(0u, 3u, psh >> (8 * j));   // 3 << (2 * cell), shift taken mod 32
+            uint32_t w;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(addr));
+            w = (w & ~m) | (cc[j] & m);
+            asm volatile("{\n\t.reg .pred q;\n\tsetp.gt.s32 q, %2, %3;\n\t@q st.shared.u32 [%0], %1;\n\t}"
+                         ::"r"(addr), "r"(w), "r"(rem), "r"(j) : "memory");
+            if (DUMP) {
+                const uint32_t b = (p >> (8 * j)) & 255u;
+                const uint32_t sir = (((b & 15u) << 5) + lane) * 16u + (b >> 4);
+                if (j < rem && sir < lim) {
+                    const uint32_t s = atomicAdd(&a->dump_counters[0], 1u);
+                    if (s < a->dump_cap) {
+                        a->d_mut_row[s] = row;
+                        a->d_mut_site[s] = (uint32_t)(reg_site0 + sir);
+                        a->d_mut_seq[s] = ev0 + j;
+                        a->d_mut_allele[s] = (uint8_t)(1u << (cc[j] & 3u));
+                    }
+                }
+            }
+        }
+    }
+};
+
+template <bool RNG, bool DUMP>
+__global__ void __launch_bounds__(CM_THREADS, 4) core_mut_kernel(const CoreMutArgs a)
+{
+    extern __shared__ uint8_t smem_dyn[];
+    // stages must sit on 2 KiB boundaries of the shared window (the slot address is an OR)
+    const uint32_t pad = (2048u - (smem_u32(smem_dyn) & 2047u)) & 2047u;
+    uint8_t *smem_raw = smem_dyn + pad;
+    uint8_t *lut_raw = smem_raw + (size_t)CM_WARPS * CM_STAGES * REGION_BYTES;
+    uint32_t *tab = reinterpret_cast<uint32_t *>(lut_raw + CM_LUT_BYTES);
+    uint64_t *bars_all = reinterpret_cast<uint64_t *>(tab + CM_GUIDE_WORDS + a.mut_size);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *stages = smem_raw + (size_t)warp * CM_STAGES * REGION_BYTES;
+    uint64_t *bars = bars_all + warp * CM_STAGES;
+
+    if (RNG) {
+#pragma unroll 1
+        for (uint32_t i = threadIdx.x; i < CM_GUIDE_WORDS + a.mut_size; i += CM_THREADS) tab[i] = a.mut_img[i];
+        if (threadIdx.x < CM_LUT_ENTRIES) {
+            uint32_t v = threadIdx.x;
+            uint4 e;
+            e.x = (v % 3u + 1u) * 0x55555555u; v /= 3u;
+            e.y = (v % 3u + 1u) * 0x55555555u; v /= 3u;
+            e.z = (v % 3u + 1u) * 0x55555555u; v /= 3u;
+            e.w = (v % 3u + 1u) * 0x55555555u;
+            reinterpret_cast<uint4 *>(lut_raw)[threadIdx.x] = e;
+        }
+    }
+    if (lane == 0) {
+        for (int s = 0; s < CM_STAGES; s++) mbar_init(&bars[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    // CTA b covers items [b*C, (b+1)*C), C = CM_WARPS*items_per_warp; warp w takes b*C + w + 8j.
+    // CTAs are short-lived on purpose: SM slots turn over every few tens of microseconds, so the
+    // (higher-priority) accessory/selection kernels of the next generation can slip in between.
+    const uint32_t total = a.n_rows * a.n_regions;
+    const uint32_t cta_items = CM_WARPS * a.items_per_warp;
+    const uint32_t cta_base = blockIdx.x * cta_items;
+    const uint32_t cta_end = min(total, cta_base + cta_items);
+    const uint32_t gw = cta_base + warp;
+    if (gw >= cta_end) return;
+    const uint32_t n_my = (cta_end - gw + CM_WARPS - 1) / CM_WARPS;
+    const uint32_t d_row = CM_WARPS / a.n_regions, d_reg = CM_WARPS % a.n_regions;
+
+    // the load side runs CM_STAGES-1 items ahead with its own (row, reg) cursor (lane 0 only)
+    uint32_t l_row = gw / a.n_regions, l_reg = gw % a.n_regions, l_j = 0;
+#define PANSIM_CM_ISSUE_LOAD()                                                                               \
+    do {                                                                                                     \
+        const uint8_t *src_ = a.old_state + (uint64_t)(a.parents ? a.parents[l_row] : l_row) * a.row_stride + \
+                              (uint64_t)l_reg * REGION_BYTES;                                                \
+        const uint32_t s_ = l_j % CM_STAGES;                                                                 \
+        mbar_arrive_expect_tx(&bars[s_], REGION_BYTES);                                                      \
+        bulk_g2s(stages + s_ * REGION_BYTES, src_, REGION_BYTES, &bars[s_]);                                 \
+        l_j++; l_row += d_row; l_reg += d_reg;                                                               \
+        if (l_reg >= a.n_regions) { l_reg -= a.n_regions; l_row++; }                                         \
+    } while (0)
+
+    if (lane == 0) {
+        const uint32_t pre = n_my < (uint32_t)(CM_STAGES - 1) ? n_my : (uint32_t)(CM_STAGES - 1);
+#pragma unroll 1
+        for (uint32_t jj = 0; jj < pre; jj++) PANSIM_CM_ISSUE_LOAD();
+    }
+
+    uint32_t row = gw / a.n_regions, reg = gw % a.n_regions;
+    for (uint32_t j = 0; j < n_my; j++) {
+        const uint32_t s = j % CM_STAGES;
+        uint32_t *sw = reinterpret_cast<uint32_t *>(stages + s * REGION_BYTES);
+
+        // RNG work that does not need the data is done before waiting for the TMA load
+        const uint32_t greg = a.region0 + reg;
+        const uint64_t reg_site0 = (uint64_t)greg * REGION_SITES;
+        const uint64_t rem_sites = a.site_limit - reg_site0;
+        const uint32_t lim = rem_sites < REGION_SITES ? (uint32_t)rem_sites : REGION_SITES;
+        const uint4 mctr = make_ctr(greg * 32u + lane, row, a.gen, STREAM_CORE_MUT);
+        uint4 c0 = make_uint4(0, 0, 0, 0), c1 = make_uint4(0, 0, 0, 0);
+        uint32_t k = 0;
+        if (RNG && a.mut_nsub) {
+            c0 = philox4x32_10(mctr, a.key);
+            uint4 t = mctr;
+            t.w += 1u;
+            c1 = philox4x32_10(t, a.key);
+            k = poisson_fast(tab, a.mut_kmax, c0.x);
+            if (a.mut_nsub > 1) k += mut_count_extra(mctr, a.key, tab, a.mut_nsub, a.mut_kmax);
+        }
+
+        mbar_wait(&bars[s], (j / CM_STAGES) & 1u);
+
+        if (RNG && a.mut_nsub) {
+            // ---- SNP mutation (population.rs:512-539) ----
+            const uint32_t kw = __reduce_max_sync(0xffffffffu, k);      // warp-uniform trip counts
+            const MutChunk<DUMP> f{smem_u32(sw) | (lane * 4u), smem_u32(lut_raw), k, lane, row, lim, reg_site0, mctr, a.key, &a};
+            // calls 0,1:  c0.x count | c0.y digit bytes of chunks 0-3 | c0.z digit byte of chunk 4 + 3 reserve bytes |
+            //             c0.w, c1.x, c1.y, c1.z, c1.w position bytes of events 0..19
+            if (kw > 0u) {
+                uint32_t res = (c0.z >> 8) | 0xFF000000u;
+                f.run(0u, c0.y & 255u, c0.w, res);
+                if (kw > 4u) f.run(4u, (c0.y >> 8) & 255u, c1.x, res);
+                if (kw > 8u) f.run(8u, (c0.y >> 16) & 255u, c1.y, res);
+                if (kw > 12u) f.run(12u, c0.y >> 24, c1.z, res);
+                if (kw > 16u) f.run(16u, c0.z & 255u, c1.w, res);
+            }
+            // later calls carry 8 events each: x = 2 digit bytes + 2 reserve bytes, y, z = position bytes
+#pragma unroll 1
+            for (uint32_t base = CM_GROUP0, call = 2u; base < kw; base += CM_TAIL, call++) {
+                uint4 t = mctr;
+                t.w += call;
+                const uint4 c = philox4x32_10(t, a.key);
+                uint32_t res = (c.x >> 16) | 0xFFFF0000u;
+                f.run(base, c.x & 255u, c.y, res);
+                if (kw > base + 4u) f.run(base + 4u, (c.x >> 8) & 255u, c.z, res);
+            }
+            // ragged last region: clear whatever the events wrote beyond the end of the alignment
+            if (lim < REGION_SITES) {
+#pragma unroll 1
+                for (uint32_t kk = 0; kk < WORDS_PER_LANE; kk++) {
+                    const uint32_t site0 = (kk * 32u + lane) * 16u;
+                    const uint32_t nv = site0 >= lim ? 0u : min(16u, lim - site0);
+                    if (nv < 16u) sw[kk * 32u + lane] &= (1u << (2u * nv)) - 1u;
+                }
+            }
+            fence_proxy_async();     // generic-proxy writes -> visible to the bulk store
+        }
+        __syncwarp();
+
+        if (lane == 0) {
+            uint8_t *dst = a.new_state + (uint64_t)row * a.row_stride + (uint64_t)reg * REGION_BYTES;
+            bulk_s2g(dst, sw, REGION_BYTES);
+            bulk_commit();
+            if (j + CM_STAGES - 1 < n_my) {
+                bulk_wait_read<1>();      // the store that last used stage (j-1)%S has left smem
+                PANSIM_CM_ISSUE_LOAD();
+            }
+        }
+        __syncwarp();
+        row += d_row; reg += d_reg;
+        if (reg >= a.n_regions) { reg -= a.n_regions; row++; }
+    }
+    if (lane == 0) bulk_wait<0>();
+#undef PANSIM_CM_ISSUE_LOAD
+}
+
+}  // namespace pansim

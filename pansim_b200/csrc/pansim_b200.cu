@@ -13,7 +13,8 @@
 
 #include "acc_step.cuh"
 #include "common.cuh"
-#include "core_step.cuh"
+#include "core_hr.cuh"
+#include "core_mut.cuh"
 #include "distance.cuh"
 #include "pack.cuh"
 #include "replay.cuh"
@@ -77,6 +78,25 @@ std::vector<uint32_t> poisson_table_image(const HostPoissonTable &t)
     return img;
 }
 
+// core_mut.cuh image: [CM_GUIDE u16 guide entries][size thresholds]; entry = 2*k0 + many,
+// many = the bin holds two or more thresholds (poisson_fast finishes with a scan)
+std::vector<uint32_t> poisson_fast_image(const HostPoissonTable &t)
+{
+    std::vector<uint32_t> img(CM_GUIDE_WORDS + t.size, 0u);
+    for (uint32_t b = 0; b < CM_GUIDE; b++) {
+        const uint32_t lo = b << CM_GUIDE_SHIFT;
+        const uint32_t hi = lo | ((1u << CM_GUIDE_SHIFT) - 1u);
+        uint32_t k0 = 0, k1 = 0;
+        while (k0 < t.kmax && t.thr[k0] <= lo) k0++;
+        k1 = k0;
+        while (k1 < t.kmax && t.thr[k1] <= hi) k1++;
+        const uint32_t entry = 2u * k0 + (k1 > k0 + 1u ? 1u : 0u);
+        img[b >> 1] |= entry << (16u * (b & 1u));
+    }
+    for (uint32_t j = 0; j < t.size; j++) img[CM_GUIDE_WORDS + j] = t.thr[j];
+    return img;
+}
+
 struct EventPool {
     std::vector<cudaEvent_t> ev;
     size_t used = 0;
@@ -98,7 +118,7 @@ struct EventPool {
     }
 };
 
-enum TimeGroup { TG_SELECT = 0, TG_ACC, TG_CORE, TG_PAIR_CORE, TG_PAIR_ACC, TG_COUNT };
+enum TimeGroup { TG_SELECT = 0, TG_ACC, TG_CORE, TG_CORE_HR, TG_PAIR_CORE, TG_PAIR_ACC, TG_COUNT };
 
 }  // namespace
 
@@ -121,8 +141,11 @@ struct pansim_ctx {
     uint32_t acc_stride_words = 0, acc_words = 0;
 
     uint8_t *core[2] = {nullptr, nullptr};
-    uint8_t *core_snap = nullptr;    // two-pass mode: gathered + mutated rows, before recombination
-    bool two_pass_hr = false;
+    // recombination list (core_hr.cuh): entries collected by hr_collect_kernel, applied by hr_apply_kernel
+    unsigned long long *d_hr_list = nullptr;
+    uint32_t *d_hr_count = nullptr;      // two counters, used alternately
+    uint32_t hr_cap = 0;
+    int hr_parity = 0;
     uint32_t *acc[2] = {nullptr, nullptr};
     int core_cur = 0, acc_cur = 0;
     bool has_core = false, has_acc = false;
@@ -131,7 +154,7 @@ struct pansim_ctx {
     double *d_lw = nullptr, *d_logfit = nullptr, *d_avgdist = nullptr;
     int32_t *d_num_genes = nullptr;
     double *d_tmp_a = nullptr, *d_tmp_b = nullptr, *d_weights = nullptr, *d_cum = nullptr;
-    int *d_err = nullptr;
+    int *d_err = nullptr;                // [0] upload / selection errors, [1] recombination list overflow
     uint32_t *d_inter = nullptr;
     double *d_rowInvK = nullptr;
     uint32_t *d_gain_thr = nullptr;      // scratch (gene counts)
@@ -140,7 +163,8 @@ struct pansim_ctx {
     bool fitness_valid = false;   // d_logfit / d_num_genes match the current accessory state
     bool fitness_blocked = false; // large shapes: blocked (fixed-association) fitness sum instead of the sequential chain
 
-    HostPoissonTable tab_mut, tab_hr;
+    HostPoissonTable tab_mut, tab_hr;    // per 256-site block (SNPs), per 8192-site region (HR)
+    uint32_t *d_mut_img = nullptr;
     uint32_t flip_thr[2] = {0, 0};
     double flip_p[2] = {0, 0};
     double hgt_scale[2] = {0, 0};
@@ -190,6 +214,7 @@ struct pansim_ctx {
 
     uint32_t core_grid = 0, core_items_per_warp = 1;
     size_t core_smem = 0;
+    int core_occupancy = 0;
 };
 
 namespace {
@@ -270,6 +295,20 @@ int ensure_stage(pansim_ctx *c, size_t bytes)
     c->stage_cap = 0;
     CU(c, cudaMalloc(&c->d_stage, bytes));
     c->stage_cap = bytes;
+    return 0;
+}
+
+// the recombination list is sized 12 sigma above its mean; an overflow (which would drop events) is an error
+int check_hr_flag(pansim_ctx *c)
+{
+    if (!c->d_hr_list) return 0;
+    int flag = 0;
+    CU(c, cudaMemcpyAsync(&flag, c->d_err + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (flag) {
+        cudaMemsetAsync(c->d_err + 1, 0, sizeof(int), c->stream);
+        FAIL(c, PANSIM_ERR_STATE, "recombination list overflow: events were dropped in an earlier generation");
+    }
     return 0;
 }
 
@@ -394,7 +433,7 @@ int launch_acc_step(pansim_ctx *c, uint32_t gen)
     return 0;
 }
 
-void fill_core_args(pansim_ctx *c, CoreStepArgs &a, uint32_t gen)
+void fill_core_args(pansim_ctx *c, CoreMutArgs &a, uint32_t gen)
 {
     memset(&a, 0, sizeof a);
     a.old_state = c->core[c->core_cur];
@@ -408,49 +447,62 @@ void fill_core_args(pansim_ctx *c, CoreStepArgs &a, uint32_t gen)
     a.site_limit = c->site_end;
     a.key = make_uint2((uint32_t)c->cfg.seed, (uint32_t)(c->cfg.seed >> 32));
     a.gen = gen;
-    a.mut_tab = c->tab_mut.d_thr; a.mut_size = c->tab_mut.size; a.mut_nsub = c->tab_mut.nsub; a.mut_kmax = c->tab_mut.kmax;
-    a.hr_tab = c->tab_hr.d_thr; a.hr_size = c->tab_hr.size; a.hr_nsub = c->tab_hr.nsub; a.hr_kmax = c->tab_hr.kmax;
+    a.mut_img = c->d_mut_img; a.mut_size = c->tab_mut.size; a.mut_nsub = c->tab_mut.nsub; a.mut_kmax = c->tab_mut.kmax;
     a.dump_counters = c->d_dump_counters;
     a.dump_cap = c->dump_cap;
     a.d_mut_row = c->d_mut_row; a.d_mut_site = c->d_mut_site; a.d_mut_seq = c->d_mut_seq; a.d_mut_allele = c->d_mut_allele;
-    a.d_hr_rec = c->d_hr_rec; a.d_hr_locus = c->d_hr_locus; a.d_hr_donor = c->d_hr_donor; a.d_hr_seq = c->d_hr_seq;
-    a.d_hr_value = c->d_hr_value;
 }
 
-int launch_core_kernel(pansim_ctx *c, const CoreStepArgs &a, bool any_rng, cudaStream_t st)
+// homologous recombination on the rows the gather + SNP pass just wrote (core_hr.cuh)
+int launch_core_hr(pansim_ctx *c, uint32_t gen, cudaStream_t st)
 {
-    if (!any_rng) {
-        core_step_kernel<false, false><<<c->core_grid, CS_THREADS, c->core_smem, st>>>(a);
-    } else if (c->dump_enabled) {
-        core_step_kernel<true, true><<<c->core_grid, CS_THREADS, c->core_smem, st>>>(a);
-    } else {
-        core_step_kernel<true, false><<<c->core_grid, CS_THREADS, c->core_smem, st>>>(a);
-    }
+    HrArgs h;
+    memset(&h, 0, sizeof h);
+    h.state = reinterpret_cast<uint32_t *>(c->core[c->core_cur ^ 1]);
+    h.n_rows = c->N;
+    h.n_regions = c->n_regions;
+    h.region0 = c->region0;
+    h.row_stride_words = c->core_stride / 4;
+    h.site_limit = c->site_end;
+    h.key = make_uint2((uint32_t)c->cfg.seed, (uint32_t)(c->cfg.seed >> 32));
+    h.gen = gen;
+    h.tab = c->tab_hr.d_thr; h.nsub = c->tab_hr.nsub; h.kmax = c->tab_hr.kmax;
+    h.list = c->d_hr_list;
+    h.count = c->d_hr_count + c->hr_parity;
+    h.count_other = c->d_hr_count + (c->hr_parity ^ 1);
+    h.cap = c->hr_cap;
+    h.err_flag = c->d_err + 1;
+    h.dump_counters = c->d_dump_counters;
+    h.dump_cap = c->dump_cap;
+    h.d_hr_rec = c->d_hr_rec; h.d_hr_locus = c->d_hr_locus; h.d_hr_donor = c->d_hr_donor; h.d_hr_seq = c->d_hr_seq;
+    h.d_hr_value = c->d_hr_value;
+    const uint32_t grid = div_up64((uint64_t)c->N * c->n_regions, HR_WARPS);
+    if (c->dump_enabled)
+        hr_collect_kernel<true><<<grid, HR_WARPS * 32, 0, st>>>(h);
+    else
+        hr_collect_kernel<false><<<grid, HR_WARPS * 32, 0, st>>>(h);
     LAUNCH_CHECK(c);
+    hr_apply_kernel<<<c->sm_count * 8, 256, 0, st>>>(h.state, h.list, h.count, h.cap);
+    LAUNCH_CHECK(c);
+    c->hr_parity ^= 1;
     return 0;
 }
 
 int launch_core_step(pansim_ctx *c, uint32_t gen, bool rng, cudaStream_t st)
 {
     if (c->Ll == 0) return 0;
-    CoreStepArgs a;
+    CoreMutArgs a;
     fill_core_args(c, a, gen);
-    const bool any_rng = rng && (a.mut_nsub || a.hr_nsub);
-    if (any_rng && c->two_pass_hr && a.hr_nsub) {
-        // Heavy recombination: recomputing the donor's SNPs for every HR event would dominate.
-        // Pass 1 writes the gathered + mutated rows (the snapshot of population.rs:693-695) to a
-        // third buffer, pass 2 streams it into the new state applying the HR events, reading
-        // donor alleles straight from the snapshot. Same events (same counters) as the fused pass.
-        CoreStepArgs p1 = a;
-        p1.new_state = c->core_snap;
-        p1.hr_nsub = 0;
-        if (int rc = launch_core_kernel(c, p1, true, st)) return rc;
-        CoreStepArgs p2 = a;
-        p2.old_state = c->core_snap;
-        p2.snapshot_pass = 1;
-        if (int rc = launch_core_kernel(c, p2, true, st)) return rc;
-    } else {
-        if (int rc = launch_core_kernel(c, a, any_rng, st)) return rc;
+    if (!rng || !a.mut_nsub)
+        core_mut_kernel<false, false><<<c->core_grid, CM_THREADS, c->core_smem, st>>>(a);
+    else if (c->dump_enabled)
+        core_mut_kernel<true, true><<<c->core_grid, CM_THREADS, c->core_smem, st>>>(a);
+    else
+        core_mut_kernel<true, false><<<c->core_grid, CM_THREADS, c->core_smem, st>>>(a);
+    LAUNCH_CHECK(c);
+    if (rng && c->tab_hr.nsub) {
+        ScopedSpan s(c, TG_CORE_HR, st);
+        if (int rc = launch_core_hr(c, gen, st)) return rc;
     }
     c->core_cur ^= 1;
     return 0;
@@ -553,7 +605,7 @@ void pansim_destroy(pansim_ctx *c)
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->stream_core) cudaStreamSynchronize(c->stream_core);
-    void *ptrs[] = {c->core[0], c->core[1], c->core_snap, c->acc[0], c->acc[1], c->d_parents_buf[0], c->d_parents_buf[1], c->d_parents_buf[2], c->d_lw, c->d_logfit, c->d_avgdist,
+    void *ptrs[] = {c->core[0], c->core[1], c->d_hr_list, c->d_hr_count, c->d_mut_img, c->acc[0], c->acc[1], c->d_parents_buf[0], c->d_parents_buf[1], c->d_parents_buf[2], c->d_lw, c->d_logfit, c->d_avgdist,
                     c->d_num_genes, c->d_tmp_a, c->d_tmp_b, c->d_weights, c->d_cum, c->d_err, c->d_inter, c->d_rowInvK, c->d_gain_planes,
                     c->d_gain_thr, c->tab_mut.d_thr, c->tab_hr.d_thr, c->d_r1, c->d_r2, c->d_cd, c->d_in, c->d_un,
                     c->d_replay, c->d_hkeys, c->d_hvals, c->d_stage, c->d_groups, c->d_partner, c->d_orig, c->d_batches, c->d_tile_slots, c->d_tile_orig, c->d_dump_counters, c->d_mut_row, c->d_mut_site,
@@ -634,11 +686,17 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
         c->p_mut_site = -std::expm1(-rate_mut);
         c->p_hr_site = -std::expm1(-rate_hr);
         build_poisson_table(rate_mut * BLOCK_SITES, c->tab_mut);
-        build_poisson_table(rate_hr * BLOCK_SITES, c->tab_hr);
-        for (HostPoissonTable *t : {&c->tab_mut, &c->tab_hr}) {
-            const std::vector<uint32_t> img = poisson_table_image(*t);
-            CU(c, cudaMalloc(&t->d_thr, img.size() * sizeof(uint32_t)));
-            CU(c, cudaMemcpy(t->d_thr, img.data(), img.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        build_poisson_table(rate_hr * REGION_SITES, c->tab_hr);
+        if ((double)c->tab_hr.nsub * c->tab_hr.kmax > 1.5e7) FAIL(c, PANSIM_ERR_INVALID, "recombination rate too high (more than ~1e7 events per 8192-site region)");
+        {
+            const std::vector<uint32_t> img = poisson_fast_image(c->tab_mut);
+            CU(c, cudaMalloc(&c->d_mut_img, img.size() * sizeof(uint32_t)));
+            CU(c, cudaMemcpy(c->d_mut_img, img.data(), img.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        }
+        {
+            const std::vector<uint32_t> img = poisson_table_image(c->tab_hr);
+            CU(c, cudaMalloc(&c->tab_hr.d_thr, img.size() * sizeof(uint32_t)));
+            CU(c, cudaMemcpy(c->tab_hr.d_thr, img.data(), img.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         }
         for (uint32_t k = 0; k < cfg->n_compartments; k++) {
             const double sites = (double)(cfg->comp_hi[k] - cfg->comp_lo[k]);
@@ -665,12 +723,15 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
         // the bit-exact sequential fitness chain is kept up to 2^25 accessory cells (cfg1-3: 4e6)
         c->fitness_blocked = (uint64_t)c->N * c->G > (1ull << 25);
         if (const char *e = getenv("PANSIM_FITNESS_BLOCKED")) c->fitness_blocked = atoi(e) != 0;
-        // two-pass recombination when a site block expects more than ~2 HR events per generation
-        c->two_pass_hr = rate_hr * BLOCK_SITES > 2.0;
-        if (const char *e = getenv("PANSIM_TWO_PASS_HR")) c->two_pass_hr = atoi(e) != 0;
-        if (c->two_pass_hr && core_bytes) {
-            if (cudaMalloc(&c->core_snap, core_bytes) != cudaSuccess) FAIL(c, PANSIM_ERR_NOMEM, "cudaMalloc of %zu bytes (core snapshot) failed", core_bytes);
-            CU(c, cudaMemset(c->core_snap, 0, core_bytes));
+        if (c->tab_hr.nsub && core_bytes) {
+            // recombination list: one entry per changed cell; sized 12 sigma above the expected number of events
+            const double mean = rate_hr * (double)c->Ll * (double)c->N;
+            const double cap = mean + 12.0 * std::sqrt(mean) + 4096.0;
+            if (cap > 4.0e9) FAIL(c, PANSIM_ERR_INVALID, "recombination rate too high for one shard (%.3g events per generation)", mean);
+            c->hr_cap = (uint32_t)cap;
+            if (cudaMalloc(&c->d_hr_list, (size_t)c->hr_cap * 8) != cudaSuccess) FAIL(c, PANSIM_ERR_NOMEM, "cudaMalloc of %zu bytes (recombination list) failed", (size_t)c->hr_cap * 8);
+            CU(c, cudaMalloc(&c->d_hr_count, 2 * sizeof(uint32_t)));
+            CU(c, cudaMemset(c->d_hr_count, 0, 2 * sizeof(uint32_t)));
         }
         const size_t n = c->N;
         for (int i = 0; i < 3; i++) CU(c, cudaMalloc(&c->d_parents_buf[i], n * 4));
@@ -684,30 +745,30 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
         CU(c, cudaMalloc(&c->d_tmp_b, n * 8));
         CU(c, cudaMalloc(&c->d_weights, n * 8));
         CU(c, cudaMalloc(&c->d_cum, n * 8));
-        CU(c, cudaMalloc(&c->d_err, sizeof(int)));
-        CU(c, cudaMemset(c->d_err, 0, sizeof(int)));
+        CU(c, cudaMalloc(&c->d_err, 2 * sizeof(int)));
+        CU(c, cudaMemset(c->d_err, 0, 2 * sizeof(int)));
         CU(c, cudaMalloc(&c->d_rowInvK, 2 * n * 8));
         CU(c, cudaMalloc(&c->d_gain_thr, (size_t)(c->G ? c->G : 1) * 4));
         CU(c, cudaMalloc(&c->d_gain_planes, (size_t)(c->acc_words ? c->acc_words : 1) * 32 * 4));
         CU(c, cudaMalloc(&c->d_dump_counters, 2 * sizeof(uint32_t)));
         CU(c, cudaMemset(c->d_dump_counters, 0, 2 * sizeof(uint32_t)));
 
-        // launch shape of the fused core kernel: persistent, grid = SMs x resident CTAs
-        c->core_smem = core_step_smem_bytes(c->tab_mut.size, c->tab_hr.size);
+        // launch shape of the core kernel
+        c->core_smem = core_mut_smem_bytes(c->tab_mut.size);
         CU(c, cudaFuncSetAttribute(pair_core_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes()));
-        CU(c, cudaFuncSetAttribute(core_step_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->core_smem));
-        CU(c, cudaFuncSetAttribute(core_step_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->core_smem));
-        CU(c, cudaFuncSetAttribute(core_step_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->core_smem));
+        CU(c, cudaFuncSetAttribute(core_mut_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->core_smem));
+        CU(c, cudaFuncSetAttribute(core_mut_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->core_smem));
+        CU(c, cudaFuncSetAttribute(core_mut_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->core_smem));
         int occ = 0;
-        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, core_step_kernel<true, false>, CS_THREADS, c->core_smem));
-        if (occ < 1) FAIL(c, PANSIM_ERR_CUDA, "core_step_kernel does not fit on an SM (smem %zu)", c->core_smem);
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, core_mut_kernel<true, false>, CM_THREADS, c->core_smem));
+        if (occ < 1) FAIL(c, PANSIM_ERR_CUDA, "core_mut_kernel does not fit on an SM (smem %zu)", c->core_smem);
+        c->core_occupancy = occ;
         // short-lived CTAs (3 items per warp, tuned on B200): many waves over the resident slots
         const uint64_t items = (uint64_t)c->N * c->n_regions;
         c->core_items_per_warp = 3;
         if (const char *e = getenv("PANSIM_CORE_ITEMS_PER_WARP")) c->core_items_per_warp = (uint32_t)std::max(1, atoi(e));
-        const uint64_t per_cta = (uint64_t)CS_WARPS * c->core_items_per_warp;
+        const uint64_t per_cta = (uint64_t)CM_WARPS * c->core_items_per_warp;
         c->core_grid = (uint32_t)std::max<uint64_t>(1, (items + per_cta - 1) / per_cta);
-        (void)occ;
         return 0;
     };
     int rc = body();
@@ -728,7 +789,7 @@ int pansim_get_info(pansim_ctx *c, pansim_info *o)
     o->algorithmic_bytes_per_pair = 2ull * ((c->Ll + 3) / 4) + 2ull * ((c->G + 7) / 8);
     o->sm_count = (uint32_t)c->sm_count;
     o->core_step_grid = c->core_grid;
-    o->core_step_block = CS_THREADS;
+    o->core_step_block = CM_THREADS;
     o->core_step_smem = (uint32_t)c->core_smem;
     return 0;
 }
@@ -763,6 +824,7 @@ int pansim_get_timing(pansim_ctx *c, pansim_timing *o)
         g[s.group] += ms;
     }
     o->select_ms = g[TG_SELECT]; o->acc_step_ms = g[TG_ACC]; o->core_step_ms = g[TG_CORE];
+    o->core_hr_ms = g[TG_CORE_HR];
     o->pair_core_ms = g[TG_PAIR_CORE]; o->pair_acc_ms = g[TG_PAIR_ACC];
     return 0;
 }
@@ -840,6 +902,7 @@ int pansim_download_core(pansim_ctx *c, uint8_t *out)
     if (!c || !out) return PANSIM_ERR_INVALID;
     CU(c, cudaSetDevice(c->cfg.device));
     if (c->Ll == 0) return 0;
+    if (int rc = check_hr_flag(c)) return rc;
     uint32_t rows_per = (uint32_t)std::max<uint64_t>(1, (256ull << 20) / c->Ll);
     if (rows_per > c->N) rows_per = c->N;
     if (int rc = ensure_stage(c, (size_t)rows_per * c->Ll)) return rc;
