@@ -11,26 +11,32 @@
 // uniform on the other N-1 rows; the order among the events of one cell is the
 // draw order.
 //
-// Two kernels, because every donor read must see the pre-recombination state:
-//   hr_collect_kernel  one warp per (region, row), one event per lane. Reads
-//                      the donor's and the recipient's cell from the state
-//                      (read-only here) and appends (word, shift, allele XOR)
-//                      for every cell whose LAST event changes it. Same-cell
-//                      events are resolved here: __match_any_sync inside a
-//                      window of 32 events, a per-warp 8192-bit claim map over
-//                      windows visited last to first.
-//   hr_apply_kernel    atomicXor of the collected deltas (cells are distinct,
-//                      so the order of application is irrelevant).
-// Items are ordered region-major so that concurrently running warps read donor
-// cells of the same few column regions (L2 locality).
+// Two steps, because every donor read must see the pre-recombination state:
+//   collect  one warp per (region, 4 rows), one event per lane. Reads the
+//            donor's and the recipient's cell from the state (read-only here)
+//            and stores (site, allele XOR) for every cell whose LAST event
+//            changes it, into the fixed slot array of that (region, row) item
+//            (u16 entries; an item that overflows its slots appends to a small
+//            global list). Same-cell events are resolved here:
+//            __match_any_sync inside a window of 32 events, a per-warp
+//            8192-bit claim map over windows visited last to first.
+//   apply    atomicXor of the collected deltas (cells are distinct, so the
+//            order of application is irrelevant).
+// The steps run either as two kernels after core_mut_kernel (this file) or
+// inside the fused generation kernel of core_gen.cuh, column block by column
+// block while the gather+SNP pass is still streaming the next blocks.
 #pragma once
 #include "common.cuh"
 
 namespace pansim {
 
-constexpr uint32_t STREAM_CORE_HR_COUNT = 7;          // counter word 3 = 7 << 16 (| 0x8000 | i for extra count draws)
+constexpr uint32_t STREAM_CORE_HR_COUNT = 7;          // one call per (region, 4 rows): word i = count uniform of row 4q+i
+constexpr uint32_t STREAM_CORE_HR_EXTRA = 8;          // extra count draws of (region, row) for means above the table range
 constexpr uint32_t HR_EVENT_W0 = 0x01000000u;         // counter word 3 of event e = HR_EVENT_W0 + e
 constexpr int HR_WARPS = 8;
+constexpr uint32_t HR_ROWS_PER_TASK = 4;
+constexpr uint32_t HR_CLAIM_WORDS = REGION_SITES / 32;   // per warp
+constexpr uint32_t HR_APPLY_ITEMS = 32;                  // items per apply task (one warp)
 
 struct HrArgs {
     uint32_t *state;          // packed core rows (gathered + mutated), words
@@ -40,11 +46,14 @@ struct HrArgs {
     uint2 key;
     uint32_t gen;
     const uint32_t *tab;      // device image [256 guide][size thresholds] of Poisson(region mean / nsub)
-    uint32_t nsub, kmax;
-    unsigned long long *list; // entries: word index << 7 | shift << 2 | allele xor
-    uint32_t *count;          // entries appended by this launch
-    uint32_t *count_other;    // zeroed here for the next generation
-    uint32_t cap;
+    uint32_t tab_words, nsub, kmax;
+    uint16_t *slots;          // [items][slot_cap]: site-in-region | xor << 13; item = region * n_rows + row
+    uint16_t *counts;         // [items]
+    uint32_t slot_cap;
+    unsigned long long *ovf;  // overflow entries: word index << 7 | shift << 2 | xor
+    uint32_t *ovf_count;      // [0] used by this generation
+    uint32_t *ovf_count_other;// zeroed for the next one
+    uint32_t ovf_cap;
     int *err_flag;
     // optional event dump
     uint32_t *dump_counters;  // [1] = HR events
@@ -53,37 +62,37 @@ struct HrArgs {
     uint8_t *d_hr_value;
 };
 
-template <bool DUMP>
-__global__ void __launch_bounds__(HR_WARPS * 32) hr_collect_kernel(const HrArgs a)
+static inline size_t hr_collect_smem_bytes(uint32_t tab_words)
 {
-    __shared__ uint32_t claim_all[HR_WARPS][REGION_SITES / 32];
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (blockIdx.x == 0 && threadIdx.x == 0) *a.count_other = 0u;
-    const uint64_t item = (uint64_t)blockIdx.x * HR_WARPS + warp;
-    if (item >= (uint64_t)a.n_rows * a.n_regions) return;
-    const uint32_t reg = (uint32_t)(item / a.n_rows), row = (uint32_t)(item % a.n_rows);
+    return (size_t)tab_words * 4 + (size_t)HR_WARPS * HR_CLAIM_WORDS * 4;
+}
+
+// one (region, row) item; warp-collective
+template <bool DUMP>
+__device__ __forceinline__ void hr_collect_item(const HrArgs &a, uint32_t *claim, uint32_t reg, uint32_t row,
+                                                uint32_t K, uint32_t lane)
+{
+    const uint64_t item = (uint64_t)reg * a.n_rows + row;
+    if (K == 0u) {
+        if (lane == 0) a.counts[item] = 0;
+        return;
+    }
     const uint32_t greg = a.region0 + reg;
-
-    const uint4 cctr = make_ctr(greg, row, a.gen, STREAM_CORE_HR_COUNT);
-    const uint32_t first = philox4x32_10(cctr, a.key).x;
-    const uint32_t K = stream_count(cctr, a.key, first, a.tab, a.nsub, a.kmax);     // warp-uniform
-    if (K == 0u) return;
-
     const uint64_t reg_site0 = (uint64_t)greg * REGION_SITES;
     const uint64_t rem_sites = a.site_limit - reg_site0;
     const uint32_t lim = rem_sites < REGION_SITES ? (uint32_t)rem_sites : REGION_SITES;
     const uint32_t n_other = a.n_rows - 1u;
     const uint64_t reg_word0 = (uint64_t)reg * REGION_WORDS;
     const uint64_t own_word0 = (uint64_t)row * a.row_stride_words + reg_word0;
+    uint16_t *slots = a.slots + item * a.slot_cap;
 
-    uint32_t *claim = claim_all[warp];
     const bool multi = K > 32u;
     if (multi) {
 #pragma unroll
-        for (int i = 0; i < (int)(REGION_SITES / 32 / 32); i++) claim[i * 32 + lane] = 0u;
+        for (int i = 0; i < (int)(HR_CLAIM_WORDS / 32); i++) claim[i * 32 + lane] = 0u;
         __syncwarp();
     }
-
+    uint32_t n_emit = 0;
 #pragma unroll 1
     for (int base = (int)((K - 1u) & ~31u); base >= 0; base -= 32) {
         const uint32_t e = (uint32_t)base + lane;
@@ -104,11 +113,13 @@ __global__ void __launch_bounds__(HR_WARPS * 32) hr_collect_kernel(const HrArgs 
             const uint32_t bit = 1u << (pos & 31u);
             keep = (atomicOr(&claim[pos >> 5], bit) & bit) == 0u;
         }
-        uint32_t delta = 0, sh = (pos & 15u) * 2u;
+        uint32_t delta = 0;
+        const uint32_t sh = (pos & 15u) * 2u;
         if (keep || (DUMP && valid)) {
-            const uint32_t dw = __ldg(a.state + (uint64_t)donor * a.row_stride_words + reg_word0 + (pos >> 4));
+            // L2 loads: in the fused kernel these rows were written by other SMs of the same launch
+            const uint32_t dw = __ldcg(a.state + (uint64_t)donor * a.row_stride_words + reg_word0 + (pos >> 4));
             const uint32_t v = (dw >> sh) & 3u;
-            if (keep) delta = ((__ldg(a.state + own_word0 + (pos >> 4)) >> sh) & 3u) ^ v;
+            if (keep) delta = ((__ldcg(a.state + own_word0 + (pos >> 4)) >> sh) & 3u) ^ v;
             if (DUMP) {
                 const uint32_t slot = atomicAdd(&a.dump_counters[1], 1u);
                 if (slot < a.dump_cap) {
@@ -121,29 +132,171 @@ __global__ void __launch_bounds__(HR_WARPS * 32) hr_collect_kernel(const HrArgs 
             }
         }
         const uint32_t emit = __ballot_sync(0xffffffffu, delta != 0u);
-        if (emit) {
-            uint32_t at = 0;
-            if (lane == 0) at = atomicAdd(a.count, (uint32_t)__popc(emit));
-            at = __shfl_sync(0xffffffffu, at, 0) + (uint32_t)__popc(emit & ((1u << lane) - 1u));
-            if (delta) {
-                if (at < a.cap)
-                    a.list[at] = ((unsigned long long)(own_word0 + (pos >> 4)) << 7) | (sh << 2) | delta;
+        if (delta) {
+            const uint32_t at = n_emit + (uint32_t)__popc(emit & ((1u << lane) - 1u));
+            if (at < a.slot_cap) {
+                slots[at] = (uint16_t)(pos | (delta << 13));
+            } else {
+                const uint32_t o = atomicAdd(a.ovf_count, 1u);
+                if (o < a.ovf_cap)
+                    a.ovf[o] = ((unsigned long long)(own_word0 + (pos >> 4)) << 7) | (sh << 2) | delta;
                 else
                     *a.err_flag = 2;
             }
         }
+        n_emit += (uint32_t)__popc(emit);
         if (multi) __syncwarp();
+    }
+    if (lane == 0) a.counts[item] = (uint16_t)min(n_emit, a.slot_cap);
+}
+
+// task = (region, rows 4q .. 4q+3): one Philox call carries the four count uniforms. When every row
+// has at most 32 events (one window each) the four windows are processed together: all Philox
+// calls, then all loads, then all stores, so one L2/DRAM round trip serves the whole task.
+template <bool DUMP>
+__device__ __forceinline__ void hr_collect_task(const HrArgs &a, const uint32_t *tab, uint32_t *claim, uint32_t reg,
+                                                uint32_t q, uint32_t lane)
+{
+    constexpr int R = (int)HR_ROWS_PER_TASK;
+    const uint32_t greg = a.region0 + reg;
+    const uint4 cc = philox4x32_10(make_ctr(greg, q, a.gen, STREAM_CORE_HR_COUNT), a.key);
+    const uint32_t u[R] = {cc.x, cc.y, cc.z, cc.w};
+    uint32_t K[R];
+    uint32_t kmaxi = 0;
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+        const uint32_t row = q * R + i;
+        K[i] = 0;
+        if (row < a.n_rows) {
+            K[i] = poisson_from_uniform(tab, a.kmax, u[i]);                                        // warp-uniform
+            if (a.nsub > 1) K[i] += stream_count_extra(make_ctr(greg, row, a.gen, STREAM_CORE_HR_EXTRA), a.key, tab, a.nsub, a.kmax);
+        }
+        kmaxi = max(kmaxi, K[i]);
+    }
+    if (kmaxi > 32u) {
+#pragma unroll 1
+        for (int i = 0; i < R; i++)
+            if (q * R + i < a.n_rows) hr_collect_item<DUMP>(a, claim, reg, q * R + i, K[i], lane);
+        return;
+    }
+
+    const uint64_t reg_site0 = (uint64_t)greg * REGION_SITES;
+    const uint64_t rem_sites = a.site_limit - reg_site0;
+    const uint32_t lim = rem_sites < REGION_SITES ? (uint32_t)rem_sites : REGION_SITES;
+    const uint32_t n_other = a.n_rows - 1u;
+    const uint32_t *col = a.state + (uint64_t)reg * REGION_WORDS;
+    uint32_t pos[R], donor[R];
+    bool valid[R], keep[R];
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+        const uint32_t row = q * R + i;
+        pos[i] = 0; donor[i] = 0; valid[i] = false;
+        if (lane < K[i]) {
+            const uint4 r = philox4x32_10(make_uint4(greg, row, a.gen, HR_EVENT_W0 + lane), a.key);
+            pos[i] = r.x >> 19;
+            donor[i] = (uint32_t)__umul64hi(((uint64_t)r.y << 32) | r.z, (uint64_t)n_other);
+            donor[i] += donor[i] >= row ? 1u : 0u;
+            valid[i] = pos[i] < lim;
+        }
+    }
+    uint32_t dw[R], ow[R];
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+        const uint32_t same = __match_any_sync(0xffffffffu, valid[i] ? pos[i] : (0x80000000u | lane));
+        keep[i] = valid[i] && ((same >> lane) >> 1) == 0u;
+        dw[i] = 0; ow[i] = 0;
+        if (keep[i] || (DUMP && valid[i])) dw[i] = __ldcg(col + (uint64_t)donor[i] * a.row_stride_words + (pos[i] >> 4));
+        if (keep[i]) ow[i] = __ldcg(col + (uint64_t)(q * R + i) * a.row_stride_words + (pos[i] >> 4));
+    }
+#pragma unroll
+    for (int i = 0; i < R; i++) {
+        const uint32_t row = q * R + i;
+        if (row >= a.n_rows) break;
+        const uint64_t item = (uint64_t)reg * a.n_rows + row;
+        const uint32_t sh = (pos[i] & 15u) * 2u;
+        const uint32_t v = (dw[i] >> sh) & 3u;
+        const uint32_t delta = keep[i] ? (((ow[i] >> sh) & 3u) ^ v) : 0u;
+        if (DUMP && valid[i]) {
+            const uint32_t slot = atomicAdd(&a.dump_counters[1], 1u);
+            if (slot < a.dump_cap) {
+                a.d_hr_rec[slot] = row;
+                a.d_hr_locus[slot] = (uint32_t)(reg_site0 + pos[i]);
+                a.d_hr_donor[slot] = donor[i];
+                a.d_hr_seq[slot] = lane;
+                a.d_hr_value[slot] = (uint8_t)(1u << v);
+            }
+        }
+        const uint32_t emit = __ballot_sync(0xffffffffu, delta != 0u);
+        if (delta) a.slots[item * a.slot_cap + (uint32_t)__popc(emit & ((1u << lane) - 1u))] = (uint16_t)(pos[i] | (delta << 13));
+        if (lane == 0) a.counts[item] = (uint16_t)__popc(emit);
     }
 }
 
-__global__ void __launch_bounds__(256) hr_apply_kernel(uint32_t *state, const unsigned long long *list,
-                                                       const uint32_t *count, uint32_t cap)
+// apply the slots of items [item0, item0 + n) (n <= 32): one item per lane, its slot line read
+// with 16-byte loads (slot_cap is a multiple of 32 entries = 64 bytes)
+__device__ __forceinline__ void hr_apply_task(const HrArgs &a, uint64_t item0, uint32_t n, uint32_t lane)
 {
-    const uint32_t n = min(*count, cap);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const unsigned long long e = list[i];
-        atomicXor(state + (e >> 7), (uint32_t)(e & 3u) << (uint32_t)((e >> 2) & 31u));
+    if (lane >= n) return;
+    const uint64_t item = item0 + lane;
+    const uint32_t cnt = __ldcg(a.counts + item);
+    if (cnt == 0u) return;
+    const uint32_t reg = (uint32_t)(item / a.n_rows), row = (uint32_t)(item % a.n_rows);
+    uint32_t *own = a.state + (uint64_t)row * a.row_stride_words + (uint64_t)reg * REGION_WORDS;
+    const uint4 *line = reinterpret_cast<const uint4 *>(a.slots + item * a.slot_cap);
+#pragma unroll 1
+    for (uint32_t e0 = 0; e0 < cnt; e0 += 32) {
+        uint4 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = (e0 + 8u * j < cnt) ? __ldcg(line + (e0 >> 3) + j) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t w[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+                const uint32_t en = (w[t >> 1] >> (16 * (t & 1))) & 0xFFFFu;
+                const uint32_t pos = en & 0x1FFFu;
+                if (e0 + 8u * j + t < cnt) atomicXor(own + (pos >> 4), (en >> 13) << ((pos & 15u) * 2u));
+            }
+        }
     }
+}
+
+__device__ __forceinline__ void hr_apply_overflow(const HrArgs &a, uint32_t first, uint32_t stride)
+{
+    const uint32_t n = min(*a.ovf_count, a.ovf_cap);
+    for (uint32_t i = first; i < n; i += stride) {
+        const unsigned long long e = __ldcg(a.ovf + i);
+        atomicXor(a.state + (e >> 7), (uint32_t)(e & 3u) << (uint32_t)((e >> 2) & 31u));
+    }
+}
+
+// ---- stand-alone launches (after core_mut_kernel has finished) ----------------------------
+
+// grid = ceil(tasks / HR_WARPS), tasks = n_regions * ceil(n_rows / 4), task = region-major
+template <bool DUMP>
+__global__ void __launch_bounds__(HR_WARPS * 32) hr_collect_kernel(const HrArgs a)
+{
+    extern __shared__ uint32_t hr_smem[];
+    uint32_t *tab = hr_smem;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t *claim = hr_smem + a.tab_words + warp * HR_CLAIM_WORDS;
+    for (uint32_t i = threadIdx.x; i < a.tab_words; i += blockDim.x) tab[i] = a.tab[i];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.ovf_count_other = 0u;
+    __syncthreads();
+    const uint32_t qn = (a.n_rows + HR_ROWS_PER_TASK - 1) / HR_ROWS_PER_TASK;
+    const uint64_t task = (uint64_t)blockIdx.x * HR_WARPS + warp;
+    if (task >= (uint64_t)a.n_regions * qn) return;
+    hr_collect_task<DUMP>(a, tab, claim, (uint32_t)(task / qn), (uint32_t)(task % qn), lane);
+}
+
+// grid = ceil(items / (32 * HR_WARPS)); block 0 also drains the overflow list
+__global__ void __launch_bounds__(HR_WARPS * 32) hr_apply_kernel(const HrArgs a)
+{
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t items = (uint64_t)a.n_rows * a.n_regions;
+    const uint64_t item0 = ((uint64_t)blockIdx.x * HR_WARPS + warp) * HR_APPLY_ITEMS;
+    if (item0 < items) hr_apply_task(a, item0, (uint32_t)min((uint64_t)HR_APPLY_ITEMS, items - item0), lane);
+    hr_apply_overflow(a, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
 }
 
 }  // namespace pansim

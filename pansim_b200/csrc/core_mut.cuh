@@ -165,24 +165,35 @@ struct MutChunk {
     }
 };
 
-template <bool RNG, bool DUMP>
-__global__ void __launch_bounds__(CM_THREADS, 4) core_mut_kernel(const CoreMutArgs a)
+// shared-memory carve-up of one CTA (dynamic shared memory, re-based to a 2 KiB boundary)
+struct MutSmem {
+    uint8_t *stages;     // CM_WARPS x CM_STAGES x 2 KiB
+    uint8_t *lut;        // 243 x uint4
+    uint32_t *tab;       // Poisson image
+    uint64_t *bars;      // CM_WARPS x CM_STAGES mbarriers
+};
+
+__device__ __forceinline__ MutSmem mut_smem_carve(uint8_t *smem_dyn, uint32_t mut_size)
 {
-    extern __shared__ uint8_t smem_dyn[];
     // stages must sit on 2 KiB boundaries of the shared window (the slot address is an OR)
     const uint32_t pad = (2048u - (smem_u32(smem_dyn) & 2047u)) & 2047u;
-    uint8_t *smem_raw = smem_dyn + pad;
-    uint8_t *lut_raw = smem_raw + (size_t)CM_WARPS * CM_STAGES * REGION_BYTES;
-    uint32_t *tab = reinterpret_cast<uint32_t *>(lut_raw + CM_LUT_BYTES);
-    uint64_t *bars_all = reinterpret_cast<uint64_t *>(tab + CM_GUIDE_WORDS + a.mut_size);
+    MutSmem m;
+    m.stages = smem_dyn + pad;
+    m.lut = m.stages + (size_t)CM_WARPS * CM_STAGES * REGION_BYTES;
+    m.tab = reinterpret_cast<uint32_t *>(m.lut + CM_LUT_BYTES);
+    m.bars = reinterpret_cast<uint64_t *>(m.tab + CM_GUIDE_WORDS + mut_size);
+    return m;
+}
 
+// CTA prologue: Poisson image and digit table into shared memory, mbarriers initialised.
+// Ends with __syncthreads().
+template <bool RNG>
+__device__ __forceinline__ void mut_cta_setup(const CoreMutArgs &a, const MutSmem &m)
+{
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint8_t *stages = smem_raw + (size_t)warp * CM_STAGES * REGION_BYTES;
-    uint64_t *bars = bars_all + warp * CM_STAGES;
-
     if (RNG) {
 #pragma unroll 1
-        for (uint32_t i = threadIdx.x; i < CM_GUIDE_WORDS + a.mut_size; i += CM_THREADS) tab[i] = a.mut_img[i];
+        for (uint32_t i = threadIdx.x; i < CM_GUIDE_WORDS + a.mut_size; i += CM_THREADS) m.tab[i] = a.mut_img[i];
         if (threadIdx.x < CM_LUT_ENTRIES) {
             uint32_t v = threadIdx.x;
             uint4 e;
@@ -190,38 +201,43 @@ __global__ void __launch_bounds__(CM_THREADS, 4) core_mut_kernel(const CoreMutAr
             e.y = (v % 3u + 1u) * 0x55555555u; v /= 3u;
             e.z = (v % 3u + 1u) * 0x55555555u; v /= 3u;
             e.w = (v % 3u + 1u) * 0x55555555u;
-            reinterpret_cast<uint4 *>(lut_raw)[threadIdx.x] = e;
+            reinterpret_cast<uint4 *>(m.lut)[threadIdx.x] = e;
         }
     }
     if (lane == 0) {
-        for (int s = 0; s < CM_STAGES; s++) mbar_init(&bars[s], 1);
+        for (int s = 0; s < CM_STAGES; s++) mbar_init(&m.bars[warp * CM_STAGES + s], 1);
         fence_mbar_init();
     }
     __syncthreads();
+}
 
-    // CTA b covers items [b*C, (b+1)*C), C = CM_WARPS*items_per_warp; warp w takes b*C + w + 8j.
-    // CTAs are short-lived on purpose: SM slots turn over every few tens of microseconds, so the
-    // (higher-priority) accessory/selection kernels of the next generation can slip in between.
-    const uint32_t total = a.n_rows * a.n_regions;
-    const uint32_t cta_items = CM_WARPS * a.items_per_warp;
-    const uint32_t cta_base = blockIdx.x * cta_items;
-    const uint32_t cta_end = min(total, cta_base + cta_items);
-    const uint32_t gw = cta_base + warp;
-    if (gw >= cta_end) return;
-    const uint32_t n_my = (cta_end - gw + CM_WARPS - 1) / CM_WARPS;
-    const uint32_t d_row = CM_WARPS / a.n_regions, d_reg = CM_WARPS % a.n_regions;
+// Items [item_begin, item_end) of a column block of `blk_regs` regions starting at local region
+// `blk_reg0`: item t -> row t / blk_regs, region blk_reg0 + t % blk_regs. Warp w takes
+// item_begin + w + 8j. Returns when all bulk stores of the calling warp have completed.
+template <bool RNG, bool DUMP>
+__device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSmem &m, uint32_t item_begin,
+                                              uint32_t item_end, uint32_t blk_regs, uint32_t blk_reg0)
+{
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *stages = m.stages + (size_t)warp * CM_STAGES * REGION_BYTES;
+    uint64_t *bars = m.bars + warp * CM_STAGES;
+    const uint32_t *tab = m.tab;
+    const uint32_t gw = item_begin + warp;
+    if (gw >= item_end) return;
+    const uint32_t n_my = (item_end - gw + CM_WARPS - 1) / CM_WARPS;
+    const uint32_t d_row = CM_WARPS / blk_regs, d_reg = CM_WARPS % blk_regs;
 
     // the load side runs CM_STAGES-1 items ahead with its own (row, reg) cursor (lane 0 only)
-    uint32_t l_row = gw / a.n_regions, l_reg = gw % a.n_regions, l_j = 0;
+    uint32_t l_row = gw / blk_regs, l_reg = gw % blk_regs, l_j = 0;
 #define PANSIM_CM_ISSUE_LOAD()                                                                               \
     do {                                                                                                     \
         const uint8_t *src_ = a.old_state + (uint64_t)(a.parents ? a.parents[l_row] : l_row) * a.row_stride + \
-                              (uint64_t)l_reg * REGION_BYTES;                                                \
+                              (uint64_t)(blk_reg0 + l_reg) * REGION_BYTES;                                   \
         const uint32_t s_ = l_j % CM_STAGES;                                                                 \
         mbar_arrive_expect_tx(&bars[s_], REGION_BYTES);                                                      \
         bulk_g2s(stages + s_ * REGION_BYTES, src_, REGION_BYTES, &bars[s_]);                                 \
         l_j++; l_row += d_row; l_reg += d_reg;                                                               \
-        if (l_reg >= a.n_regions) { l_reg -= a.n_regions; l_row++; }                                         \
+        if (l_reg >= blk_regs) { l_reg -= blk_regs; l_row++; }                                               \
     } while (0)
 
     if (lane == 0) {
@@ -230,10 +246,11 @@ __global__ void __launch_bounds__(CM_THREADS, 4) core_mut_kernel(const CoreMutAr
         for (uint32_t jj = 0; jj < pre; jj++) PANSIM_CM_ISSUE_LOAD();
     }
 
-    uint32_t row = gw / a.n_regions, reg = gw % a.n_regions;
+    uint32_t row = gw / blk_regs, breg = gw % blk_regs;
     for (uint32_t j = 0; j < n_my; j++) {
         const uint32_t s = j % CM_STAGES;
         uint32_t *sw = reinterpret_cast<uint32_t *>(stages + s * REGION_BYTES);
+        const uint32_t reg = blk_reg0 + breg;
 
         // RNG work that does not need the data is done before waiting for the TMA load
         const uint32_t greg = a.region0 + reg;
@@ -257,7 +274,7 @@ __global__ void __launch_bounds__(CM_THREADS, 4) core_mut_kernel(const CoreMutAr
         if (RNG && a.mut_nsub) {
             // ---- SNP mutation (population.rs:512-539) ----
             const uint32_t kw = __reduce_max_sync(0xffffffffu, k);      // warp-uniform trip counts
-            const MutChunk<DUMP> f{smem_u32(sw) | (lane * 4u), smem_u32(lut_raw), k, lane, row, lim, reg_site0, mctr, a.key, &a};
+            const MutChunk<DUMP> f{smem_u32(sw) | (lane * 4u), smem_u32(m.lut), k, lane, row, lim, reg_site0, mctr, a.key, &a};
             // calls 0,1:  c0.x count | c0.y digit bytes of chunks 0-3 | c0.z digit byte of chunk 4 + 3 reserve bytes |
             //             c0.w, c1.x, c1.y, c1.z, c1.w position bytes of events 0..19
             if (kw > 0u) {
@@ -301,11 +318,26 @@ __global__ void __launch_bounds__(CM_THREADS, 4) core_mut_kernel(const CoreMutAr
             }
         }
         __syncwarp();
-        row += d_row; reg += d_reg;
-        if (reg >= a.n_regions) { reg -= a.n_regions; row++; }
+        row += d_row; breg += d_reg;
+        if (breg >= blk_regs) { breg -= blk_regs; row++; }
     }
     if (lane == 0) bulk_wait<0>();
 #undef PANSIM_CM_ISSUE_LOAD
+}
+
+// Stand-alone launch: CTA b covers items [b*C, (b+1)*C) of the whole shard, C = CM_WARPS*items_per_warp.
+// CTAs are short-lived on purpose: SM slots turn over every few tens of microseconds, so the
+// (higher-priority) accessory/selection kernels of the next generation can slip in between.
+template <bool RNG, bool DUMP>
+__global__ void __launch_bounds__(CM_THREADS, 4) core_mut_kernel(const CoreMutArgs a)
+{
+    extern __shared__ uint8_t smem_dyn[];
+    const MutSmem m = mut_smem_carve(smem_dyn, a.mut_size);
+    mut_cta_setup<RNG>(a, m);
+    const uint32_t total = a.n_rows * a.n_regions;
+    const uint32_t cta_items = CM_WARPS * a.items_per_warp;
+    const uint32_t cta_base = blockIdx.x * cta_items;
+    mut_cta_items<RNG, DUMP>(a, m, cta_base, min(total, cta_base + cta_items), a.n_regions, 0u);
 }
 
 }  // namespace pansim

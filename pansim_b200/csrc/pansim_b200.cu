@@ -13,6 +13,7 @@
 
 #include "acc_step.cuh"
 #include "common.cuh"
+#include "core_gen.cuh"
 #include "core_hr.cuh"
 #include "core_mut.cuh"
 #include "distance.cuh"
@@ -141,11 +142,18 @@ struct pansim_ctx {
     uint32_t acc_stride_words = 0, acc_words = 0;
 
     uint8_t *core[2] = {nullptr, nullptr};
-    // recombination list (core_hr.cuh): entries collected by hr_collect_kernel, applied by hr_apply_kernel
-    unsigned long long *d_hr_list = nullptr;
-    uint32_t *d_hr_count = nullptr;      // two counters, used alternately
-    uint32_t hr_cap = 0;
+    // recombination (core_hr.cuh): per-item slots filled by the collect step, drained by the apply step
+    uint16_t *d_hr_slots = nullptr, *d_hr_counts = nullptr;
+    uint32_t hr_slot_cap = 0;
+    unsigned long long *d_hr_ovf = nullptr;
+    uint32_t *d_hr_ovf_count = nullptr;  // two counters, used alternately
+    uint32_t hr_ovf_cap = 0;
     int hr_parity = 0;
+    // fused generation kernel (core_gen.cuh)
+    bool core_fused = false;             // measured slower than the three launches (HR tail inside 55 KB CTAs); opt-in via PANSIM_CORE_FUSED=1
+    GenSched sched{};
+    uint32_t *d_gen_ctl = nullptr;       // two control blocks, used alternately
+    size_t hr_smem = 0;
     uint32_t *acc[2] = {nullptr, nullptr};
     int core_cur = 0, acc_cur = 0;
     bool has_core = false, has_acc = false;
@@ -301,13 +309,13 @@ int ensure_stage(pansim_ctx *c, size_t bytes)
 // the recombination list is sized 12 sigma above its mean; an overflow (which would drop events) is an error
 int check_hr_flag(pansim_ctx *c)
 {
-    if (!c->d_hr_list) return 0;
+    if (!c->d_hr_slots) return 0;
     int flag = 0;
     CU(c, cudaMemcpyAsync(&flag, c->d_err + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     if (flag) {
         cudaMemsetAsync(c->d_err + 1, 0, sizeof(int), c->stream);
-        FAIL(c, PANSIM_ERR_STATE, "recombination list overflow: events were dropped in an earlier generation");
+        FAIL(c, PANSIM_ERR_STATE, "recombination overflow list full: events were dropped in an earlier generation");
     }
     return 0;
 }
@@ -453,10 +461,8 @@ void fill_core_args(pansim_ctx *c, CoreMutArgs &a, uint32_t gen)
     a.d_mut_row = c->d_mut_row; a.d_mut_site = c->d_mut_site; a.d_mut_seq = c->d_mut_seq; a.d_mut_allele = c->d_mut_allele;
 }
 
-// homologous recombination on the rows the gather + SNP pass just wrote (core_hr.cuh)
-int launch_core_hr(pansim_ctx *c, uint32_t gen, cudaStream_t st)
+void fill_hr_args(pansim_ctx *c, HrArgs &h, uint32_t gen)
 {
-    HrArgs h;
     memset(&h, 0, sizeof h);
     h.state = reinterpret_cast<uint32_t *>(c->core[c->core_cur ^ 1]);
     h.n_rows = c->N;
@@ -466,23 +472,34 @@ int launch_core_hr(pansim_ctx *c, uint32_t gen, cudaStream_t st)
     h.site_limit = c->site_end;
     h.key = make_uint2((uint32_t)c->cfg.seed, (uint32_t)(c->cfg.seed >> 32));
     h.gen = gen;
-    h.tab = c->tab_hr.d_thr; h.nsub = c->tab_hr.nsub; h.kmax = c->tab_hr.kmax;
-    h.list = c->d_hr_list;
-    h.count = c->d_hr_count + c->hr_parity;
-    h.count_other = c->d_hr_count + (c->hr_parity ^ 1);
-    h.cap = c->hr_cap;
+    h.tab = c->tab_hr.d_thr; h.tab_words = GUIDE_ENTRIES + c->tab_hr.size; h.nsub = c->tab_hr.nsub; h.kmax = c->tab_hr.kmax;
+    h.slots = c->d_hr_slots;
+    h.counts = c->d_hr_counts;
+    h.slot_cap = c->hr_slot_cap;
+    h.ovf = c->d_hr_ovf;
+    h.ovf_count = c->d_hr_ovf_count + c->hr_parity;
+    h.ovf_count_other = c->d_hr_ovf_count + (c->hr_parity ^ 1);
+    h.ovf_cap = c->hr_ovf_cap;
     h.err_flag = c->d_err + 1;
     h.dump_counters = c->d_dump_counters;
     h.dump_cap = c->dump_cap;
     h.d_hr_rec = c->d_hr_rec; h.d_hr_locus = c->d_hr_locus; h.d_hr_donor = c->d_hr_donor; h.d_hr_seq = c->d_hr_seq;
     h.d_hr_value = c->d_hr_value;
-    const uint32_t grid = div_up64((uint64_t)c->N * c->n_regions, HR_WARPS);
+}
+
+// homologous recombination on the rows the gather + SNP pass just wrote, as two launches (core_hr.cuh)
+int launch_core_hr(pansim_ctx *c, uint32_t gen, cudaStream_t st)
+{
+    HrArgs h;
+    fill_hr_args(c, h, gen);
+    const uint64_t qn = (c->N + HR_ROWS_PER_TASK - 1) / HR_ROWS_PER_TASK;
+    const uint32_t grid = div_up64((uint64_t)c->n_regions * qn, HR_WARPS);
     if (c->dump_enabled)
-        hr_collect_kernel<true><<<grid, HR_WARPS * 32, 0, st>>>(h);
+        hr_collect_kernel<true><<<grid, HR_WARPS * 32, c->hr_smem, st>>>(h);
     else
-        hr_collect_kernel<false><<<grid, HR_WARPS * 32, 0, st>>>(h);
+        hr_collect_kernel<false><<<grid, HR_WARPS * 32, c->hr_smem, st>>>(h);
     LAUNCH_CHECK(c);
-    hr_apply_kernel<<<c->sm_count * 8, 256, 0, st>>>(h.state, h.list, h.count, h.cap);
+    hr_apply_kernel<<<div_up64((uint64_t)c->N * c->n_regions, HR_WARPS * HR_APPLY_ITEMS), HR_WARPS * 32, 0, st>>>(h);
     LAUNCH_CHECK(c);
     c->hr_parity ^= 1;
     return 0;
@@ -493,6 +510,23 @@ int launch_core_step(pansim_ctx *c, uint32_t gen, bool rng, cudaStream_t st)
     if (c->Ll == 0) return 0;
     CoreMutArgs a;
     fill_core_args(c, a, gen);
+    const bool hr = rng && c->tab_hr.nsub;
+    if (hr && c->core_fused) {
+        // one launch: gather + SNP, recombination collect and apply, pipelined over column blocks (core_gen.cuh)
+        HrArgs h;
+        fill_hr_args(c, h, gen);
+        GenSched s = c->sched;
+        s.ctl = c->d_gen_ctl + (size_t)c->hr_parity * s.ctl_words;
+        s.ctl_other = c->d_gen_ctl + (size_t)(c->hr_parity ^ 1) * s.ctl_words;
+        if (c->dump_enabled)
+            core_gen_kernel<true><<<gen_grid(s), CM_THREADS, c->core_smem, st>>>(a, h, s);
+        else
+            core_gen_kernel<false><<<gen_grid(s), CM_THREADS, c->core_smem, st>>>(a, h, s);
+        LAUNCH_CHECK(c);
+        c->hr_parity ^= 1;
+        c->core_cur ^= 1;
+        return 0;
+    }
     if (!rng || !a.mut_nsub)
         core_mut_kernel<false, false><<<c->core_grid, CM_THREADS, c->core_smem, st>>>(a);
     else if (c->dump_enabled)
@@ -500,8 +534,8 @@ int launch_core_step(pansim_ctx *c, uint32_t gen, bool rng, cudaStream_t st)
     else
         core_mut_kernel<true, false><<<c->core_grid, CM_THREADS, c->core_smem, st>>>(a);
     LAUNCH_CHECK(c);
-    if (rng && c->tab_hr.nsub) {
-        ScopedSpan s(c, TG_CORE_HR, st);
+    if (hr) {
+        ScopedSpan sp(c, TG_CORE_HR, st);
         if (int rc = launch_core_hr(c, gen, st)) return rc;
     }
     c->core_cur ^= 1;
@@ -605,7 +639,7 @@ void pansim_destroy(pansim_ctx *c)
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->stream_core) cudaStreamSynchronize(c->stream_core);
-    void *ptrs[] = {c->core[0], c->core[1], c->d_hr_list, c->d_hr_count, c->d_mut_img, c->acc[0], c->acc[1], c->d_parents_buf[0], c->d_parents_buf[1], c->d_parents_buf[2], c->d_lw, c->d_logfit, c->d_avgdist,
+    void *ptrs[] = {c->core[0], c->core[1], c->d_hr_slots, c->d_hr_counts, c->d_hr_ovf, c->d_hr_ovf_count, c->d_gen_ctl, c->d_mut_img, c->acc[0], c->acc[1], c->d_parents_buf[0], c->d_parents_buf[1], c->d_parents_buf[2], c->d_lw, c->d_logfit, c->d_avgdist,
                     c->d_num_genes, c->d_tmp_a, c->d_tmp_b, c->d_weights, c->d_cum, c->d_err, c->d_inter, c->d_rowInvK, c->d_gain_planes,
                     c->d_gain_thr, c->tab_mut.d_thr, c->tab_hr.d_thr, c->d_r1, c->d_r2, c->d_cd, c->d_in, c->d_un,
                     c->d_replay, c->d_hkeys, c->d_hvals, c->d_stage, c->d_groups, c->d_partner, c->d_orig, c->d_batches, c->d_tile_slots, c->d_tile_orig, c->d_dump_counters, c->d_mut_row, c->d_mut_site,
@@ -724,14 +758,23 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
         c->fitness_blocked = (uint64_t)c->N * c->G > (1ull << 25);
         if (const char *e = getenv("PANSIM_FITNESS_BLOCKED")) c->fitness_blocked = atoi(e) != 0;
         if (c->tab_hr.nsub && core_bytes) {
-            // recombination list: one entry per changed cell; sized 12 sigma above the expected number of events
+            // recombination slots: per (region, row) item room for mean + 6 sigma changed cells (a multiple of 32,
+            // 32 when the mean is small); the rare item that needs more spills to the overflow list
+            const double m_item = rate_hr * REGION_SITES;
+            uint32_t cap = 32;
+            if (m_item > 24.0) cap = 32u * (uint32_t)std::ceil((m_item + 6.0 * std::sqrt(m_item)) / 32.0);
+            if (cap > 8192) cap = 8192;                               // a region has 8192 cells
+            c->hr_slot_cap = cap;
+            const size_t items = (size_t)c->N * c->n_regions;
+            if (cudaMalloc(&c->d_hr_slots, items * cap * 2) != cudaSuccess) FAIL(c, PANSIM_ERR_NOMEM, "cudaMalloc of %zu bytes (recombination slots) failed", items * cap * 2);
+            CU(c, cudaMalloc(&c->d_hr_counts, items * 2));
+            CU(c, cudaMemset(c->d_hr_counts, 0, items * 2));
             const double mean = rate_hr * (double)c->Ll * (double)c->N;
-            const double cap = mean + 12.0 * std::sqrt(mean) + 4096.0;
-            if (cap > 4.0e9) FAIL(c, PANSIM_ERR_INVALID, "recombination rate too high for one shard (%.3g events per generation)", mean);
-            c->hr_cap = (uint32_t)cap;
-            if (cudaMalloc(&c->d_hr_list, (size_t)c->hr_cap * 8) != cudaSuccess) FAIL(c, PANSIM_ERR_NOMEM, "cudaMalloc of %zu bytes (recombination list) failed", (size_t)c->hr_cap * 8);
-            CU(c, cudaMalloc(&c->d_hr_count, 2 * sizeof(uint32_t)));
-            CU(c, cudaMemset(c->d_hr_count, 0, 2 * sizeof(uint32_t)));
+            c->hr_ovf_cap = (uint32_t)std::min(4.0e8, 65536.0 + 0.02 * mean);
+            CU(c, cudaMalloc(&c->d_hr_ovf, (size_t)c->hr_ovf_cap * 8));
+            CU(c, cudaMalloc(&c->d_hr_ovf_count, 2 * sizeof(uint32_t)));
+            CU(c, cudaMemset(c->d_hr_ovf_count, 0, 2 * sizeof(uint32_t)));
+            c->hr_smem = hr_collect_smem_bytes(GUIDE_ENTRIES + c->tab_hr.size);
         }
         const size_t n = c->N;
         for (int i = 0; i < 3; i++) CU(c, cudaMalloc(&c->d_parents_buf[i], n * 4));
@@ -769,6 +812,33 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
         if (const char *e = getenv("PANSIM_CORE_ITEMS_PER_WARP")) c->core_items_per_warp = (uint32_t)std::max(1, atoi(e));
         const uint64_t per_cta = (uint64_t)CM_WARPS * c->core_items_per_warp;
         c->core_grid = (uint32_t)std::max<uint64_t>(1, (items + per_cta - 1) / per_cta);
+        if (c->tab_hr.nsub && core_bytes) {
+            // fused generation kernel: column blocks of ~PANSIM_CORE_BLOCK_MB of packed state (all rows)
+            if (const char *e = getenv("PANSIM_CORE_FUSED")) c->core_fused = atoi(e) != 0;
+            double block_mb = 4.0;
+            if (const char *e = getenv("PANSIM_CORE_BLOCK_MB")) block_mb = std::max(0.001, atof(e));
+            GenSched &s = c->sched;
+            s.blk_regs = (uint32_t)std::max(1.0, std::floor(block_mb * 1048576.0 / ((double)c->N * REGION_BYTES)));
+            if (s.blk_regs > c->n_regions) s.blk_regs = c->n_regions;
+            s.n_blocks = (c->n_regions + s.blk_regs - 1) / s.blk_regs;
+            s.ctas = div_up64((uint64_t)c->N * s.blk_regs, per_cta);
+            // a block is collected once a full wave of later CTAs has been dispatched after it
+            const uint32_t wave = (uint32_t)(c->sm_count * occ);
+            s.lag_collect = std::max(1u, (wave + s.ctas - 1) / s.ctas + 1u);
+            if (const char *e = getenv("PANSIM_CORE_LAG")) s.lag_collect = (uint32_t)std::max(1, atoi(e));
+            s.lag_apply = s.lag_collect + std::max(1u, (wave / 4 + s.ctas - 1) / s.ctas);
+            s.ctas_overflow = 8;
+            s.ctl_words = 1 + 2 * s.n_blocks;
+            CU(c, cudaMalloc(&c->d_gen_ctl, 2 * (size_t)s.ctl_words * 4));
+            CU(c, cudaMemset(c->d_gen_ctl, 0, 2 * (size_t)s.ctl_words * 4));
+            if (c->hr_smem > c->core_smem) FAIL(c, PANSIM_ERR_INVALID, "recombination table does not fit the fused kernel's shared memory");
+            CU(c, cudaFuncSetAttribute(core_gen_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->core_smem));
+            CU(c, cudaFuncSetAttribute(core_gen_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->core_smem));
+            if (c->hr_smem > 48 * 1024) {
+                CU(c, cudaFuncSetAttribute(hr_collect_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->hr_smem));
+                CU(c, cudaFuncSetAttribute(hr_collect_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->hr_smem));
+            }
+        }
         return 0;
     };
     int rc = body();

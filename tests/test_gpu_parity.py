@@ -513,6 +513,33 @@ def test_recombination_list_pass_last_event_of_a_cell_wins(kw):
         assert repeats > 0
 
 
+@pytest.mark.parametrize("kw,block_mb,lag", [
+    (dict(pop_size=200, core_size=8192 * 40 + 77, HR_rate=0.05), "0.5", "1"),      # 14 column blocks
+    (dict(pop_size=200, core_size=8192 * 40 + 77, HR_rate=0.05), "0.01", "2"),     # one region per block, lag 2
+    (dict(pop_size=64, core_size=8192 * 9, HR_rate=1.0, core_mu=0.2), "0.2", "1"), # multi-window items
+    (dict(pop_size=3000, core_size=8192 * 12 + 5, HR_rate=0.05), "16", "1"),       # default block size, 3 blocks
+])
+def test_fused_generation_kernel_equals_separate_launches(monkeypatch, kw, block_mb, lag):
+    """core_gen_kernel pipelines gather+SNP, recombination collect and apply over column blocks
+    inside one launch (CTA roles ordered by ticket, acquire/release counters between them). It
+    must leave exactly the state that the three stand-alone launches leave."""
+    p = small_params(n_gen=4, **kw)
+    d = pb.derive(p)
+    rng = np.random.default_rng(23)
+    core, acc = random_state(rng, p.pop_size, p.core_size, d.pan_size)
+    states = []
+    for fused in ("0", "1"):
+        monkeypatch.setenv("PANSIM_CORE_FUSED", fused)
+        monkeypatch.setenv("PANSIM_CORE_BLOCK_MB", block_mb)
+        monkeypatch.setenv("PANSIM_CORE_LAG", lag)
+        with make(p) as sim:
+            sim.upload(core, acc)
+            sim.run_generations(0, p.n_gen)
+            states.append(sim.download_core())
+    assert (states[0] == states[1]).all()
+    assert (states[0] != core).any()
+
+
 def test_recombination_is_reproducible_and_seed_dependent():
     p = small_params(HR_rate=1.0, n_gen=2)
     d = pb.derive(p)
