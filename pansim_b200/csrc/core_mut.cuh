@@ -73,7 +73,7 @@ struct CoreMutArgs {
 static inline size_t core_mut_smem_bytes(uint32_t mut_size)
 {
     return 2048 /* alignment slack */ + (size_t)CM_WARPS * CM_STAGES * REGION_BYTES + CM_LUT_BYTES +
-           (size_t)(CM_GUIDE_WORDS + mut_size) * sizeof(uint32_t) + (size_t)CM_WARPS * CM_STAGES * sizeof(uint64_t);
+           (size_t)((CM_GUIDE_WORDS + mut_size + 1u) & ~1u) * sizeof(uint32_t) + (size_t)CM_WARPS * CM_STAGES * sizeof(uint64_t);
 }
 
 // Poisson by CDF inversion (see common.cuh) with a 512-bin u16 guide: entry =
@@ -181,7 +181,7 @@ __device__ __forceinline__ MutSmem mut_smem_carve(uint8_t *smem_dyn, uint32_t mu
     m.stages = smem_dyn + pad;
     m.lut = m.stages + (size_t)CM_WARPS * CM_STAGES * REGION_BYTES;
     m.tab = reinterpret_cast<uint32_t *>(m.lut + CM_LUT_BYTES);
-    m.bars = reinterpret_cast<uint64_t *>(m.tab + CM_GUIDE_WORDS + mut_size);
+    m.bars = reinterpret_cast<uint64_t *>(m.tab + ((CM_GUIDE_WORDS + mut_size + 1u) & ~1u));   // mbarriers are 8-byte objects
     return m;
 }
 

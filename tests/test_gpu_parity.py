@@ -632,3 +632,17 @@ def test_blocked_fitness_sum_for_large_shapes(monkeypatch):
     np.testing.assert_allclose(lf, olf, rtol=1e-12, atol=1e-12)
     assert (lf[acc[:, 7] == 1] == 0.0).all()
     np.testing.assert_allclose(w / w.sum(), ow / ow.sum(), rtol=1e-10)
+
+
+def test_zero_core_mutation_rate_is_pure_gather():
+    """core_mu = 0 (hence no recombination either, main.rs:275-279): the generate-mode core step is
+    next_generation alone (population.rs:450-465); every child row equals its parent's row."""
+    rng = np.random.default_rng(5)
+    N, L, G = 40, 20000, 64
+    core, acc = random_state(rng, N, L, G)
+    p = pb.Params(pop_size=N, core_size=L, pan_genes=G, core_genes=0, core_mu=0.0, HR_rate=0.05)
+    with make(p) as sim:
+        sim.upload(core, acc)
+        sim.run_generations(0, 1)
+        parents = sim.parents()
+        assert (sim.download_core() == core[parents]).all()

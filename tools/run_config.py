@@ -52,7 +52,7 @@ def main():
         ms = tm.total_ms / gens
         core_bytes = 2 * p.pop_size * ((p.core_size + 3) // 4)
         out = dict(shape=dict(N=p.pop_size, L=p.core_size, G=d.pan_size), init_s=round(t_init, 2),
-                   ms_per_generation=ms, generations_per_s=1e3 / ms, core_step_ms=tm.core_step_ms / gens,
+                   ms_per_generation=ms, generations_per_s=1e3 / ms, core_step_ms=tm.core_step_ms / gens, core_hr_ms=tm.core_hr_ms / gens,
                    core_step_GBps=core_bytes / (tm.core_step_ms / gens * 1e-3) / 1e9,
                    acc_ms=tm.acc_step_ms / gens, select_ms=tm.select_ms / gens,
                    pair_ms=tp.pair_core_ms + tp.pair_acc_ms, pairs_per_s=pairs / ((tp.pair_core_ms + tp.pair_acc_ms) * 1e-3),
