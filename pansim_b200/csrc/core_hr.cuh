@@ -30,9 +30,11 @@
 
 namespace pansim {
 
-constexpr uint32_t STREAM_CORE_HR_COUNT = 7;          // one call per (region, 4 rows): word i = count uniform of row 4q+i
 constexpr uint32_t STREAM_CORE_HR_EXTRA = 8;          // extra count draws of (region, row) for means above the table range
 constexpr uint32_t HR_EVENT_W0 = 0x01000000u;         // counter word 3 of event e = HR_EVENT_W0 + e
+// Philox call of event e of item (region, row): x -> site, (y, z) -> donor; word w of the call of
+// event 0 is the uniform the item's event COUNT is drawn from (every lane of a warp makes the call
+// of event `lane` anyway, so the count costs one shuffle instead of a Philox call of its own).
 constexpr int HR_WARPS = 8;
 constexpr uint32_t HR_ROWS_PER_TASK = 4;
 constexpr uint32_t HR_CLAIM_WORDS = REGION_SITES / 32;   // per warp
@@ -45,7 +47,7 @@ struct HrArgs {
     uint64_t site_limit;
     uint2 key;
     uint32_t gen;
-    const uint32_t *tab;      // device image [256 guide][size thresholds] of Poisson(region mean / nsub)
+    const uint32_t *tab;      // device thresholds T[j] = round(CDF(j) * 2^32) of Poisson(region mean / nsub), padded with 0xFFFFFFFF
     uint32_t tab_words, nsub, kmax;
     uint16_t *slots;          // [items][slot_cap]: site-in-region | xor << 13; item = region * n_rows + row
     uint16_t *counts;         // [items]
@@ -65,6 +67,48 @@ struct HrArgs {
 static inline size_t hr_collect_smem_bytes(uint32_t tab_words)
 {
     return (size_t)tab_words * 4 + (size_t)HR_WARPS * HR_CLAIM_WORDS * 4;
+}
+
+// ---- event count of one (region, row) item: warp-collective, exact CDF inversion ----------------
+// k = #{j : T[j] <= u} capped at kmax; lane-parallel compare + ballot over the threshold table
+__device__ __forceinline__ uint32_t hr_count_from_uniform(const uint32_t *thr, uint32_t size, uint32_t kmax, uint32_t u,
+                                                          uint32_t lane)
+{
+    uint32_t k = 0;
+    for (uint32_t j0 = 0; j0 < size; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        k += (uint32_t)__popc(__ballot_sync(0xffffffffu, j < size && thr[j] <= u));
+    }
+    return min(k, kmax);
+}
+
+// means above the table range: nsub - 1 more draws from dedicated count calls (exact by additivity)
+__device__ __noinline__ uint32_t hr_count_extra(uint32_t greg, uint32_t row, uint32_t gen, uint2 key, const uint32_t *thr,
+                                                uint32_t size, uint32_t nsub, uint32_t kmax, uint32_t lane)
+{
+    uint32_t k = 0;
+    for (uint32_t s = 1; s < nsub; s++) {
+        uint4 c = make_ctr(greg, row, gen, STREAM_CORE_HR_EXTRA);
+        c.w |= 0x8000u | ((s - 1) >> 2);
+        const uint4 r = philox4x32_10(c, key);
+        const uint32_t sel = (s - 1) & 3u;
+        const uint32_t u = sel == 0 ? r.x : sel == 1 ? r.y : sel == 2 ? r.z : r.w;
+        k += hr_count_from_uniform(thr, size, kmax, u, lane);
+    }
+    return k;
+}
+
+// event e of item (global region greg, row): site of the region and donor row (population.rs:616-619)
+struct HrEvent { uint32_t pos, donor, w; };
+__device__ __forceinline__ HrEvent hr_event(uint32_t greg, uint32_t row, uint32_t gen, uint2 key, uint32_t e, uint32_t n_other)
+{
+    const uint4 r = philox4x32_10(make_uint4(greg, row, gen, HR_EVENT_W0 + e), key);
+    HrEvent ev;
+    ev.pos = r.x >> 19;                                                                   // uniform site of the region
+    ev.donor = (uint32_t)__umul64hi(((uint64_t)r.y << 32) | r.z, (uint64_t)n_other);      // bias <= N / 2^64
+    ev.donor += ev.donor >= row ? 1u : 0u;
+    ev.w = r.w;
+    return ev;
 }
 
 // one (region, row) item; warp-collective
@@ -99,10 +143,8 @@ __device__ __forceinline__ void hr_collect_item(const HrArgs &a, uint32_t *claim
         uint32_t pos = 0, donor = 0;
         bool valid = false;
         if (e < K) {
-            const uint4 r = philox4x32_10(make_uint4(greg, row, a.gen, HR_EVENT_W0 + e), a.key);
-            pos = r.x >> 19;                                                   // uniform site of the region
-            donor = (uint32_t)__umul64hi(((uint64_t)r.y << 32) | r.z, (uint64_t)n_other);   // bias <= N / 2^64
-            donor += donor >= row ? 1u : 0u;                                   // population.rs:616-619
+            const HrEvent ev = hr_event(greg, row, a.gen, a.key, e, n_other);
+            pos = ev.pos; donor = ev.donor;
             valid = pos < lim;                                                 // ragged last region: thinned away
         }
         // the last event of a cell wins (population.rs:745): highest lane of this window ...
@@ -150,26 +192,27 @@ __device__ __forceinline__ void hr_collect_item(const HrArgs &a, uint32_t *claim
     if (lane == 0) a.counts[item] = (uint16_t)min(n_emit, a.slot_cap);
 }
 
-// task = (region, rows 4q .. 4q+3): one Philox call carries the four count uniforms. When every row
-// has at most 32 events (one window each) the four windows are processed together: all Philox
-// calls, then all loads, then all stores, so one L2/DRAM round trip serves the whole task.
+// task = (region, rows 4q .. 4q+3). When every row has at most 32 events (one window each) the four
+// windows are processed together: all Philox calls, then all loads, then all stores, so one L2/DRAM
+// round trip serves the whole task.
 template <bool DUMP>
 __device__ __forceinline__ void hr_collect_task(const HrArgs &a, const uint32_t *tab, uint32_t *claim, uint32_t reg,
                                                 uint32_t q, uint32_t lane)
 {
     constexpr int R = (int)HR_ROWS_PER_TASK;
     const uint32_t greg = a.region0 + reg;
-    const uint4 cc = philox4x32_10(make_ctr(greg, q, a.gen, STREAM_CORE_HR_COUNT), a.key);
-    const uint32_t u[R] = {cc.x, cc.y, cc.z, cc.w};
-    uint32_t K[R];
+    const uint32_t n_other = a.n_rows - 1u;
+    uint32_t K[R], pos[R], donor[R];
     uint32_t kmaxi = 0;
 #pragma unroll
     for (int i = 0; i < R; i++) {
         const uint32_t row = q * R + i;
-        K[i] = 0;
+        K[i] = 0; pos[i] = 0; donor[i] = 0;
         if (row < a.n_rows) {
-            K[i] = poisson_from_uniform(tab, a.kmax, u[i]);                                        // warp-uniform
-            if (a.nsub > 1) K[i] += stream_count_extra(make_ctr(greg, row, a.gen, STREAM_CORE_HR_EXTRA), a.key, tab, a.nsub, a.kmax);
+            const HrEvent ev = hr_event(greg, row, a.gen, a.key, lane, n_other);      // first window: event `lane`
+            pos[i] = ev.pos; donor[i] = ev.donor;
+            K[i] = hr_count_from_uniform(tab, a.tab_words, a.kmax, __shfl_sync(0xffffffffu, ev.w, 0), lane);   // warp-uniform
+            if (a.nsub > 1) K[i] += hr_count_extra(greg, row, a.gen, a.key, tab, a.tab_words, a.nsub, a.kmax, lane);
         }
         kmaxi = max(kmaxi, K[i]);
     }
@@ -183,22 +226,10 @@ __device__ __forceinline__ void hr_collect_task(const HrArgs &a, const uint32_t 
     const uint64_t reg_site0 = (uint64_t)greg * REGION_SITES;
     const uint64_t rem_sites = a.site_limit - reg_site0;
     const uint32_t lim = rem_sites < REGION_SITES ? (uint32_t)rem_sites : REGION_SITES;
-    const uint32_t n_other = a.n_rows - 1u;
     const uint32_t *col = a.state + (uint64_t)reg * REGION_WORDS;
-    uint32_t pos[R], donor[R];
     bool valid[R], keep[R];
 #pragma unroll
-    for (int i = 0; i < R; i++) {
-        const uint32_t row = q * R + i;
-        pos[i] = 0; donor[i] = 0; valid[i] = false;
-        if (lane < K[i]) {
-            const uint4 r = philox4x32_10(make_uint4(greg, row, a.gen, HR_EVENT_W0 + lane), a.key);
-            pos[i] = r.x >> 19;
-            donor[i] = (uint32_t)__umul64hi(((uint64_t)r.y << 32) | r.z, (uint64_t)n_other);
-            donor[i] += donor[i] >= row ? 1u : 0u;
-            valid[i] = pos[i] < lim;
-        }
-    }
+    for (int i = 0; i < R; i++) valid[i] = lane < K[i] && pos[i] < lim;
     uint32_t dw[R], ow[R];
 #pragma unroll
     for (int i = 0; i < R; i++) {

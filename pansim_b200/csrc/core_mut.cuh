@@ -3,8 +3,18 @@
 // One pass over the 2-bit packed core alignment does, per output row i:
 //   gather-by-parent   next[i,:] = pop[parents[i],:]      (population.rs:450-465)
 //   SNP mutation       population.rs:512-539
-// Homologous recombination (population.rs:544-751) follows as the sparse pass
-// of core_hr.cuh on the finished rows (which ARE the snapshot of :693-695).
+// Homologous recombination (population.rs:544-751) needs the finished rows of
+// ALL individuals (they are the snapshot of :693-695), so it cannot be applied
+// while this pass is still writing them. It is DEFERRED instead: the rows this
+// kernel writes are the pre-recombination snapshot of generation g, and the
+// recombination events of generation g are applied by the NEXT launch to every
+// region right after it has been loaded (a child inherits its parent's row
+// *after* recombination). The donor cells are then read from the old buffer,
+// which is read-only here, so there is no hazard and no second pass over the
+// state; the events are recomputed from their counters (core_hr.cuh), and the
+// donor words are fetched one item ahead of their use. A reader of the state
+// (distances, downloads) first materialises the pending events with the
+// stand-alone kernels of core_hr.cuh; both routes give identical states.
 //
 // Every output cell is a pure function of (old state, parents, Philox key):
 // no races, no atomics, independent of grid size and of the column sharding.
@@ -35,6 +45,7 @@
 // steady state.
 #pragma once
 #include "common.cuh"
+#include "core_hr.cuh"
 
 namespace pansim {
 
@@ -63,6 +74,9 @@ struct CoreMutArgs {
     uint32_t gen;
     const uint32_t *mut_img;  // device image [CM_GUIDE u16 guide][mut_size thresholds]
     uint32_t mut_size, mut_nsub, mut_kmax;
+    // recombination events of generation hr_gen still pending on old_state (hr_nsub = 0: none)
+    const uint32_t *hr_thr;   // device thresholds of the per-region event count (HrArgs::tab)
+    uint32_t hr_size, hr_nsub, hr_kmax, hr_gen;
     // optional event dump (parity instrumentation)
     uint32_t *dump_counters;  // [0] = SNP events
     uint32_t dump_cap;
@@ -70,10 +84,15 @@ struct CoreMutArgs {
     uint8_t *d_mut_allele;
 };
 
-static inline size_t core_mut_smem_bytes(uint32_t mut_size)
+__host__ __device__ static inline uint32_t core_mut_tab_words(uint32_t mut_size, uint32_t hr_size)
+{
+    return (CM_GUIDE_WORDS + mut_size + hr_size + 1u) & ~1u;     // mbarriers behind it are 8-byte objects
+}
+
+static inline size_t core_mut_smem_bytes(uint32_t mut_size, uint32_t hr_size)
 {
     return 2048 /* alignment slack */ + (size_t)CM_WARPS * CM_STAGES * REGION_BYTES + CM_LUT_BYTES +
-           (size_t)((CM_GUIDE_WORDS + mut_size + 1u) & ~1u) * sizeof(uint32_t) + (size_t)CM_WARPS * CM_STAGES * sizeof(uint64_t);
+           (size_t)core_mut_tab_words(mut_size, hr_size) * sizeof(uint32_t) + (size_t)CM_WARPS * CM_STAGES * sizeof(uint64_t);
 }
 
 // Poisson by CDF inversion (see common.cuh) with a 512-bin u16 guide: entry =
@@ -165,15 +184,57 @@ struct MutChunk {
     }
 };
 
+// ---- pending recombination events of the previous generation (see the header) ----------------
+// One window = events base .. base+31 of item (parent row prow, local region reg), one per lane.
+// K = event count of the item (computed here for base 0), pk = site | keep << 31 where `keep`
+// marks the last event of its cell within the window (population.rs:745), dw = the donor's word.
+struct HrWindow { uint32_t K, pk, dw; };
+
+__device__ __forceinline__ HrWindow hr_window_fetch(const CoreMutArgs &a, const uint32_t *hr_thr, uint32_t prow, uint32_t reg,
+                                                    uint32_t lane, uint32_t base, uint32_t K_known)
+{
+    const uint32_t greg = a.region0 + reg;
+    const uint64_t rem_sites = a.site_limit - (uint64_t)greg * REGION_SITES;
+    const uint32_t lim = rem_sites < REGION_SITES ? (uint32_t)rem_sites : REGION_SITES;
+    const HrEvent ev = hr_event(greg, prow, a.hr_gen, a.key, base + lane, a.n_rows - 1u);
+    HrWindow h;
+    h.K = K_known;
+    if (base == 0u) {
+        h.K = hr_count_from_uniform(hr_thr, a.hr_size, a.hr_kmax, __shfl_sync(0xffffffffu, ev.w, 0), lane);
+        if (a.hr_nsub > 1) h.K += hr_count_extra(greg, prow, a.hr_gen, a.key, hr_thr, a.hr_size, a.hr_nsub, a.hr_kmax, lane);
+    }
+    const bool valid = base + lane < h.K && ev.pos < lim;                  // ragged last region: thinned away
+    const uint32_t same = __match_any_sync(0xffffffffu, valid ? ev.pos : (0x80000000u | lane));
+    const bool keep = valid && ((same >> lane) >> 1) == 0u;
+    h.pk = ev.pos | (keep ? 0x80000000u : 0u);
+    h.dw = 0;
+    if (keep)   // the old buffer is read-only during this launch: the snapshot the donor cell is taken from (:693-695)
+        h.dw = __ldcg(reinterpret_cast<const uint32_t *>(a.old_state + (uint64_t)ev.donor * a.row_stride) +
+                      (uint64_t)reg * REGION_WORDS + (ev.pos >> 4));
+    return h;
+}
+
+// kept cells of one window are distinct, so the XOR of a lane touches bits no other lane reads or writes
+__device__ __forceinline__ void hr_window_apply(uint32_t *sw, const HrWindow &h)
+{
+    if (h.pk & 0x80000000u) {
+        const uint32_t pos = h.pk & 0x1FFFu;
+        const uint32_t delta = (sw[pos >> 4] ^ h.dw) & (3u << ((pos & 15u) * 2u));
+        if (delta) atomicXor(&sw[pos >> 4], delta);
+    }
+    __syncwarp();
+}
+
 // shared-memory carve-up of one CTA (dynamic shared memory, re-based to a 2 KiB boundary)
 struct MutSmem {
     uint8_t *stages;     // CM_WARPS x CM_STAGES x 2 KiB
     uint8_t *lut;        // 243 x uint4
-    uint32_t *tab;       // Poisson image
+    uint32_t *tab;       // Poisson image (SNP count per 256-site block)
+    uint32_t *hr_thr;    // Poisson thresholds (pending recombination events per region)
     uint64_t *bars;      // CM_WARPS x CM_STAGES mbarriers
 };
 
-__device__ __forceinline__ MutSmem mut_smem_carve(uint8_t *smem_dyn, uint32_t mut_size)
+__device__ __forceinline__ MutSmem mut_smem_carve(uint8_t *smem_dyn, uint32_t mut_size, uint32_t hr_size)
 {
     // stages must sit on 2 KiB boundaries of the shared window (the slot address is an OR)
     const uint32_t pad = (2048u - (smem_u32(smem_dyn) & 2047u)) & 2047u;
@@ -181,7 +242,8 @@ __device__ __forceinline__ MutSmem mut_smem_carve(uint8_t *smem_dyn, uint32_t mu
     m.stages = smem_dyn + pad;
     m.lut = m.stages + (size_t)CM_WARPS * CM_STAGES * REGION_BYTES;
     m.tab = reinterpret_cast<uint32_t *>(m.lut + CM_LUT_BYTES);
-    m.bars = reinterpret_cast<uint64_t *>(m.tab + ((CM_GUIDE_WORDS + mut_size + 1u) & ~1u));   // mbarriers are 8-byte objects
+    m.hr_thr = m.tab + CM_GUIDE_WORDS + mut_size;
+    m.bars = reinterpret_cast<uint64_t *>(m.tab + core_mut_tab_words(mut_size, hr_size));
     return m;
 }
 
@@ -194,6 +256,8 @@ __device__ __forceinline__ void mut_cta_setup(const CoreMutArgs &a, const MutSme
     if (RNG) {
 #pragma unroll 1
         for (uint32_t i = threadIdx.x; i < CM_GUIDE_WORDS + a.mut_size; i += CM_THREADS) m.tab[i] = a.mut_img[i];
+        if (a.hr_nsub)
+            for (uint32_t i = threadIdx.x; i < a.hr_size; i += CM_THREADS) m.hr_thr[i] = a.hr_thr[i];
         if (threadIdx.x < CM_LUT_ENTRIES) {
             uint32_t v = threadIdx.x;
             uint4 e;
@@ -247,6 +311,9 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
     }
 
     uint32_t row = gw / blk_regs, breg = gw % blk_regs;
+    const bool hr_on = RNG && a.hr_nsub != 0u;
+    HrWindow hw_cur{0u, 0u, 0u};
+    if (hr_on) hw_cur = hr_window_fetch(a, m.hr_thr, a.parents ? __ldg(a.parents + row) : row, blk_reg0 + breg, lane, 0u, 0u);
     for (uint32_t j = 0; j < n_my; j++) {
         const uint32_t s = j % CM_STAGES;
         uint32_t *sw = reinterpret_cast<uint32_t *>(stages + s * REGION_BYTES);
@@ -270,6 +337,24 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
         }
 
         mbar_wait(&bars[s], (j / CM_STAGES) & 1u);
+
+        if (hr_on) {
+            // ---- recombination of the previous generation on the parent's row (population.rs:725-748):
+            // windows in draw order, so a later event of a cell overwrites an earlier one ----
+            if (hw_cur.K) {
+                hr_window_apply(sw, hw_cur);
+#pragma unroll 1
+                for (uint32_t base = 32u; base < hw_cur.K; base += 32u)
+                    hr_window_apply(sw, hr_window_fetch(a, m.hr_thr, a.parents ? __ldg(a.parents + row) : row, reg, lane, base, hw_cur.K));
+            }
+            // first window of the NEXT item, fetched into the registers just consumed: its donor
+            // loads are in flight while this item's SNP events are applied
+            if (j + 1 < n_my) {
+                uint32_t nrow = row + d_row, nreg = breg + d_reg;
+                if (nreg >= blk_regs) { nreg -= blk_regs; nrow++; }
+                hw_cur = hr_window_fetch(a, m.hr_thr, a.parents ? __ldg(a.parents + nrow) : nrow, blk_reg0 + nreg, lane, 0u, 0u);
+            }
+        }
 
         if (RNG && a.mut_nsub) {
             // ---- SNP mutation (population.rs:512-539) ----
@@ -304,8 +389,8 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
                     if (nv < 16u) sw[kk * 32u + lane] &= (1u << (2u * nv)) - 1u;
                 }
             }
-            fence_proxy_async();     // generic-proxy writes -> visible to the bulk store
         }
+        if (RNG && (a.mut_nsub || hr_on)) fence_proxy_async();     // generic-proxy writes -> visible to the bulk store
         __syncwarp();
 
         if (lane == 0) {
@@ -332,7 +417,7 @@ template <bool RNG, bool DUMP>
 __global__ void __launch_bounds__(CM_THREADS, 4) core_mut_kernel(const CoreMutArgs a)
 {
     extern __shared__ uint8_t smem_dyn[];
-    const MutSmem m = mut_smem_carve(smem_dyn, a.mut_size);
+    const MutSmem m = mut_smem_carve(smem_dyn, a.mut_size, a.hr_nsub ? a.hr_size : 0u);
     mut_cta_setup<RNG>(a, m);
     const uint32_t total = a.n_rows * a.n_regions;
     const uint32_t cta_items = CM_WARPS * a.items_per_warp;

@@ -13,7 +13,7 @@
 
 #include "acc_step.cuh"
 #include "common.cuh"
-#include "core_gen.cuh"
+#include "core_mut.cuh"
 #include "core_hr.cuh"
 #include "core_mut.cuh"
 #include "distance.cuh"
@@ -60,23 +60,6 @@ void build_poisson_table(double mean, HostPoissonTable &t)
     while (size < t.thr.size() + 1) size <<= 1;
     t.size = size;
     t.thr.resize(size, 0xFFFFFFFFu);
-}
-
-// device image: [GUIDE_ENTRIES guide words][size thresholds]; see common.cuh
-std::vector<uint32_t> poisson_table_image(const HostPoissonTable &t)
-{
-    std::vector<uint32_t> img(GUIDE_ENTRIES + t.size);
-    for (uint32_t b = 0; b < GUIDE_ENTRIES; b++) {
-        const uint32_t lo = b << GUIDE_SHIFT;
-        const uint32_t hi = lo | ((1u << GUIDE_SHIFT) - 1u);
-        uint32_t k0 = 0, k1 = 0;
-        while (k0 < t.kmax && t.thr[k0] <= lo) k0++;
-        k1 = k0;
-        while (k1 < t.kmax && t.thr[k1] <= hi) k1++;
-        img[b] = 2u * k0 + (k1 != k0 ? 1u : 0u);
-    }
-    for (uint32_t j = 0; j < t.size; j++) img[GUIDE_ENTRIES + j] = t.thr[j];
-    return img;
 }
 
 // core_mut.cuh image: [CM_GUIDE u16 guide entries][size thresholds]; entry = 2*k0 + many,
@@ -127,7 +110,9 @@ struct pansim_ctx {
     pansim_config cfg;
     std::string err;
     cudaStream_t stream = nullptr;        // accessory / selection chain, copies, distances
-    cudaStream_t stream_core = nullptr;   // fused core step (runs concurrently with the chain above)
+    cudaStream_t stream_core = nullptr;   // core step (runs concurrently with the chain above)
+    cudaStream_t stream_aux = nullptr;    // fitness sum, concurrent with the intersection counts of the competition term
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_parents[3] = {nullptr, nullptr, nullptr};    // parents[i] written
     cudaEvent_t ev_core_done[3] = {nullptr, nullptr, nullptr};  // core step that read parents[i] finished
     bool core_done_valid[3] = {false, false, false};
@@ -149,10 +134,12 @@ struct pansim_ctx {
     uint32_t *d_hr_ovf_count = nullptr;  // two counters, used alternately
     uint32_t hr_ovf_cap = 0;
     int hr_parity = 0;
-    // fused generation kernel (core_gen.cuh)
-    bool core_fused = false;             // measured slower than the three launches (HR tail inside 55 KB CTAs); opt-in via PANSIM_CORE_FUSED=1
-    GenSched sched{};
-    uint32_t *d_gen_ctl = nullptr;       // two control blocks, used alternately
+    // deferred recombination (core_mut.cuh): the current core buffer holds the pre-recombination rows of
+    // generation hr_pending_gen; the next core step applies the events while it gathers, a reader of the
+    // state materialises them first (core_materialize)
+    bool hr_pending = false;
+    uint32_t hr_pending_gen = 0;
+    bool hr_defer = true;                // PANSIM_HR_DEFER=0: recombination as two launches right after every core step
     size_t hr_smem = 0;
     uint32_t *acc[2] = {nullptr, nullptr};
     int core_cur = 0, acc_cur = 0;
@@ -334,16 +321,17 @@ int check_device_flag(pansim_ctx *c, int code, const char *what)
 
 // ---- kernel group launchers (asynchronous on ctx->stream) -----------------
 
-int launch_fitness(pansim_ctx *c)
+int launch_fitness(pansim_ctx *c, cudaStream_t st = nullptr)
 {
     if (c->fitness_valid) return 0;
+    if (!st) st = c->stream;
     const uint32_t *acc = c->acc[c->acc_cur];
     if (c->fitness_blocked)
-        fitness_blocked_kernel<<<div_up64(c->N, FIT_WARPS), FIT_WARPS * 32, 0, c->stream>>>(acc, c->N, c->G, c->acc_stride_words,
-                                                                                       c->d_lw, c->d_logfit, c->d_num_genes);
+        fitness_blocked_kernel<<<div_up64(c->N, FIT_WARPS), FIT_WARPS * 32, 0, st>>>(acc, c->N, c->G, c->acc_stride_words,
+                                                                                c->d_lw, c->d_logfit, c->d_num_genes);
     else
-        fitness_kernel<<<div_up64(c->N, FIT_WARPS), FIT_WARPS * 32, 0, c->stream>>>(acc, c->N, c->G, c->acc_stride_words,
-                                                                               c->d_lw, c->d_logfit, c->d_num_genes);
+        fitness_kernel<<<div_up64(c->N, FIT_WARPS), FIT_WARPS * 32, 0, st>>>(acc, c->N, c->G, c->acc_stride_words,
+                                                                        c->d_lw, c->d_logfit, c->d_num_genes);
     LAUNCH_CHECK(c);
     c->fitness_valid = true;
     return 0;
@@ -353,11 +341,19 @@ int launch_competition(pansim_ctx *c)
 {
     if (c->N < 2) FAIL(c, PANSIM_ERR_INVALID, "average_distance needs pop_size >= 2");
     if (!c->d_inter) CU(c, cudaMalloc(&c->d_inter, (size_t)c->N * c->N * sizeof(uint32_t)));
-    if (launch_fitness(c)) return PANSIM_ERR_CUDA;           // row popcounts (num_genes)
+    // the fitness sum (also the row popcounts the distances need) runs beside the intersection counts
+    const bool fork = !c->fitness_valid;
+    if (fork) {
+        CU(c, cudaEventRecord(c->ev_fork, c->stream));
+        CU(c, cudaStreamWaitEvent(c->stream_aux, c->ev_fork, 0));
+        if (launch_fitness(c, c->stream_aux)) return PANSIM_ERR_CUDA;
+        CU(c, cudaEventRecord(c->ev_join, c->stream_aux));
+    }
     const uint32_t nb = div_up64(c->N, 32);
     acc_inter_kernel<<<dim3(nb, nb), 256, 0, c->stream>>>(c->acc[c->acc_cur], c->N, c->acc_stride_words,
                                                           c->acc_words, c->d_inter);
     LAUNCH_CHECK(c);
+    if (fork) CU(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     avg_distance_kernel<<<div_up64(c->N, AVG_WARPS), AVG_WARPS * 32, 0, c->stream>>>(c->d_inter, c->d_num_genes, c->N,
                                                                     c->cfg.core_genes, c->d_avgdist);
     LAUNCH_CHECK(c);
@@ -456,15 +452,17 @@ void fill_core_args(pansim_ctx *c, CoreMutArgs &a, uint32_t gen)
     a.key = make_uint2((uint32_t)c->cfg.seed, (uint32_t)(c->cfg.seed >> 32));
     a.gen = gen;
     a.mut_img = c->d_mut_img; a.mut_size = c->tab_mut.size; a.mut_nsub = c->tab_mut.nsub; a.mut_kmax = c->tab_mut.kmax;
+    a.hr_thr = c->tab_hr.d_thr; a.hr_size = c->tab_hr.size; a.hr_kmax = c->tab_hr.kmax; a.hr_gen = c->hr_pending_gen;
+    a.hr_nsub = c->hr_pending ? c->tab_hr.nsub : 0u;
     a.dump_counters = c->d_dump_counters;
     a.dump_cap = c->dump_cap;
     a.d_mut_row = c->d_mut_row; a.d_mut_site = c->d_mut_site; a.d_mut_seq = c->d_mut_seq; a.d_mut_allele = c->d_mut_allele;
 }
 
-void fill_hr_args(pansim_ctx *c, HrArgs &h, uint32_t gen)
+void fill_hr_args(pansim_ctx *c, HrArgs &h, uint32_t gen, uint8_t *state)
 {
     memset(&h, 0, sizeof h);
-    h.state = reinterpret_cast<uint32_t *>(c->core[c->core_cur ^ 1]);
+    h.state = reinterpret_cast<uint32_t *>(state);
     h.n_rows = c->N;
     h.n_regions = c->n_regions;
     h.region0 = c->region0;
@@ -472,7 +470,7 @@ void fill_hr_args(pansim_ctx *c, HrArgs &h, uint32_t gen)
     h.site_limit = c->site_end;
     h.key = make_uint2((uint32_t)c->cfg.seed, (uint32_t)(c->cfg.seed >> 32));
     h.gen = gen;
-    h.tab = c->tab_hr.d_thr; h.tab_words = GUIDE_ENTRIES + c->tab_hr.size; h.nsub = c->tab_hr.nsub; h.kmax = c->tab_hr.kmax;
+    h.tab = c->tab_hr.d_thr; h.tab_words = c->tab_hr.size; h.nsub = c->tab_hr.nsub; h.kmax = c->tab_hr.kmax;
     h.slots = c->d_hr_slots;
     h.counts = c->d_hr_counts;
     h.slot_cap = c->hr_slot_cap;
@@ -487,11 +485,12 @@ void fill_hr_args(pansim_ctx *c, HrArgs &h, uint32_t gen)
     h.d_hr_value = c->d_hr_value;
 }
 
-// homologous recombination on the rows the gather + SNP pass just wrote, as two launches (core_hr.cuh)
-int launch_core_hr(pansim_ctx *c, uint32_t gen, cudaStream_t st)
+// homologous recombination of generation `gen` on the rows the gather + SNP pass wrote into `state`,
+// as two launches (core_hr.cuh)
+int launch_core_hr(pansim_ctx *c, uint32_t gen, uint8_t *state, cudaStream_t st)
 {
     HrArgs h;
-    fill_hr_args(c, h, gen);
+    fill_hr_args(c, h, gen, state);
     const uint64_t qn = (c->N + HR_ROWS_PER_TASK - 1) / HR_ROWS_PER_TASK;
     const uint32_t grid = div_up64((uint64_t)c->n_regions * qn, HR_WARPS);
     if (c->dump_enabled)
@@ -505,40 +504,45 @@ int launch_core_hr(pansim_ctx *c, uint32_t gen, cudaStream_t st)
     return 0;
 }
 
+// Apply the pending recombination events to the current core buffer (deferred mode, core_mut.cuh).
+// Every reader of the core state other than the generate-mode core step calls this first.
+int core_materialize(pansim_ctx *c, cudaStream_t st)
+{
+    if (!c->hr_pending) return 0;
+    ScopedSpan sp(c, TG_CORE_HR, st);
+    if (int rc = launch_core_hr(c, c->hr_pending_gen, c->core[c->core_cur], st)) return rc;
+    c->hr_pending = false;
+    return 0;
+}
+
 int launch_core_step(pansim_ctx *c, uint32_t gen, bool rng, cudaStream_t st)
 {
     if (c->Ll == 0) return 0;
+    const bool hr = rng && c->tab_hr.nsub;
+    const bool defer = c->hr_defer && !c->dump_enabled;
+    // replay / plain gather, the event dump and the non-deferred mode work on materialised rows
+    if (!rng || !defer)
+        if (int rc = core_materialize(c, st)) return rc;
     CoreMutArgs a;
     fill_core_args(c, a, gen);
-    const bool hr = rng && c->tab_hr.nsub;
-    if (hr && c->core_fused) {
-        // one launch: gather + SNP, recombination collect and apply, pipelined over column blocks (core_gen.cuh)
-        HrArgs h;
-        fill_hr_args(c, h, gen);
-        GenSched s = c->sched;
-        s.ctl = c->d_gen_ctl + (size_t)c->hr_parity * s.ctl_words;
-        s.ctl_other = c->d_gen_ctl + (size_t)(c->hr_parity ^ 1) * s.ctl_words;
-        if (c->dump_enabled)
-            core_gen_kernel<true><<<gen_grid(s), CM_THREADS, c->core_smem, st>>>(a, h, s);
-        else
-            core_gen_kernel<false><<<gen_grid(s), CM_THREADS, c->core_smem, st>>>(a, h, s);
-        LAUNCH_CHECK(c);
-        c->hr_parity ^= 1;
-        c->core_cur ^= 1;
-        return 0;
-    }
-    if (!rng || !a.mut_nsub)
+    if (!rng || (!a.mut_nsub && !a.hr_nsub))
         core_mut_kernel<false, false><<<c->core_grid, CM_THREADS, c->core_smem, st>>>(a);
     else if (c->dump_enabled)
         core_mut_kernel<true, true><<<c->core_grid, CM_THREADS, c->core_smem, st>>>(a);
     else
         core_mut_kernel<true, false><<<c->core_grid, CM_THREADS, c->core_smem, st>>>(a);
     LAUNCH_CHECK(c);
-    if (hr) {
-        ScopedSpan sp(c, TG_CORE_HR, st);
-        if (int rc = launch_core_hr(c, gen, st)) return rc;
-    }
     c->core_cur ^= 1;
+    c->hr_pending = false;
+    if (hr) {
+        if (defer) {
+            c->hr_pending = true;
+            c->hr_pending_gen = gen;
+        } else {
+            ScopedSpan sp(c, TG_CORE_HR, st);
+            if (int rc = launch_core_hr(c, gen, c->core[c->core_cur], st)) return rc;
+        }
+    }
     return 0;
 }
 
@@ -639,7 +643,8 @@ void pansim_destroy(pansim_ctx *c)
     cudaSetDevice(c->cfg.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->stream_core) cudaStreamSynchronize(c->stream_core);
-    void *ptrs[] = {c->core[0], c->core[1], c->d_hr_slots, c->d_hr_counts, c->d_hr_ovf, c->d_hr_ovf_count, c->d_gen_ctl, c->d_mut_img, c->acc[0], c->acc[1], c->d_parents_buf[0], c->d_parents_buf[1], c->d_parents_buf[2], c->d_lw, c->d_logfit, c->d_avgdist,
+    if (c->stream_aux) cudaStreamSynchronize(c->stream_aux);
+    void *ptrs[] = {c->core[0], c->core[1], c->d_hr_slots, c->d_hr_counts, c->d_hr_ovf, c->d_hr_ovf_count, c->d_mut_img, c->acc[0], c->acc[1], c->d_parents_buf[0], c->d_parents_buf[1], c->d_parents_buf[2], c->d_lw, c->d_logfit, c->d_avgdist,
                     c->d_num_genes, c->d_tmp_a, c->d_tmp_b, c->d_weights, c->d_cum, c->d_err, c->d_inter, c->d_rowInvK, c->d_gain_planes,
                     c->d_gain_thr, c->tab_mut.d_thr, c->tab_hr.d_thr, c->d_r1, c->d_r2, c->d_cd, c->d_in, c->d_un,
                     c->d_replay, c->d_hkeys, c->d_hvals, c->d_stage, c->d_groups, c->d_partner, c->d_orig, c->d_batches, c->d_tile_slots, c->d_tile_orig, c->d_dump_counters, c->d_mut_row, c->d_mut_site,
@@ -652,6 +657,9 @@ void pansim_destroy(pansim_ctx *c)
         if (c->ev_parents[i]) cudaEventDestroy(c->ev_parents[i]);
         if (c->ev_core_done[i]) cudaEventDestroy(c->ev_core_done[i]);
     }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->stream_aux) cudaStreamDestroy(c->stream_aux);
     if (c->stream_core) cudaStreamDestroy(c->stream_core);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -708,6 +716,9 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
             CU(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
             CU(c, cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, hi));
             CU(c, cudaStreamCreateWithPriority(&c->stream_core, cudaStreamNonBlocking, lo));
+            CU(c, cudaStreamCreateWithPriority(&c->stream_aux, cudaStreamNonBlocking, hi));
+            CU(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+            CU(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
         }
         for (int i = 0; i < 3; i++) {
             CU(c, cudaEventCreateWithFlags(&c->ev_parents[i], cudaEventDisableTiming));
@@ -728,9 +739,8 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
             CU(c, cudaMemcpy(c->d_mut_img, img.data(), img.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         }
         {
-            const std::vector<uint32_t> img = poisson_table_image(c->tab_hr);
-            CU(c, cudaMalloc(&c->tab_hr.d_thr, img.size() * sizeof(uint32_t)));
-            CU(c, cudaMemcpy(c->tab_hr.d_thr, img.data(), img.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            CU(c, cudaMalloc(&c->tab_hr.d_thr, c->tab_hr.thr.size() * sizeof(uint32_t)));      // thresholds only (core_hr.cuh)
+            CU(c, cudaMemcpy(c->tab_hr.d_thr, c->tab_hr.thr.data(), c->tab_hr.thr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         }
         for (uint32_t k = 0; k < cfg->n_compartments; k++) {
             const double sites = (double)(cfg->comp_hi[k] - cfg->comp_lo[k]);
@@ -774,7 +784,7 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
             CU(c, cudaMalloc(&c->d_hr_ovf, (size_t)c->hr_ovf_cap * 8));
             CU(c, cudaMalloc(&c->d_hr_ovf_count, 2 * sizeof(uint32_t)));
             CU(c, cudaMemset(c->d_hr_ovf_count, 0, 2 * sizeof(uint32_t)));
-            c->hr_smem = hr_collect_smem_bytes(GUIDE_ENTRIES + c->tab_hr.size);
+            c->hr_smem = hr_collect_smem_bytes(c->tab_hr.size);
         }
         const size_t n = c->N;
         for (int i = 0; i < 3; i++) CU(c, cudaMalloc(&c->d_parents_buf[i], n * 4));
@@ -797,7 +807,8 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
         CU(c, cudaMemset(c->d_dump_counters, 0, 2 * sizeof(uint32_t)));
 
         // launch shape of the core kernel
-        c->core_smem = core_mut_smem_bytes(c->tab_mut.size);
+        c->core_smem = core_mut_smem_bytes(c->tab_mut.size, c->tab_hr.nsub ? c->tab_hr.size : 0u);
+        if (const char *e = getenv("PANSIM_HR_DEFER")) c->hr_defer = atoi(e) != 0;
         CU(c, cudaFuncSetAttribute(pair_core_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes()));
         CU(c, cudaFuncSetAttribute(core_mut_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->core_smem));
         CU(c, cudaFuncSetAttribute(core_mut_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->core_smem));
@@ -809,35 +820,17 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
         // short-lived CTAs (3 items per warp, tuned on B200): many waves over the resident slots
         const uint64_t items = (uint64_t)c->N * c->n_regions;
         c->core_items_per_warp = 3;
+        if (const char *e = getenv("PANSIM_CORE_CTAS_PER_SM")) {
+            // long-lived CTAs: a grid of (CTAs per SM) x (SM count), each warp takes its share of the items
+            const uint64_t ctas = (uint64_t)std::max(1, atoi(e)) * c->sm_count;
+            c->core_items_per_warp = (uint32_t)std::max<uint64_t>(1, (items + ctas * CM_WARPS - 1) / (ctas * CM_WARPS));
+        }
         if (const char *e = getenv("PANSIM_CORE_ITEMS_PER_WARP")) c->core_items_per_warp = (uint32_t)std::max(1, atoi(e));
         const uint64_t per_cta = (uint64_t)CM_WARPS * c->core_items_per_warp;
         c->core_grid = (uint32_t)std::max<uint64_t>(1, (items + per_cta - 1) / per_cta);
-        if (c->tab_hr.nsub && core_bytes) {
-            // fused generation kernel: column blocks of ~PANSIM_CORE_BLOCK_MB of packed state (all rows)
-            if (const char *e = getenv("PANSIM_CORE_FUSED")) c->core_fused = atoi(e) != 0;
-            double block_mb = 4.0;
-            if (const char *e = getenv("PANSIM_CORE_BLOCK_MB")) block_mb = std::max(0.001, atof(e));
-            GenSched &s = c->sched;
-            s.blk_regs = (uint32_t)std::max(1.0, std::floor(block_mb * 1048576.0 / ((double)c->N * REGION_BYTES)));
-            if (s.blk_regs > c->n_regions) s.blk_regs = c->n_regions;
-            s.n_blocks = (c->n_regions + s.blk_regs - 1) / s.blk_regs;
-            s.ctas = div_up64((uint64_t)c->N * s.blk_regs, per_cta);
-            // a block is collected once a full wave of later CTAs has been dispatched after it
-            const uint32_t wave = (uint32_t)(c->sm_count * occ);
-            s.lag_collect = std::max(1u, (wave + s.ctas - 1) / s.ctas + 1u);
-            if (const char *e = getenv("PANSIM_CORE_LAG")) s.lag_collect = (uint32_t)std::max(1, atoi(e));
-            s.lag_apply = s.lag_collect + std::max(1u, (wave / 4 + s.ctas - 1) / s.ctas);
-            s.ctas_overflow = 8;
-            s.ctl_words = 1 + 2 * s.n_blocks;
-            CU(c, cudaMalloc(&c->d_gen_ctl, 2 * (size_t)s.ctl_words * 4));
-            CU(c, cudaMemset(c->d_gen_ctl, 0, 2 * (size_t)s.ctl_words * 4));
-            if (c->hr_smem > c->core_smem) FAIL(c, PANSIM_ERR_INVALID, "recombination table does not fit the fused kernel's shared memory");
-            CU(c, cudaFuncSetAttribute(core_gen_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->core_smem));
-            CU(c, cudaFuncSetAttribute(core_gen_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->core_smem));
-            if (c->hr_smem > 48 * 1024) {
-                CU(c, cudaFuncSetAttribute(hr_collect_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->hr_smem));
-                CU(c, cudaFuncSetAttribute(hr_collect_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->hr_smem));
-            }
+        if (c->tab_hr.nsub && core_bytes && c->hr_smem > 48 * 1024) {
+            CU(c, cudaFuncSetAttribute(hr_collect_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->hr_smem));
+            CU(c, cudaFuncSetAttribute(hr_collect_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->hr_smem));
         }
         return 0;
     };
@@ -910,6 +903,7 @@ int pansim_upload_core(pansim_ctx *c, const uint8_t *bytes)
     if (rows_per > c->N) rows_per = c->N;
     if (int rc = ensure_stage(c, (size_t)rows_per * c->Ll)) return rc;
     uint8_t *dst = c->core[c->core_cur];
+    c->hr_pending = false;                       // the state is replaced
     for (uint32_t r0 = 0; r0 < c->N; r0 += rows_per) {
         const uint32_t nr = std::min(rows_per, c->N - r0);
         CU(c, cudaMemcpyAsync(c->d_stage, bytes + (size_t)r0 * c->Ll, (size_t)nr * c->Ll, cudaMemcpyHostToDevice, c->stream));
@@ -948,6 +942,7 @@ int pansim_set_initial(pansim_ctx *c, const uint8_t *core_row, const uint8_t *ac
         if (int rc = ensure_stage(c, (size_t)c->Ll)) return rc;
         CU(c, cudaMemcpyAsync(c->d_stage, core_row + c->site_begin, c->Ll, cudaMemcpyHostToDevice, c->stream));
         uint8_t *dst = c->core[c->core_cur];
+        c->hr_pending = false;                   // the state is replaced
         pack_core_kernel<<<div_up64(c->core_stride / 4, 256), 256, 0, c->stream>>>(c->d_stage, c->Ll, 0, 1, dst, c->core_stride, c->d_err);
         LAUNCH_CHECK(c);
         if (c->N > 1) {
@@ -972,6 +967,7 @@ int pansim_download_core(pansim_ctx *c, uint8_t *out)
     if (!c || !out) return PANSIM_ERR_INVALID;
     CU(c, cudaSetDevice(c->cfg.device));
     if (c->Ll == 0) return 0;
+    if (int rc = core_materialize(c, c->stream)) return rc;
     if (int rc = check_hr_flag(c)) return rc;
     uint32_t rows_per = (uint32_t)std::max<uint64_t>(1, (256ull << 20) / c->Ll);
     if (rows_per > c->N) rows_per = c->N;
@@ -992,6 +988,7 @@ int pansim_export_core_csv(pansim_ctx *c, uint32_t row_begin, uint32_t row_end, 
     if (!c || !out || row_begin > row_end || row_end > c->N) return PANSIM_ERR_INVALID;
     CU(c, cudaSetDevice(c->cfg.device));
     if (c->Ll == 0) return 0;
+    if (int rc = core_materialize(c, c->stream)) return rc;
     const size_t row_bytes = 2 * (size_t)c->Ll;
     uint32_t rows_per = (uint32_t)std::max<uint64_t>(1, (256ull << 20) / row_bytes);
     if (int rc = ensure_stage(c, (size_t)std::min<uint32_t>(rows_per, std::max(1u, row_end - row_begin)) * row_bytes)) return rc;
@@ -1394,6 +1391,8 @@ static int pair_counts_impl(pansim_ctx *c, const uint32_t *r1, const uint32_t *r
     CU(c, cudaMemcpyAsync(c->d_r1, r1, P * 4, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemcpyAsync(c->d_r2, r2, P * 4, cudaMemcpyHostToDevice, c->stream));
     timing_begin(c);
+    if (d_cd && c->Ll)
+        if (int rc = core_materialize(c, c->stream)) return rc;     // recombination events still pending on the rows
     if (d_cd) {
         ScopedSpan s(c, TG_PAIR_CORE);
         if (c->Ll == 0) {

@@ -513,31 +513,38 @@ def test_recombination_list_pass_last_event_of_a_cell_wins(kw):
         assert repeats > 0
 
 
-@pytest.mark.parametrize("kw,block_mb,lag", [
-    (dict(pop_size=200, core_size=8192 * 40 + 77, HR_rate=0.05), "0.5", "1"),      # 14 column blocks
-    (dict(pop_size=200, core_size=8192 * 40 + 77, HR_rate=0.05), "0.01", "2"),     # one region per block, lag 2
-    (dict(pop_size=64, core_size=8192 * 9, HR_rate=1.0, core_mu=0.2), "0.2", "1"), # multi-window items
-    (dict(pop_size=3000, core_size=8192 * 12 + 5, HR_rate=0.05), "16", "1"),       # default block size, 3 blocks
+@pytest.mark.parametrize("kw", [
+    dict(pop_size=200, core_size=8192 * 40 + 77, HR_rate=0.05),            # default rates, ragged last region
+    dict(pop_size=64, core_size=8192 * 9, HR_rate=1.0, core_mu=0.2),       # several windows of 32 events per item
+    dict(pop_size=40, core_size=8192 * 2 + 999, HR_rate=4.0, core_mu=0.6), # ~2000 events per region, many same-cell repeats
+    dict(pop_size=3000, core_size=8192 * 12 + 5, HR_rate=0.05),
+    dict(pop_size=2, core_size=100, HR_rate=1.0, core_mu=0.5),             # the only possible donor is the other row
 ])
-def test_fused_generation_kernel_equals_separate_launches(monkeypatch, kw, block_mb, lag):
-    """core_gen_kernel pipelines gather+SNP, recombination collect and apply over column blocks
-    inside one launch (CTA roles ordered by ticket, acquire/release counters between them). It
-    must leave exactly the state that the three stand-alone launches leave."""
-    p = small_params(n_gen=4, **kw)
+def test_deferred_recombination_equals_immediate(monkeypatch, kw):
+    """Default mode defers the recombination events of generation g: the next core step applies them
+    to every region it gathers (donor cells read from the old, read-only buffer), and a reader of
+    the state materialises them first (core_mut.cuh header). The state seen by download / distances
+    after every generation must equal the one left by the immediate mode (PANSIM_HR_DEFER=0: collect +
+    apply launches right after each gather+SNP pass), which the event-dump tests pin to the oracle."""
+    p = small_params(n_gen=5, **kw)
     d = pb.derive(p)
     rng = np.random.default_rng(23)
     core, acc = random_state(rng, p.pop_size, p.core_size, d.pan_size)
-    states = []
-    for fused in ("0", "1"):
-        monkeypatch.setenv("PANSIM_CORE_FUSED", fused)
-        monkeypatch.setenv("PANSIM_CORE_BLOCK_MB", block_mb)
-        monkeypatch.setenv("PANSIM_CORE_LAG", lag)
+    r1, r2 = sample_pairs(rng, p.pop_size, 50)
+    out = {}
+    for defer in ("0", "1"):
+        monkeypatch.setenv("PANSIM_HR_DEFER", defer)
         with make(p) as sim:
             sim.upload(core, acc)
-            sim.run_generations(0, p.n_gen)
-            states.append(sim.download_core())
-    assert (states[0] == states[1]).all()
-    assert (states[0] != core).any()
+            sim.run_generations(0, 3)                    # two deferred applications inside the batch
+            mid = sim.download_core()                    # materialises generation 2's events
+            sim.run_generations(3, 1)
+            cd = sim.pair_counts(r1, r2)[0]              # materialises generation 3's events
+            sim.run_generations(4, 1)
+            out[defer] = (mid, cd, sim.download_core(), sim.parents())
+    for a, b in zip(out["0"], out["1"]):
+        assert (a == b).all()
+    assert (out["0"][2] != core).any()
 
 
 def test_recombination_is_reproducible_and_seed_dependent():
