@@ -72,10 +72,12 @@ struct CoreMutArgs {
     uint64_t site_limit;      // global site index one past the last valid site of this shard
     uint2 key;
     uint32_t gen;
-    const uint32_t *mut_img;  // device image [CM_GUIDE u16 guide][mut_size thresholds]
+    // constants of the launch, one contiguous device image copied into shared memory by a single bulk
+    // copy: [243 x uint4 allele-digit table (CM_LUT_BYTES)][CM_GUIDE u16 guide][mut_size thresholds of the
+    // SNP count per 256-site block][hr_size thresholds of the recombination count per region]
+    const uint8_t *const_img;
     uint32_t mut_size, mut_nsub, mut_kmax;
     // recombination events of generation hr_gen still pending on old_state (hr_nsub = 0: none)
-    const uint32_t *hr_thr;   // device thresholds of the per-region event count (HrArgs::tab)
     uint32_t hr_size, hr_nsub, hr_kmax, hr_gen;
     // optional event dump (parity instrumentation)
     uint32_t *dump_counters;  // [0] = SNP events
@@ -86,13 +88,19 @@ struct CoreMutArgs {
 
 __host__ __device__ static inline uint32_t core_mut_tab_words(uint32_t mut_size, uint32_t hr_size)
 {
-    return (CM_GUIDE_WORDS + mut_size + hr_size + 1u) & ~1u;     // mbarriers behind it are 8-byte objects
+    return (CM_GUIDE_WORDS + mut_size + hr_size + 3u) & ~3u;     // bulk copies move multiples of 16 bytes
+}
+
+// bytes of the constant image (device and shared memory)
+__host__ __device__ static inline uint32_t core_mut_const_bytes(uint32_t mut_size, uint32_t hr_size)
+{
+    return CM_LUT_BYTES + core_mut_tab_words(mut_size, hr_size) * 4u;
 }
 
 static inline size_t core_mut_smem_bytes(uint32_t mut_size, uint32_t hr_size)
 {
-    return 2048 /* alignment slack */ + (size_t)CM_WARPS * CM_STAGES * REGION_BYTES + CM_LUT_BYTES +
-           (size_t)core_mut_tab_words(mut_size, hr_size) * sizeof(uint32_t) + (size_t)CM_WARPS * CM_STAGES * sizeof(uint64_t);
+    return 2048 /* alignment slack */ + (size_t)CM_WARPS * CM_STAGES * REGION_BYTES + core_mut_const_bytes(mut_size, hr_size) +
+           (size_t)(CM_WARPS * CM_STAGES + 1) * sizeof(uint64_t);
 }
 
 // Poisson by CDF inversion (see common.cuh) with a 512-bin u16 guide: entry =
@@ -231,7 +239,7 @@ struct MutSmem {
     uint8_t *lut;        // 243 x uint4
     uint32_t *tab;       // Poisson image (SNP count per 256-site block)
     uint32_t *hr_thr;    // Poisson thresholds (pending recombination events per region)
-    uint64_t *bars;      // CM_WARPS x CM_STAGES mbarriers
+    uint64_t *bars;      // CM_WARPS x CM_STAGES mbarriers of the stage ring, then one for the constant image
 };
 
 __device__ __forceinline__ MutSmem mut_smem_carve(uint8_t *smem_dyn, uint32_t mut_size, uint32_t hr_size)
@@ -247,33 +255,26 @@ __device__ __forceinline__ MutSmem mut_smem_carve(uint8_t *smem_dyn, uint32_t mu
     return m;
 }
 
-// CTA prologue: Poisson image and digit table into shared memory, mbarriers initialised.
-// Ends with __syncthreads().
+// CTA prologue: mbarriers initialised, bulk copy of the constant image started (completion on
+// bars[CM_WARPS * CM_STAGES]; mut_const_wait before the first table access). Ends with __syncthreads().
 template <bool RNG>
 __device__ __forceinline__ void mut_cta_setup(const CoreMutArgs &a, const MutSmem &m)
 {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (RNG) {
-#pragma unroll 1
-        for (uint32_t i = threadIdx.x; i < CM_GUIDE_WORDS + a.mut_size; i += CM_THREADS) m.tab[i] = a.mut_img[i];
-        if (a.hr_nsub)
-            for (uint32_t i = threadIdx.x; i < a.hr_size; i += CM_THREADS) m.hr_thr[i] = a.hr_thr[i];
-        if (threadIdx.x < CM_LUT_ENTRIES) {
-            uint32_t v = threadIdx.x;
-            uint4 e;
-            e.x = (v % 3u + 1u) * 0x55555555u; v /= 3u;
-            e.y = (v % 3u + 1u) * 0x55555555u; v /= 3u;
-            e.z = (v % 3u + 1u) * 0x55555555u; v /= 3u;
-            e.w = (v % 3u + 1u) * 0x55555555u;
-            reinterpret_cast<uint4 *>(m.lut)[threadIdx.x] = e;
-        }
-    }
     if (lane == 0) {
         for (int s = 0; s < CM_STAGES; s++) mbar_init(&m.bars[warp * CM_STAGES + s], 1);
+        if (warp == 0) mbar_init(&m.bars[CM_WARPS * CM_STAGES], 1);
         fence_mbar_init();
     }
     __syncthreads();
+    if (RNG && threadIdx.x == 0) {
+        const uint32_t bytes = core_mut_const_bytes(a.mut_size, a.hr_nsub ? a.hr_size : 0u);
+        mbar_arrive_expect_tx(&m.bars[CM_WARPS * CM_STAGES], bytes);
+        bulk_g2s(m.lut, a.const_img, bytes, &m.bars[CM_WARPS * CM_STAGES]);
+    }
 }
+
+__device__ __forceinline__ void mut_const_wait(const MutSmem &m) { mbar_wait(&m.bars[CM_WARPS * CM_STAGES], 0u); }
 
 // Items [item_begin, item_end) of a column block of `blk_regs` regions starting at local region
 // `blk_reg0`: item t -> row t / blk_regs, region blk_reg0 + t % blk_regs. Warp w takes
@@ -311,6 +312,7 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
     }
 
     uint32_t row = gw / blk_regs, breg = gw % blk_regs;
+    if (RNG) mut_const_wait(m);
     const bool hr_on = RNG && a.hr_nsub != 0u;
     HrWindow hw_cur{0u, 0u, 0u};
     if (hr_on) hw_cur = hr_window_fetch(a, m.hr_thr, a.parents ? __ldg(a.parents + row) : row, blk_reg0 + breg, lane, 0u, 0u);

@@ -159,7 +159,7 @@ struct pansim_ctx {
     bool fitness_blocked = false; // large shapes: blocked (fixed-association) fitness sum instead of the sequential chain
 
     HostPoissonTable tab_mut, tab_hr;    // per 256-site block (SNPs), per 8192-site region (HR)
-    uint32_t *d_mut_img = nullptr;
+    uint8_t *d_core_img = nullptr;       // constant image of the core kernel (core_mut.cuh)
     uint32_t flip_thr[2] = {0, 0};
     double flip_p[2] = {0, 0};
     double hgt_scale[2] = {0, 0};
@@ -451,8 +451,8 @@ void fill_core_args(pansim_ctx *c, CoreMutArgs &a, uint32_t gen)
     a.site_limit = c->site_end;
     a.key = make_uint2((uint32_t)c->cfg.seed, (uint32_t)(c->cfg.seed >> 32));
     a.gen = gen;
-    a.mut_img = c->d_mut_img; a.mut_size = c->tab_mut.size; a.mut_nsub = c->tab_mut.nsub; a.mut_kmax = c->tab_mut.kmax;
-    a.hr_thr = c->tab_hr.d_thr; a.hr_size = c->tab_hr.size; a.hr_kmax = c->tab_hr.kmax; a.hr_gen = c->hr_pending_gen;
+    a.const_img = c->d_core_img; a.mut_size = c->tab_mut.size; a.mut_nsub = c->tab_mut.nsub; a.mut_kmax = c->tab_mut.kmax;
+    a.hr_size = c->tab_hr.size; a.hr_kmax = c->tab_hr.kmax; a.hr_gen = c->hr_pending_gen;
     a.hr_nsub = c->hr_pending ? c->tab_hr.nsub : 0u;
     a.dump_counters = c->d_dump_counters;
     a.dump_cap = c->dump_cap;
@@ -644,7 +644,7 @@ void pansim_destroy(pansim_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->stream_core) cudaStreamSynchronize(c->stream_core);
     if (c->stream_aux) cudaStreamSynchronize(c->stream_aux);
-    void *ptrs[] = {c->core[0], c->core[1], c->d_hr_slots, c->d_hr_counts, c->d_hr_ovf, c->d_hr_ovf_count, c->d_mut_img, c->acc[0], c->acc[1], c->d_parents_buf[0], c->d_parents_buf[1], c->d_parents_buf[2], c->d_lw, c->d_logfit, c->d_avgdist,
+    void *ptrs[] = {c->core[0], c->core[1], c->d_hr_slots, c->d_hr_counts, c->d_hr_ovf, c->d_hr_ovf_count, c->d_core_img, c->acc[0], c->acc[1], c->d_parents_buf[0], c->d_parents_buf[1], c->d_parents_buf[2], c->d_lw, c->d_logfit, c->d_avgdist,
                     c->d_num_genes, c->d_tmp_a, c->d_tmp_b, c->d_weights, c->d_cum, c->d_err, c->d_inter, c->d_rowInvK, c->d_gain_planes,
                     c->d_gain_thr, c->tab_mut.d_thr, c->tab_hr.d_thr, c->d_r1, c->d_r2, c->d_cd, c->d_in, c->d_un,
                     c->d_replay, c->d_hkeys, c->d_hvals, c->d_stage, c->d_groups, c->d_partner, c->d_orig, c->d_batches, c->d_tile_slots, c->d_tile_orig, c->d_dump_counters, c->d_mut_row, c->d_mut_site,
@@ -734,9 +734,20 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
         build_poisson_table(rate_hr * REGION_SITES, c->tab_hr);
         if ((double)c->tab_hr.nsub * c->tab_hr.kmax > 1.5e7) FAIL(c, PANSIM_ERR_INVALID, "recombination rate too high (more than ~1e7 events per 8192-site region)");
         {
-            const std::vector<uint32_t> img = poisson_fast_image(c->tab_mut);
-            CU(c, cudaMalloc(&c->d_mut_img, img.size() * sizeof(uint32_t)));
-            CU(c, cudaMemcpy(c->d_mut_img, img.data(), img.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+            // constant image of the core kernel: allele-digit table, SNP count table, recombination thresholds
+            const uint32_t hr_size = c->tab_hr.nsub ? c->tab_hr.size : 0u;
+            std::vector<uint8_t> img(core_mut_const_bytes(c->tab_mut.size, hr_size), 0);
+            uint32_t *lut = reinterpret_cast<uint32_t *>(img.data());
+            for (uint32_t v = 0; v < CM_LUT_ENTRIES; v++) {
+                // entry v = base-3 digits of v; word j = allele code (digit j) + 1 in all 16 cells: {C,G,T} (population.rs:531)
+                uint32_t t = v;
+                for (int j = 0; j < 4; j++) { lut[v * 4 + j] = (t % 3u + 1u) * 0x55555555u; t /= 3u; }
+            }
+            const std::vector<uint32_t> mimg = poisson_fast_image(c->tab_mut);
+            memcpy(img.data() + CM_LUT_BYTES, mimg.data(), mimg.size() * 4);
+            if (hr_size) memcpy(img.data() + CM_LUT_BYTES + mimg.size() * 4, c->tab_hr.thr.data(), (size_t)hr_size * 4);
+            CU(c, cudaMalloc(&c->d_core_img, img.size()));
+            CU(c, cudaMemcpy(c->d_core_img, img.data(), img.size(), cudaMemcpyHostToDevice));
         }
         {
             CU(c, cudaMalloc(&c->tab_hr.d_thr, c->tab_hr.thr.size() * sizeof(uint32_t)));      // thresholds only (core_hr.cuh)
