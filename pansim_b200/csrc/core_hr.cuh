@@ -100,7 +100,8 @@ __device__ __noinline__ uint32_t hr_count_extra(uint32_t greg, uint32_t row, uin
 
 // event e of item (global region greg, row): site of the region and donor row (population.rs:616-619)
 struct HrEvent { uint32_t pos, donor, w; };
-__device__ __forceinline__ HrEvent hr_event(uint32_t greg, uint32_t row, uint32_t gen, uint2 key, uint32_t e, uint32_t n_other)
+template <typename Key>      // uint2 key or precomputed PhiloxKeys
+__device__ __forceinline__ HrEvent hr_event(uint32_t greg, uint32_t row, uint32_t gen, const Key &key, uint32_t e, uint32_t n_other)
 {
     const uint4 r = philox4x32_10(make_uint4(greg, row, gen, HR_EVENT_W0 + e), key);
     HrEvent ev;

@@ -71,6 +71,7 @@ struct CoreMutArgs {
     uint32_t items_per_warp;
     uint64_t site_limit;      // global site index one past the last valid site of this shard
     uint2 key;
+    PhiloxKeys rk;            // round keys of `key`
     uint32_t gen;
     // constants of the launch, one contiguous device image copied into shared memory by a single bulk
     // copy: [243 x uint4 allele-digit table (CM_LUT_BYTES)][CM_GUIDE u16 guide][mut_size thresholds of the
@@ -204,7 +205,7 @@ __device__ __forceinline__ HrWindow hr_window_fetch(const CoreMutArgs &a, const 
     const uint32_t greg = a.region0 + reg;
     const uint64_t rem_sites = a.site_limit - (uint64_t)greg * REGION_SITES;
     const uint32_t lim = rem_sites < REGION_SITES ? (uint32_t)rem_sites : REGION_SITES;
-    const HrEvent ev = hr_event(greg, prow, a.hr_gen, a.key, base + lane, a.n_rows - 1u);
+    const HrEvent ev = hr_event(greg, prow, a.hr_gen, a.rk, base + lane, a.n_rows - 1u);
     HrWindow h;
     h.K = K_known;
     if (base == 0u) {
@@ -292,16 +293,20 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
     const uint32_t n_my = (item_end - gw + CM_WARPS - 1) / CM_WARPS;
     const uint32_t d_row = CM_WARPS / blk_regs, d_reg = CM_WARPS % blk_regs;
 
-    // the load side runs CM_STAGES-1 items ahead with its own (row, reg) cursor (lane 0 only)
-    uint32_t l_row = gw / blk_regs, l_reg = gw % blk_regs, l_j = 0;
+    // the load side runs CM_STAGES-1 items ahead with its own (row, reg, stage) cursor (lane 0 only)
+    uint32_t l_row = gw / blk_regs, l_reg = gw % blk_regs, l_stage = 0;
+    const uint32_t stages_s = smem_u32(stages), bars_s = smem_u32(bars);
+    const uint8_t *old_blk = a.old_state + (uint64_t)blk_reg0 * REGION_BYTES;
 #define PANSIM_CM_ISSUE_LOAD()                                                                               \
     do {                                                                                                     \
-        const uint8_t *src_ = a.old_state + (uint64_t)(a.parents ? a.parents[l_row] : l_row) * a.row_stride + \
-                              (uint64_t)(blk_reg0 + l_reg) * REGION_BYTES;                                   \
-        const uint32_t s_ = l_j % CM_STAGES;                                                                 \
-        mbar_arrive_expect_tx(&bars[s_], REGION_BYTES);                                                      \
-        bulk_g2s(stages + s_ * REGION_BYTES, src_, REGION_BYTES, &bars[s_]);                                 \
-        l_j++; l_row += d_row; l_reg += d_reg;                                                               \
+        const uint8_t *src_ = old_blk + (uint64_t)(a.parents ? __ldg(a.parents + l_row) : l_row) * a.row_stride + \
+                              l_reg * REGION_BYTES;                                                          \
+        const uint32_t bar_ = bars_s + l_stage * 8u;                                                         \
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_), "n"(REGION_BYTES) : "memory"); \
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" \
+                     ::"r"(stages_s + l_stage * REGION_BYTES), "l"(src_), "n"(REGION_BYTES), "r"(bar_) : "memory"); \
+        l_stage = l_stage == (uint32_t)(CM_STAGES - 1) ? 0u : l_stage + 1u;                                  \
+        l_row += d_row; l_reg += d_reg;                                                                      \
         if (l_reg >= blk_regs) { l_reg -= blk_regs; l_row++; }                                               \
     } while (0)
 
@@ -316,8 +321,8 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
     const bool hr_on = RNG && a.hr_nsub != 0u;
     HrWindow hw_cur{0u, 0u, 0u};
     if (hr_on) hw_cur = hr_window_fetch(a, m.hr_thr, a.parents ? __ldg(a.parents + row) : row, blk_reg0 + breg, lane, 0u, 0u);
+    uint32_t s = 0, par = 0;                 // stage of item j and the phase parity of its mbarrier
     for (uint32_t j = 0; j < n_my; j++) {
-        const uint32_t s = j % CM_STAGES;
         uint32_t *sw = reinterpret_cast<uint32_t *>(stages + s * REGION_BYTES);
         const uint32_t reg = blk_reg0 + breg;
 
@@ -330,15 +335,15 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
         uint4 c0 = make_uint4(0, 0, 0, 0), c1 = make_uint4(0, 0, 0, 0);
         uint32_t k = 0;
         if (RNG && a.mut_nsub) {
-            c0 = philox4x32_10(mctr, a.key);
+            c0 = philox4x32_10(mctr, a.rk);
             uint4 t = mctr;
             t.w += 1u;
-            c1 = philox4x32_10(t, a.key);
+            c1 = philox4x32_10(t, a.rk);
             k = poisson_fast(tab, a.mut_kmax, c0.x);
             if (a.mut_nsub > 1) k += mut_count_extra(mctr, a.key, tab, a.mut_nsub, a.mut_kmax);
         }
 
-        mbar_wait(&bars[s], (j / CM_STAGES) & 1u);
+        mbar_wait(&bars[s], par);
 
         if (hr_on) {
             // ---- recombination of the previous generation on the parent's row (population.rs:725-748):
@@ -377,7 +382,7 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
             for (uint32_t base = CM_GROUP0, call = 2u; base < kw; base += CM_TAIL, call++) {
                 uint4 t = mctr;
                 t.w += call;
-                const uint4 c = philox4x32_10(t, a.key);
+                const uint4 c = philox4x32_10(t, a.rk);
                 uint32_t res = (c.x >> 16) | 0xFFFF0000u;
                 f.run(base, c.x & 255u, c.y, res);
                 if (kw > base + 4u) f.run(base + 4u, (c.x >> 8) & 255u, c.z, res);
@@ -407,6 +412,7 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
         __syncwarp();
         row += d_row; breg += d_reg;
         if (breg >= blk_regs) { breg -= blk_regs; row++; }
+        if (++s == (uint32_t)CM_STAGES) { s = 0; par ^= 1u; }
     }
     if (lane == 0) bulk_wait<0>();
 #undef PANSIM_CM_ISSUE_LOAD

@@ -450,6 +450,7 @@ void fill_core_args(pansim_ctx *c, CoreMutArgs &a, uint32_t gen)
     a.items_per_warp = c->core_items_per_warp;
     a.site_limit = c->site_end;
     a.key = make_uint2((uint32_t)c->cfg.seed, (uint32_t)(c->cfg.seed >> 32));
+    a.rk = philox_key_schedule(a.key);
     a.gen = gen;
     a.const_img = c->d_core_img; a.mut_size = c->tab_mut.size; a.mut_nsub = c->tab_mut.nsub; a.mut_kmax = c->tab_mut.kmax;
     a.hr_size = c->tab_hr.size; a.hr_kmax = c->tab_hr.kmax; a.hr_gen = c->hr_pending_gen;
