@@ -116,6 +116,7 @@ struct pansim_ctx {
     cudaEvent_t ev_parents[3] = {nullptr, nullptr, nullptr};    // parents[i] written
     cudaEvent_t ev_core_done[3] = {nullptr, nullptr, nullptr};  // core step that read parents[i] finished
     bool core_done_valid[3] = {false, false, false};
+    bool core_unjoined = false;           // a core step is in flight on stream_core that `stream` has not been ordered after
     uint32_t *d_parents_buf[3] = {nullptr, nullptr, nullptr};
     int parents_idx = 0;
     int sm_count = 0;
@@ -156,6 +157,8 @@ struct pansim_ctx {
     uint32_t *d_gain_planes = nullptr;   // [gene words][32] bit-planes of the HGT gain thresholds
     bool avgdist_valid = false;
     bool fitness_valid = false;   // d_logfit / d_num_genes match the current accessory state
+    bool neutral = true;          // every selection coefficient is 0 (ln(1 + s_j) = +0.0 for all genes)
+    bool inter_popc = false;      // competition term: AND/popcount tiles instead of the tensor-core kernel
     bool fitness_blocked = false; // large shapes: blocked (fixed-association) fitness sum instead of the sequential chain
 
     HostPoissonTable tab_mut, tab_hr;    // per 256-site block (SNPs), per 8192-site region (HR)
@@ -326,12 +329,15 @@ int launch_fitness(pansim_ctx *c, cudaStream_t st = nullptr)
     if (c->fitness_valid) return 0;
     if (!st) st = c->stream;
     const uint32_t *acc = c->acc[c->acc_cur];
-    if (c->fitness_blocked)
+    if (c->neutral)          // every ln(1 + s_j) is +0.0: the sum is +0.0, only the row popcounts are needed
+        fitness_kernel<true><<<div_up64(c->N, FIT_WARPS), FIT_WARPS * 32, 0, st>>>(acc, c->N, c->G, c->acc_stride_words,
+                                                                              c->d_lw, c->d_logfit, c->d_num_genes);
+    else if (c->fitness_blocked)
         fitness_blocked_kernel<<<div_up64(c->N, FIT_WARPS), FIT_WARPS * 32, 0, st>>>(acc, c->N, c->G, c->acc_stride_words,
                                                                                 c->d_lw, c->d_logfit, c->d_num_genes);
     else
-        fitness_kernel<<<div_up64(c->N, FIT_WARPS), FIT_WARPS * 32, 0, st>>>(acc, c->N, c->G, c->acc_stride_words,
-                                                                        c->d_lw, c->d_logfit, c->d_num_genes);
+        fitness_kernel<false><<<div_up64(c->N, FIT_WARPS), FIT_WARPS * 32, 0, st>>>(acc, c->N, c->G, c->acc_stride_words,
+                                                                               c->d_lw, c->d_logfit, c->d_num_genes);
     LAUNCH_CHECK(c);
     c->fitness_valid = true;
     return 0;
@@ -349,9 +355,15 @@ int launch_competition(pansim_ctx *c)
         if (launch_fitness(c, c->stream_aux)) return PANSIM_ERR_CUDA;
         CU(c, cudaEventRecord(c->ev_join, c->stream_aux));
     }
-    const uint32_t nb = div_up64(c->N, 32);
-    acc_inter_kernel<<<dim3(nb, nb), 256, 0, c->stream>>>(c->acc[c->acc_cur], c->N, c->acc_stride_words,
-                                                          c->acc_words, c->d_inter);
+    if (c->inter_popc) {     // PANSIM_INTER_POPC=1: the AND/popcount tile kernel instead of the tensor-core one
+        const uint32_t nb = div_up64(c->N, 32);
+        acc_inter_kernel<<<dim3(nb, nb), 256, 0, c->stream>>>(c->acc[c->acc_cur], c->N, c->acc_stride_words,
+                                                              c->acc_words, c->d_inter);
+    } else {
+        const uint32_t nb = div_up64(c->N, IM_TILE);
+        acc_inter_mma_kernel<<<dim3(nb, nb), 256, 0, c->stream>>>(c->acc[c->acc_cur], c->N, c->acc_stride_words,
+                                                                  c->acc_words, c->d_inter);
+    }
     LAUNCH_CHECK(c);
     if (fork) CU(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     avg_distance_kernel<<<div_up64(c->N, AVG_WARPS), AVG_WARPS * 32, 0, c->stream>>>(c->d_inter, c->d_num_genes, c->N,
@@ -505,10 +517,24 @@ int launch_core_hr(pansim_ctx *c, uint32_t gen, uint8_t *state, cudaStream_t st)
     return 0;
 }
 
+// Order `stream` after the core step that is still in flight on stream_core (if any). The
+// generate-mode entry points return without waiting for the core kernel, so that the selection
+// chain of the next generation overlaps it; whoever touches the core buffers on `stream` joins first.
+int ensure_core_joined(pansim_ctx *c)
+{
+    if (!c->core_unjoined) return 0;
+    const int i = c->parents_idx;
+    if (c->core_done_valid[i]) CU(c, cudaStreamWaitEvent(c->stream, c->ev_core_done[i], 0));
+    c->core_unjoined = false;
+    return 0;
+}
+
 // Apply the pending recombination events to the current core buffer (deferred mode, core_mut.cuh).
 // Every reader of the core state other than the generate-mode core step calls this first.
 int core_materialize(pansim_ctx *c, cudaStream_t st)
 {
+    if (st == c->stream)
+        if (int rc = ensure_core_joined(c)) return rc;
     if (!c->hr_pending) return 0;
     ScopedSpan sp(c, TG_CORE_HR, st);
     if (int rc = launch_core_hr(c, c->hr_pending_gen, c->core[c->core_cur], st)) return rc;
@@ -519,6 +545,8 @@ int core_materialize(pansim_ctx *c, cudaStream_t st)
 int launch_core_step(pansim_ctx *c, uint32_t gen, bool rng, cudaStream_t st)
 {
     if (c->Ll == 0) return 0;
+    if (st == c->stream)
+        if (int rc = ensure_core_joined(c)) return rc;
     const bool hr = rng && c->tab_hr.nsub;
     const bool defer = c->hr_defer && !c->dump_enabled;
     // replay / plain gather, the event dump and the non-deferred mode work on materialised rows
@@ -578,6 +606,7 @@ int launch_population_steps(pansim_ctx *c, uint32_t gen)
     }
     CU(c, cudaEventRecord(c->ev_core_done[i], c->stream_core));
     c->core_done_valid[i] = true;
+    c->core_unjoined = true;
     {
         ScopedSpan s(c, TG_ACC);
         if (int rc = launch_acc_step(c, gen)) return rc;
@@ -586,12 +615,7 @@ int launch_population_steps(pansim_ctx *c, uint32_t gen)
 }
 
 // after a batch of generations: later work on c->stream must see the core state
-int join_core_stream(pansim_ctx *c)
-{
-    const int i = c->parents_idx;
-    if (c->core_done_valid[i]) CU(c, cudaStreamWaitEvent(c->stream, c->ev_core_done[i], 0));
-    return 0;
-}
+int join_core_stream(pansim_ctx *c) { return ensure_core_joined(c); }
 
 int step_device(pansim_ctx *c, uint32_t gen)
 {
@@ -779,6 +803,7 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
         // the bit-exact sequential fitness chain is kept up to 2^25 accessory cells (cfg1-3: 4e6)
         c->fitness_blocked = (uint64_t)c->N * c->G > (1ull << 25);
         if (const char *e = getenv("PANSIM_FITNESS_BLOCKED")) c->fitness_blocked = atoi(e) != 0;
+        if (const char *e = getenv("PANSIM_INTER_POPC")) c->inter_popc = atoi(e) != 0;
         if (c->tab_hr.nsub && core_bytes) {
             // recombination slots: per (region, row) item room for mean + 6 sigma changed cells (a multiple of 32,
             // 32 when the mean is small); the rare item that needs more spills to the overflow list
@@ -890,6 +915,7 @@ int pansim_get_timing(pansim_ctx *c, pansim_timing *o)
     o->launches = c->launches;
     CU(c, cudaSetDevice(c->cfg.device));
     CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaStreamSynchronize(c->stream_core));
     if (!c->timing_enabled || !c->t_begin || !c->t_end) return 0;
     CU(c, cudaEventElapsedTime(&o->total_ms, c->t_begin, c->t_end));
     float g[TG_COUNT] = {0};
@@ -914,6 +940,7 @@ int pansim_upload_core(pansim_ctx *c, const uint8_t *bytes)
     uint32_t rows_per = (uint32_t)std::max<uint64_t>(1, (256ull << 20) / c->Ll);
     if (rows_per > c->N) rows_per = c->N;
     if (int rc = ensure_stage(c, (size_t)rows_per * c->Ll)) return rc;
+    if (int rc = ensure_core_joined(c)) return rc;
     uint8_t *dst = c->core[c->core_cur];
     c->hr_pending = false;                       // the state is replaced
     for (uint32_t r0 = 0; r0 < c->N; r0 += rows_per) {
@@ -953,6 +980,7 @@ int pansim_set_initial(pansim_ctx *c, const uint8_t *core_row, const uint8_t *ac
     if (c->Ll) {
         if (int rc = ensure_stage(c, (size_t)c->Ll)) return rc;
         CU(c, cudaMemcpyAsync(c->d_stage, core_row + c->site_begin, c->Ll, cudaMemcpyHostToDevice, c->stream));
+        if (int rc = ensure_core_joined(c)) return rc;
         uint8_t *dst = c->core[c->core_cur];
         c->hr_pending = false;                   // the state is replaced
         pack_core_kernel<<<div_up64(c->core_stride / 4, 256), 256, 0, c->stream>>>(c->d_stage, c->Ll, 0, 1, dst, c->core_stride, c->d_err);
@@ -1034,7 +1062,12 @@ int pansim_set_selection(pansim_ctx *c, const double *s)
     CU(c, cudaSetDevice(c->cfg.device));
     if (c->G == 0) return 0;
     std::vector<double> lw(c->G);
-    for (uint32_t j = 0; j < c->G; j++) lw[j] = std::log(1.0 + s[j] * 1.0);   // population.rs:306 with x = 1
+    bool neutral = true;
+    for (uint32_t j = 0; j < c->G; j++) {
+        lw[j] = std::log(1.0 + s[j] * 1.0);                                   // population.rs:306 with x = 1
+        if (!(lw[j] == 0.0) || std::signbit(lw[j])) neutral = false;
+    }
+    c->neutral = neutral;
     CU(c, cudaMemcpyAsync(c->d_lw, lw.data(), (size_t)c->G * 8, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     c->fitness_valid = false;
@@ -1120,10 +1153,11 @@ int pansim_step_with_parents(pansim_ctx *c, uint32_t gen, const uint32_t *parent
     if (c->dump_enabled) CU(c, cudaMemsetAsync(c->d_dump_counters, 0, 2 * sizeof(uint32_t), c->stream));
     timing_begin(c);
     if (int rc = launch_population_steps(c, gen)) return rc;
-    if (int rc = join_core_stream(c)) return rc;
     timing_end(c);
     c->avgdist_valid = false;
-    CU(c, cudaStreamSynchronize(c->stream));
+    // Returns with the step enqueued (the parents vector has been consumed: the upload from pageable
+    // host memory is synchronous for the host). The core kernel keeps running beside the next
+    // generation's selection chain; every call that reads or writes the core state joins it first.
     return 0;
 }
 
@@ -1512,6 +1546,7 @@ int pansim_fetch_event_dump(pansim_ctx *c, pansim_event_dump *o)
     if (!c->dump_enabled) FAIL(c, PANSIM_ERR_STATE, "event dump not enabled");
     CU(c, cudaSetDevice(c->cfg.device));
     CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaStreamSynchronize(c->stream_core));
     memset(o, 0, sizeof *o);
     uint32_t cnt[2];
     CU(c, cudaMemcpy(cnt, c->d_dump_counters, sizeof cnt, cudaMemcpyDeviceToHost));

@@ -19,7 +19,11 @@ namespace pansim {
 // ---------------------------------------------------------------------------
 constexpr int FIT_WARPS = 4;
 constexpr int FIT_CHUNK_WORDS = 32;               // 1024 genes per compaction round
+constexpr int FIT_BATCH = 8;                      // chain elements loaded ahead of the additions
 
+// COUNT_ONLY: every selection coefficient is 0 (neutral run: lw_j = ln(1) = +0.0 for all j), the sum
+// is +0.0 whatever the genome; only the row popcounts are needed.
+template <bool COUNT_ONLY>
 __global__ void __launch_bounds__(FIT_WARPS * 32) fitness_kernel(const uint32_t *acc, uint32_t n_rows,
                                                                  uint32_t n_genes, uint32_t stride_words,
                                                                  const double *lw, double *logfit,
@@ -28,15 +32,25 @@ __global__ void __launch_bounds__(FIT_WARPS * 32) fitness_kernel(const uint32_t 
     // Terms of absent genes are ln(1 + s*0) = +0.0: adding them never changes the
     // running sum, so only present genes are added -- in increasing column order,
     // by a single sequential f64 chain per row (bit-exact vs population.rs:303-317).
-    // The warp first compacts the present genes' lw values into shared memory so
-    // the chain is not exposed to load latency.
-    __shared__ double list[FIT_WARPS][FIT_CHUNK_WORDS * 32];
+    // The warp first compacts the present genes' lw values into shared memory, padded with +0.0
+    // to whole batches (the running sum starts at +0.0 and can never become -0.0, so x + (+0.0)
+    // = x); the chain then runs one batch of shared-memory loads ahead of its additions, so it
+    // advances at the latency of a dependent DADD (8.2 cycles on B200).
+    __shared__ double list[COUNT_ONLY ? 1 : FIT_WARPS][COUNT_ONLY ? 1 : FIT_CHUNK_WORDS * 32 + 2 * FIT_BATCH];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t row = blockIdx.x * FIT_WARPS + warp;
     if (row >= n_rows) return;
     const uint32_t *r = acc + (uint64_t)row * stride_words;
     const uint32_t n_words = (n_genes + 31u) / 32u;
-    double *mine = list[warp];
+    if (COUNT_ONLY) {
+        int32_t cnt = 0;
+        for (uint32_t w = lane; w < n_words; w += 32) cnt += __popc(r[w]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) { logfit[row] = 0.0; num_genes[row] = cnt; }
+        return;
+    }
+    double *mine = list[COUNT_ONLY ? 0 : warp];
     double sum = 0.0;
     bool neg_inf = false;
     int32_t cnt = 0;
@@ -53,6 +67,7 @@ __global__ void __launch_bounds__(FIT_WARPS * 32) fitness_kernel(const uint32_t 
         uint32_t off = incl - c;
         const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
         cnt += (int32_t)tot;
+        if (lane < 2 * FIT_BATCH) mine[tot + lane] = 0.0;          // padding behind the last value
         while (bits) {
             const uint32_t b = __ffs(bits) - 1;
             bits &= bits - 1;
@@ -61,14 +76,19 @@ __global__ void __launch_bounds__(FIT_WARPS * 32) fitness_kernel(const uint32_t 
             mine[off++] = v;
         }
         __syncwarp();
-        // every lane runs the same chain; loads are batched so the chain only waits on the adds
-        uint32_t t = 0;
-        for (; t + 8 <= tot; t += 8) {
-            const double v0 = mine[t], v1 = mine[t + 1], v2 = mine[t + 2], v3 = mine[t + 3];
-            const double v4 = mine[t + 4], v5 = mine[t + 5], v6 = mine[t + 6], v7 = mine[t + 7];
-            sum += v0; sum += v1; sum += v2; sum += v3; sum += v4; sum += v5; sum += v6; sum += v7;
+        // every lane runs the same chain
+        double nx[FIT_BATCH];
+#pragma unroll
+        for (int q = 0; q < FIT_BATCH; q++) nx[q] = mine[q];
+        for (uint32_t t = 0; t < tot; t += FIT_BATCH) {
+            double cu[FIT_BATCH];
+#pragma unroll
+            for (int q = 0; q < FIT_BATCH; q++) cu[q] = nx[q];
+#pragma unroll
+            for (int q = 0; q < FIT_BATCH; q++) nx[q] = mine[t + FIT_BATCH + q];
+#pragma unroll
+            for (int q = 0; q < FIT_BATCH; q++) sum += cu[q];
         }
-        for (; t < tot; t++) sum += mine[t];
         __syncwarp();
     }
     neg_inf = __any_sync(0xffffffffu, neg_inf);
@@ -172,35 +192,131 @@ __global__ void __launch_bounds__(256) acc_inter_kernel(const uint32_t *acc, uin
     }
 }
 
+// K2a (tensor cores): the intersection counts are the dense contraction X * X^T of the 0/1
+// presence matrix, so they run on the tensor cores as an integer MMA with exact s32 accumulation:
+// warp-level mma.sync m16n8k32 u8 x u8 (IMMA.16832 in SASS), the bits of a 32-gene word expanded
+// to 0/1 bytes in registers. A dot product does not care in which k slot a gene sits as long as
+// both operands agree, so the expansion is the cheapest one: the thread with t = lane % 4 takes
+// bits {t, t+8, t+16, t+24} ((w >> t) & 0x01010101) for the low k half of the fragment and bits
+// {t+4, ...} for the high half -- over t = 0..3 every bit of the word exactly once.
+// CTA = 64 x 64 pairs, 8 warps of 16 x 32; upper-triangle tiles only, mirrored on store.
+constexpr int IM_TILE = 64;
+constexpr int IM_CHUNK = 32;      // words per shared-memory chunk
+
+__device__ __forceinline__ void imma_16832_u8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                              uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256) acc_inter_mma_kernel(const uint32_t *acc, uint32_t n_rows,
+                                                            uint32_t stride_words, uint32_t n_words,
+                                                            uint32_t *inter)
+{
+    const uint32_t bi = blockIdx.y, bj = blockIdx.x;
+    if (bj < bi) return;
+    __shared__ uint32_t Ri[IM_TILE][IM_CHUNK + 1];
+    __shared__ uint32_t Rj[IM_TILE][IM_CHUNK + 1];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t g = lane >> 2, t = lane & 3;
+    const uint32_t mrow = (warp & 3u) * 16u;          // this warp's 16 rows of the i tile
+    const uint32_t ncol = (warp >> 2) * 32u;          // and 32 columns (4 n-tiles of 8) of the j tile
+    int c[4][4];
+#pragma unroll
+    for (int n = 0; n < 4; n++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) c[n][q] = 0;
+    for (uint32_t w0 = 0; w0 < n_words; w0 += IM_CHUNK) {
+        __syncthreads();
+        const uint32_t w = w0 + lane;
+#pragma unroll
+        for (uint32_t q = 0; q < IM_TILE / 8; q++) {
+            const uint32_t rr = warp + 8u * q;
+            const uint32_t ri = bi * IM_TILE + rr, rj = bj * IM_TILE + rr;
+            Ri[rr][lane] = (w < n_words && ri < n_rows) ? acc[(uint64_t)ri * stride_words + w] : 0u;
+            Rj[rr][lane] = (w < n_words && rj < n_rows) ? acc[(uint64_t)rj * stride_words + w] : 0u;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (uint32_t ks = 0; ks < IM_CHUNK; ks++) {
+            const uint32_t wa = Ri[mrow + g][ks] >> t, wb = Ri[mrow + g + 8][ks] >> t;
+            const uint32_t a0 = wa & 0x01010101u, a1 = wb & 0x01010101u;
+            const uint32_t a2 = (wa >> 4) & 0x01010101u, a3 = (wb >> 4) & 0x01010101u;
+#pragma unroll
+            for (int n = 0; n < 4; n++) {
+                const uint32_t wj = Rj[ncol + n * 8 + g][ks] >> t;
+                imma_16832_u8(c[n], a0, a1, a2, a3, wj & 0x01010101u, (wj >> 4) & 0x01010101u);
+            }
+        }
+    }
+    // accumulator layout: c[n][0..1] = (row g, cols 2t, 2t+1), c[n][2..3] = (row g + 8, same cols)
+#pragma unroll
+    for (int n = 0; n < 4; n++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t i = bi * IM_TILE + mrow + g + ((q >> 1) ? 8u : 0u);
+            const uint32_t j = bj * IM_TILE + ncol + n * 8 + 2 * t + (q & 1);
+            if (i < n_rows && j < n_rows) {
+                inter[(uint64_t)i * n_rows + j] = (uint32_t)c[n][q];
+                inter[(uint64_t)j * n_rows + i] = (uint32_t)c[n][q];
+            }
+        }
+}
+
 // K2b: mean Jaccard distance of individual i to all j != i, summed in j order
 // exactly like get_distance + the fold of population.rs:770-771.
-constexpr int AVG_WARPS = 4;
+constexpr int AVG_WARPS = 8;
+constexpr int AVG_RING = 256;       // distances evaluated per round (8 per lane)
+constexpr int AVG_BATCH = 8;
 
 __global__ void __launch_bounds__(AVG_WARPS * 32) avg_distance_kernel(const uint32_t *inter,
                                                                       const int32_t *num_genes, uint32_t n_rows,
                                                                       uint32_t core_genes, double *avgdist)
 {
-    // One warp per individual: the 32 lanes evaluate 32 distances in parallel (the
-    // f64 division is the expensive part), then the values are added one by one in
-    // j order -- the same sequential chain as the fold of population.rs:770.
-    // Lanes with j == i or j >= N contribute +0.0, which never changes the sum.
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t i = blockIdx.x * AVG_WARPS + (threadIdx.x >> 5);
+    // One warp per individual. Per round the 32 lanes evaluate 256 distances in parallel (the
+    // f64 divisions are independent) into shared memory, then the values are added one by one in
+    // j order -- the same sequential chain as the fold of population.rs:770 -- with the loads one
+    // batch ahead of the additions. Entries with j == i or j >= N are +0.0, which never changes
+    // the (non-negative) sum.
+    __shared__ double ring[AVG_WARPS][AVG_RING + 2 * AVG_BATCH];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t i = blockIdx.x * AVG_WARPS + warp;
     if (i >= n_rows) return;
+    double *mine = ring[warp];
+    if (lane < 2 * AVG_BATCH) mine[AVG_RING + lane] = 0.0;
     const double cg = (double)core_genes;
     const uint32_t ki = (uint32_t)num_genes[i];
     const uint32_t *irow = inter + (uint64_t)i * n_rows;
     double sum = 0.0;
-    for (uint32_t j0 = 0; j0 < n_rows; j0 += 32) {
-        const uint32_t j = j0 + lane;
-        double d = 0.0;
-        if (j < n_rows && j != i) {
-            const uint32_t in = irow[j];
-            const uint32_t un = ki + (uint32_t)num_genes[j] - in;
-            d = 1.0 - (((double)in + 0.0 + cg) / ((double)un + 0.0 + cg));   // :144-145
-        }
+    for (uint32_t j0 = 0; j0 < n_rows; j0 += AVG_RING) {
 #pragma unroll
-        for (int t = 0; t < 32; t++) sum += __shfl_sync(0xffffffffu, d, t);
+        for (int q = 0; q < AVG_RING / 32; q++) {
+            const uint32_t j = j0 + q * 32 + lane;
+            double d = 0.0;
+            if (j < n_rows && j != i) {
+                const uint32_t in = irow[j];
+                const uint32_t un = ki + (uint32_t)num_genes[j] - in;
+                d = 1.0 - (((double)in + 0.0 + cg) / ((double)un + 0.0 + cg));   // :144-145
+            }
+            mine[q * 32 + lane] = d;
+        }
+        __syncwarp();
+        const uint32_t tot = min((uint32_t)AVG_RING, n_rows - j0);
+        double nx[AVG_BATCH];
+#pragma unroll
+        for (int q = 0; q < AVG_BATCH; q++) nx[q] = mine[q];
+        for (uint32_t t = 0; t < tot; t += AVG_BATCH) {
+            double cu[AVG_BATCH];
+#pragma unroll
+            for (int q = 0; q < AVG_BATCH; q++) cu[q] = nx[q];
+#pragma unroll
+            for (int q = 0; q < AVG_BATCH; q++) nx[q] = mine[t + AVG_BATCH + q];
+#pragma unroll
+            for (int q = 0; q < AVG_BATCH; q++) sum += cu[q];
+        }
+        __syncwarp();
     }
     if (lane == 0) {
         double fd = sum / (double)(n_rows - 1u);
@@ -215,42 +331,33 @@ __global__ void __launch_bounds__(AVG_WARPS * 32) avg_distance_kernel(const uint
 // and N draws from Philox(seed, gen, individual). Single CTA: N is small and
 // the whole thing is a chain of reductions.
 // ---------------------------------------------------------------------------
-constexpr int SEL_THREADS = 1024;
+constexpr int SEL_THREADS = 256;      // one CTA slot of an SM: the kernel has to squeeze in beside the core step
+constexpr int SEL_WARPS = SEL_THREADS / 32;
 
-__device__ __forceinline__ double block_reduce(double v, bool is_max, double *scratch)
+// block-wide reduction of three values at once (fixed order: shuffle tree, then the warp results
+// in warp order), result in every thread
+template <bool IS_MAX>
+__device__ __forceinline__ void block_reduce3(double &x, double &y, double &z, double (*scratch)[3])
 {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        const double t = __shfl_xor_sync(0xffffffffu, v, o);
-        v = is_max ? fmax(v, t) : v + t;
+        const double tx = __shfl_xor_sync(0xffffffffu, x, o), ty = __shfl_xor_sync(0xffffffffu, y, o),
+                     tz = __shfl_xor_sync(0xffffffffu, z, o);
+        x = IS_MAX ? fmax(x, tx) : x + tx;
+        y = IS_MAX ? fmax(y, ty) : y + ty;
+        z = IS_MAX ? fmax(z, tz) : z + tz;
     }
     __syncthreads();
-    if (lane == 0) scratch[warp] = v;
+    if (lane == 0) { scratch[warp][0] = x; scratch[warp][1] = y; scratch[warp][2] = z; }
     __syncthreads();
-    double r = scratch[0];
-    for (int q = 1; q < SEL_THREADS / 32; q++) r = is_max ? fmax(r, scratch[q]) : r + scratch[q];
-    return r;
-}
-
-// v[i] <- exp(v[i] - lse(v)) / sum(...)   (population.rs:325-340)
-__device__ void softmax_inplace(double *v, uint32_t n, double *scratch)
-{
-    double m = -INFINITY;
-    for (uint32_t i = threadIdx.x; i < n; i += SEL_THREADS) m = fmax(m, v[i]);
-    m = block_reduce(m, true, scratch);
-    double s = 0.0;
-    for (uint32_t i = threadIdx.x; i < n; i += SEL_THREADS) s += exp(v[i] - m);
-    s = block_reduce(s, false, scratch);
-    const double lse = (m == -INFINITY) ? -INFINITY : m + log(s);
-    double t = 0.0;
-    for (uint32_t i = threadIdx.x; i < n; i += SEL_THREADS) {
-        const double e = exp(v[i] - lse);
-        v[i] = e;
-        t += e;
+    x = scratch[0][0]; y = scratch[0][1]; z = scratch[0][2];
+#pragma unroll
+    for (int q = 1; q < SEL_WARPS; q++) {
+        x = IS_MAX ? fmax(x, scratch[q][0]) : x + scratch[q][0];
+        y = IS_MAX ? fmax(y, scratch[q][1]) : y + scratch[q][1];
+        z = IS_MAX ? fmax(z, scratch[q][2]) : z + scratch[q][2];
     }
-    t = block_reduce(t, false, scratch);
-    for (uint32_t i = threadIdx.x; i < n; i += SEL_THREADS) v[i] = v[i] / t;
 }
 
 struct SelectArgs {
@@ -271,52 +378,67 @@ struct SelectArgs {
     int *err_flag;                // set to 1 if WeightedIndex::new would fail
 };
 
+// The three softmaxes of population.rs:325-382 (fitness a, genome size b, competition c) are
+// independent of each other, so each of their passes is made once for all three:
+//   m = max v; s = sum exp(v - m); lse = m + ln s; e_i = exp(v_i - lse); out_i = e_i / sum e
 __global__ void __launch_bounds__(SEL_THREADS) select_parents_kernel(const SelectArgs a)
 {
-    __shared__ double scratch[SEL_THREADS / 32];
-    __shared__ double chunk_sum[SEL_THREADS];
+    __shared__ double scratch[SEL_WARPS][3];
+    __shared__ double warp_excl[SEL_WARPS + 1];
     __shared__ int bad;
-    const uint32_t n = a.n_rows;
-    if (threadIdx.x == 0) bad = 0;
+    const uint32_t n = a.n_rows, tid = threadIdx.x;
+    const bool use_a = a.n_genes > 0, use_b = !a.no_control_genome_size;
+    double *va = a.tmp_a, *vb = a.tmp_b, *vc = a.cumulative;      // vc: scratch until the cumulative sums are written
+    if (tid == 0) bad = 0;
 
-    // a_i: softmax of log-fitness (skipped when there is no accessory genome, :293-296)
-    for (uint32_t i = threadIdx.x; i < n; i += SEL_THREADS) a.tmp_a[i] = (a.n_genes > 0) ? a.logfit[i] : 1.0;
-    __syncthreads();
-    if (a.n_genes > 0) softmax_inplace(a.tmp_a, n, scratch);
-    __syncthreads();
-
-    if (!a.no_control_genome_size) {
-        for (uint32_t i = threadIdx.x; i < n; i += SEL_THREADS)
-            a.tmp_b[i] = (double)(a.num_genes[i] - a.avg_gene_num) * a.log_penalty;     // :350,355
-        __syncthreads();
-        softmax_inplace(a.tmp_b, n, scratch);
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < n; i += SEL_THREADS) a.weights[i] = a.tmp_b[i] * a.tmp_a[i];  // :368
-    } else {
-        for (uint32_t i = threadIdx.x; i < n; i += SEL_THREADS) a.weights[i] = a.tmp_a[i];               // :371
+    // pass 0: the three arguments and their maxima
+    double ma = -INFINITY, mb = -INFINITY, mc = -INFINITY;
+    for (uint32_t i = tid; i < n; i += SEL_THREADS) {
+        const double xa = use_a ? a.logfit[i] : 0.0;
+        const double xb = use_b ? (double)(a.num_genes[i] - a.avg_gene_num) * a.log_penalty : 0.0;     // :350,355
+        const double xc = a.competition_strength * log(a.avgdist ? a.avgdist[i] : 1.0);                // :375
+        vb[i] = xb; vc[i] = xc;
+        ma = fmax(ma, xa); mb = fmax(mb, xb); mc = fmax(mc, xc);
     }
-    __syncthreads();
-
-    for (uint32_t i = threadIdx.x; i < n; i += SEL_THREADS)
-        a.tmp_b[i] = a.competition_strength * log(a.avgdist ? a.avgdist[i] : 1.0);       // :375
-    __syncthreads();
-    softmax_inplace(a.tmp_b, n, scratch);
-    __syncthreads();
-    double mx = -INFINITY;
-    for (uint32_t i = threadIdx.x; i < n; i += SEL_THREADS) {
-        const double w = a.weights[i] * a.tmp_b[i];                                      // :391
+    block_reduce3<true>(ma, mb, mc, scratch);
+    // pass 1: log-sum-exp
+    double sa = 0.0, sb = 0.0, sc = 0.0;
+    for (uint32_t i = tid; i < n; i += SEL_THREADS) {
+        if (use_a) sa += exp(a.logfit[i] - ma);
+        if (use_b) sb += exp(vb[i] - mb);
+        sc += exp(vc[i] - mc);
+    }
+    block_reduce3<false>(sa, sb, sc, scratch);
+    const double la = (ma == -INFINITY) ? -INFINITY : ma + log(sa);
+    const double lb = (mb == -INFINITY) ? -INFINITY : mb + log(sb);
+    const double lc = (mc == -INFINITY) ? -INFINITY : mc + log(sc);
+    // pass 2: exp(v - lse) and their totals
+    double ta = 0.0, tb = 0.0, tc = 0.0;
+    for (uint32_t i = tid; i < n; i += SEL_THREADS) {
+        const double ea = use_a ? exp(a.logfit[i] - la) : 1.0;
+        const double eb = use_b ? exp(vb[i] - lb) : 1.0;
+        const double ec = exp(vc[i] - lc);
+        va[i] = ea; vb[i] = eb; vc[i] = ec;
+        ta += ea; tb += eb; tc += ec;
+    }
+    block_reduce3<false>(ta, tb, tc, scratch);
+    // pass 3: weights (population.rs:365-393) and their maximum
+    double mx = -INFINITY, dummy0 = -INFINITY, dummy1 = -INFINITY;
+    for (uint32_t i = tid; i < n; i += SEL_THREADS) {
+        const double wa = use_a ? va[i] / ta : 1.0;                 // a_i = 1 without an accessory genome (:293-296)
+        const double w0 = use_b ? (vb[i] / tb) * wa : wa;           // :368 / :371
+        const double w = w0 * (vc[i] / tc);                         // :391
         a.weights[i] = w;
         mx = fmax(mx, w);
     }
-    mx = block_reduce(mx, true, scratch);
+    block_reduce3<true>(mx, dummy0, dummy1, scratch);
     if (mx == 0.0)                                                                       // :435-437
-        for (uint32_t i = threadIdx.x; i < n; i += SEL_THREADS) a.weights[i] = 1.0;
+        for (uint32_t i = tid; i < n; i += SEL_THREADS) a.weights[i] = 1.0;
     __syncthreads();
 
-    // WeightedIndex::new: cumulative sums; contiguous chunk per thread, then a
-    // scan of the chunk totals.
+    // WeightedIndex::new: cumulative sums; contiguous chunk per thread, then a scan of the chunk totals
     const uint32_t per = (n + SEL_THREADS - 1) / SEL_THREADS;
-    const uint32_t lo = threadIdx.x * per, hi = min(n, lo + per);
+    const uint32_t lo = min(n, tid * per), hi = min(n, lo + per);
     double s = 0.0;
     bool mybad = false;
     for (uint32_t i = lo; i < hi; i++) {
@@ -325,53 +447,36 @@ __global__ void __launch_bounds__(SEL_THREADS) select_parents_kernel(const Selec
         s += w;
     }
     if (mybad) bad = 1;
-    // block-wide exclusive scan of the 1024 chunk totals (warp shuffles, fixed order)
-    {
-        const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        double v = s;
+    const uint32_t lane = tid & 31, warp = tid >> 5;
+    double v = s;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const double t = __shfl_up_sync(0xffffffffu, v, o);
-            if ((int)lane >= o) v += t;
-        }
-        if (lane == 31) scratch[warp] = v;
-        __syncthreads();
-        if (warp == 0) {
-            const double wt = scratch[lane];
-            double wv = wt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const double t = __shfl_up_sync(0xffffffffu, wv, o);
-                if ((int)lane >= o) wv += t;
-            }
-            chunk_sum[lane] = wv - wt;            // exclusive offset of each warp
-            if (lane == 31) {
-                chunk_sum[32] = wv;               // grand total
-                if (!(wv > 0.0) || isinf(wv)) bad = 1;
-            }
-        }
-        __syncthreads();
-        const double excl = chunk_sum[warp] + (v - s);
-        const double tot = chunk_sum[32];
-        __syncthreads();
-        chunk_sum[threadIdx.x] = excl;
-        if (threadIdx.x == 0) scratch[0] = tot;
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, v, o);
+        if ((int)lane >= o) v += t;
+    }
+    if (lane == 31) scratch[warp][0] = v;
+    __syncthreads();
+    if (tid == 0) {
+        double run = 0.0;
+        for (int q = 0; q < SEL_WARPS; q++) { warp_excl[q] = run; run += scratch[q][0]; }
+        warp_excl[SEL_WARPS] = run;
+        if (!(run > 0.0) || isinf(run)) bad = 1;
     }
     __syncthreads();
-    const double total = scratch[0];
-    double run = chunk_sum[threadIdx.x];
+    const double total = warp_excl[SEL_WARPS];
+    double run = warp_excl[warp] + (v - s);
     for (uint32_t i = lo; i < hi; i++) {
         run += a.weights[i];
         a.cumulative[i] = run;
     }
     __syncthreads();
     if (bad) {
-        if (threadIdx.x == 0) *a.err_flag = 1;
-        for (uint32_t i = threadIdx.x; i < n; i += SEL_THREADS) a.parents[i] = i;
+        if (tid == 0) *a.err_flag = 1;
+        for (uint32_t i = tid; i < n; i += SEL_THREADS) a.parents[i] = i;
         return;
     }
     // N draws: u ~ U[0,total), index = #cumulative[0..n-1) <= u
-    for (uint32_t i = threadIdx.x; i < n; i += SEL_THREADS) {
+    for (uint32_t i = tid; i < n; i += SEL_THREADS) {
         const uint4 r = philox4x32_10(make_ctr(i, 0u, a.gen, STREAM_PARENTS), a.key);
         const uint64_t bits = (((uint64_t)r.x << 32) | r.y) >> 11;
         const double u = (double)bits * 0x1.0p-53 * total;

@@ -173,6 +173,34 @@ def test_fitness_and_average_distance_bit_exact():
     np.testing.assert_allclose(w / w.sum(), ow / ow.sum(), rtol=1e-12)
 
 
+@pytest.mark.parametrize("N,G,dens", [(200, 4000, 0.25), (131, 1030, 0.5), (65, 31, 0.3), (300, 33, 0.9), (2, 5, 0.5)])
+def test_competition_and_fitness_kernels_over_shapes(N, G, dens):
+    """The intersection counts run as an integer MMA over 64x64 pair tiles and 32-word chunks
+    (select.cuh K2a), the distances and the fitness sum as per-row sequential f64 chains fed from
+    shared memory in rounds of 256 / 1024 values: shapes with several tiles, ragged last tiles,
+    a ragged last word and fewer rows than one tile must all stay bit-exact."""
+    rng = np.random.default_rng(N + G)
+    core, acc = random_state(rng, N, 20, G, dens)
+    sel = rng.normal(0, 0.2, G).clip(-0.95, None)
+    p = pb.Params(pop_size=N, core_size=20, pan_genes=G + 7, core_genes=7, competition_strength=1.0)
+    opan = ob.Population(acc, False, 7)
+    with make(p) as sim:
+        sim.upload(core, acc)
+        # neutral fast path first (all coefficients 0: popcounts only, log-fitness +0.0) ...
+        sim.sample_indices(0, np.ones(N))
+        _, ng0, lf0 = sim.weights()
+        assert (ng0 == acc.sum(1)).all() and (lf0 == 0.0).all() and not np.signbit(lf0).any()
+        # ... then the sequential chain
+        sim.set_selection(sel)
+        oavg = opan.average_distance()
+        assert (sim.average_distance() == oavg).all()
+        sim.sample_indices(1)
+        w, ng, lf = sim.weights()
+    ow, ong, olf = opan.selection_weights(pb.derive(p).avg_gene_num, oavg, sel, False, p.genome_size_penalty, 1.0)
+    assert (ng == ong).all() and (lf == olf).all()
+    np.testing.assert_allclose(w / w.sum(), ow / ow.sum(), rtol=1e-11)
+
+
 def test_average_distance_identical_population_is_min_positive():
     p = pb.Params(pop_size=5, core_size=16, pan_genes=40, core_genes=8, competition_strength=1.0)
     with make(p) as sim:
