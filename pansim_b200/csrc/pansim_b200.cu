@@ -102,7 +102,8 @@ struct EventPool {
     }
 };
 
-enum TimeGroup { TG_SELECT = 0, TG_ACC, TG_CORE, TG_CORE_HR, TG_PAIR_CORE, TG_PAIR_ACC, TG_COUNT };
+enum TimeGroup { TG_SELECT = 0, TG_ACC, TG_CORE, TG_CORE_HR, TG_PAIR_CORE, TG_PAIR_ACC,
+                 TG_D_INTER, TG_D_AVG, TG_D_SEL, TG_D_FLIP, TG_D_GAIN, TG_D_HGT, TG_COUNT };   // TG_D_*: PANSIM_FINE_TIMING=1 (debug)
 
 }  // namespace
 
@@ -204,6 +205,7 @@ struct pansim_ctx {
 
     // timing
     bool timing_enabled = true;
+    bool fine_timing = false;            // PANSIM_FINE_TIMING=1: per-kernel spans of the selection chain, printed by pansim_get_timing
     EventPool pool;
     struct Span { cudaEvent_t a, b; int group; };
     std::vector<Span> spans;
@@ -263,6 +265,19 @@ struct ScopedSpan {
             cudaEventRecord(b, st);
             c->spans.push_back({a, b, group});
         }
+    }
+};
+
+// debug-only sub-span (PANSIM_FINE_TIMING=1)
+struct FineSpan {
+    pansim_ctx *c; int group; cudaEvent_t a = nullptr;
+    FineSpan(pansim_ctx *ctx, int g) : c(ctx), group(g)
+    {
+        if (c->fine_timing && c->timing_enabled) { a = c->pool.get(); cudaEventRecord(a, c->stream); }
+    }
+    ~FineSpan()
+    {
+        if (a) { cudaEvent_t b = c->pool.get(); cudaEventRecord(b, c->stream); c->spans.push_back({a, b, group}); }
     }
 };
 
@@ -330,14 +345,14 @@ int launch_fitness(pansim_ctx *c, cudaStream_t st = nullptr)
     if (!st) st = c->stream;
     const uint32_t *acc = c->acc[c->acc_cur];
     if (c->neutral)          // every ln(1 + s_j) is +0.0: the sum is +0.0, only the row popcounts are needed
-        fitness_kernel<true><<<div_up64(c->N, FIT_WARPS), FIT_WARPS * 32, 0, st>>>(acc, c->N, c->G, c->acc_stride_words,
-                                                                              c->d_lw, c->d_logfit, c->d_num_genes);
+        fitness_count_kernel<<<div_up64(c->N, FIT_WARPS), FIT_WARPS * 32, 0, st>>>(acc, c->N, c->G, c->acc_stride_words,
+                                                                              c->d_logfit, c->d_num_genes);
     else if (c->fitness_blocked)
         fitness_blocked_kernel<<<div_up64(c->N, FIT_WARPS), FIT_WARPS * 32, 0, st>>>(acc, c->N, c->G, c->acc_stride_words,
                                                                                 c->d_lw, c->d_logfit, c->d_num_genes);
     else
-        fitness_kernel<false><<<div_up64(c->N, FIT_WARPS), FIT_WARPS * 32, 0, st>>>(acc, c->N, c->G, c->acc_stride_words,
-                                                                               c->d_lw, c->d_logfit, c->d_num_genes);
+        fitness_kernel<<<div_up64(c->N, FIT_ROWS), FIT_ROWS * 64, 0, st>>>(acc, c->N, c->G, c->acc_stride_words,
+                                                                      c->d_lw, c->d_logfit, c->d_num_genes);
     LAUNCH_CHECK(c);
     c->fitness_valid = true;
     return 0;
@@ -348,6 +363,7 @@ int launch_competition(pansim_ctx *c)
     if (c->N < 2) FAIL(c, PANSIM_ERR_INVALID, "average_distance needs pop_size >= 2");
     if (!c->d_inter) CU(c, cudaMalloc(&c->d_inter, (size_t)c->N * c->N * sizeof(uint32_t)));
     // the fitness sum (also the row popcounts the distances need) runs beside the intersection counts
+    FineSpan *fs = new FineSpan(c, TG_D_INTER);
     const bool fork = !c->fitness_valid;
     if (fork) {
         CU(c, cudaEventRecord(c->ev_fork, c->stream));
@@ -366,6 +382,8 @@ int launch_competition(pansim_ctx *c)
     }
     LAUNCH_CHECK(c);
     if (fork) CU(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    delete fs;
+    FineSpan fs2(c, TG_D_AVG);
     avg_distance_kernel<<<div_up64(c->N, AVG_WARPS), AVG_WARPS * 32, 0, c->stream>>>(c->d_inter, c->d_num_genes, c->N,
                                                                     c->cfg.core_genes, c->d_avgdist);
     LAUNCH_CHECK(c);
@@ -394,7 +412,13 @@ int launch_select(pansim_ctx *c, uint32_t gen, bool use_avgdist)
     a.cumulative = c->d_cum;
     a.parents = c->d_parents;
     a.err_flag = c->d_err;
-    select_parents_kernel<<<1, SEL_THREADS, 0, c->stream>>>(a);
+    {
+        FineSpan fs(c, TG_D_SEL);
+        if (c->N <= SEL_SMALL_MAX)
+            select_parents_small_kernel<<<1, SEL_THREADS, 0, c->stream>>>(a);
+        else
+            select_parents_kernel<<<1, SEL_THREADS, 0, c->stream>>>(a);
+    }
     LAUNCH_CHECK(c);
     return 0;
 }
@@ -426,20 +450,29 @@ int launch_acc_step(pansim_ctx *c, uint32_t gen)
     AccArgs a;
     fill_acc_args(c, a, gen);
     const uint32_t rows_per_cta = 8;
-    if (c->dump_enabled)
-        acc_gather_flip_kernel<true><<<div_up64(c->N, rows_per_cta), 256, 0, c->stream>>>(a);
-    else
-        acc_gather_flip_kernel<false><<<div_up64(c->N, rows_per_cta), 256, 0, c->stream>>>(a);
+    {
+        FineSpan fs(c, TG_D_FLIP);
+        if (c->dump_enabled)
+            acc_gather_flip_kernel<true><<<div_up64(c->N, rows_per_cta), 256, 0, c->stream>>>(a);
+        else
+            acc_gather_flip_kernel<false><<<div_up64(c->N, rows_per_cta), 256, 0, c->stream>>>(a);
+    }
     LAUNCH_CHECK(c);
     const bool hgt = (a.hgt_scale0 > 0.0 || a.hgt_scale1 > 0.0);
     if (hgt) {
-        acc_gain_threshold_kernel<<<c->acc_words, GAIN_WARPS * 32, 0, c->stream>>>(a);
+        {
+            FineSpan fs(c, TG_D_GAIN);
+            acc_gain_threshold_kernel<<<c->acc_words, GAIN_WARPS * 32, 0, c->stream>>>(a);
+        }
         LAUNCH_CHECK(c);
         const uint64_t total = (uint64_t)c->N * c->acc_stride_words;
-        if (c->dump_enabled)
-            acc_hgt_apply_kernel<true><<<div_up64(total, 256), 256, 0, c->stream>>>(a);
-        else
-            acc_hgt_apply_kernel<false><<<div_up64(total, 256), 256, 0, c->stream>>>(a);
+        {
+            FineSpan fs(c, TG_D_HGT);
+            if (c->dump_enabled)
+                acc_hgt_apply_kernel<true><<<div_up64(total, 256), 256, 0, c->stream>>>(a);
+            else
+                acc_hgt_apply_kernel<false><<<div_up64(total, 256), 256, 0, c->stream>>>(a);
+        }
         LAUNCH_CHECK(c);
     } else if (c->dump_enabled) {
         CU(c, cudaMemsetAsync(c->d_dump_gain, 0, (size_t)c->N * c->acc_stride_words * 4, c->stream));
@@ -804,6 +837,7 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
         c->fitness_blocked = (uint64_t)c->N * c->G > (1ull << 25);
         if (const char *e = getenv("PANSIM_FITNESS_BLOCKED")) c->fitness_blocked = atoi(e) != 0;
         if (const char *e = getenv("PANSIM_INTER_POPC")) c->inter_popc = atoi(e) != 0;
+        if (const char *e = getenv("PANSIM_FINE_TIMING")) c->fine_timing = atoi(e) != 0;
         if (c->tab_hr.nsub && core_bytes) {
             // recombination slots: per (region, row) item room for mean + 6 sigma changed cells (a multiple of 32,
             // 32 when the mean is small); the rare item that needs more spills to the overflow list
@@ -924,6 +958,9 @@ int pansim_get_timing(pansim_ctx *c, pansim_timing *o)
         CU(c, cudaEventElapsedTime(&ms, s.a, s.b));
         g[s.group] += ms;
     }
+    if (c->fine_timing)
+        fprintf(stderr, "[pansim fine timing, ms over the batch] inter(+fitness join) %.4f avg %.4f select %.4f flip %.4f gain %.4f hgt %.4f | groups: select %.4f acc %.4f core %.4f\n",
+                g[TG_D_INTER], g[TG_D_AVG], g[TG_D_SEL], g[TG_D_FLIP], g[TG_D_GAIN], g[TG_D_HGT], g[TG_SELECT], g[TG_ACC], g[TG_CORE]);
     o->select_ms = g[TG_SELECT]; o->acc_step_ms = g[TG_ACC]; o->core_step_ms = g[TG_CORE];
     o->core_hr_ms = g[TG_CORE_HR];
     o->pair_core_ms = g[TG_PAIR_CORE]; o->pair_acc_ms = g[TG_PAIR_ACC];

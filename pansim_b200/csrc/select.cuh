@@ -17,84 +17,124 @@ namespace pansim {
 // sum bit for bit (population.rs:303-317). A present gene with lw_j = -inf
 // (s_j = -1) sets l_i := 0.0 (population.rs:312-318).
 // ---------------------------------------------------------------------------
-constexpr int FIT_WARPS = 4;
+constexpr int FIT_WARPS = 4;                      // rows per CTA of the blocked / count-only kernels
+constexpr int FIT_ROWS = 2;                       // rows per CTA of the sequential kernel (two warps per row)
 constexpr int FIT_CHUNK_WORDS = 32;               // 1024 genes per compaction round
 constexpr int FIT_BATCH = 8;                      // chain elements loaded ahead of the additions
 
-// COUNT_ONLY: every selection coefficient is 0 (neutral run: lw_j = ln(1) = +0.0 for all j), the sum
-// is +0.0 whatever the genome; only the row popcounts are needed.
-template <bool COUNT_ONLY>
-__global__ void __launch_bounds__(FIT_WARPS * 32) fitness_kernel(const uint32_t *acc, uint32_t n_rows,
-                                                                 uint32_t n_genes, uint32_t stride_words,
-                                                                 const double *lw, double *logfit,
-                                                                 int32_t *num_genes)
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads)
 {
-    // Terms of absent genes are ln(1 + s*0) = +0.0: adding them never changes the
-    // running sum, so only present genes are added -- in increasing column order,
-    // by a single sequential f64 chain per row (bit-exact vs population.rs:303-317).
-    // The warp first compacts the present genes' lw values into shared memory, padded with +0.0
-    // to whole batches (the running sum starts at +0.0 and can never become -0.0, so x + (+0.0)
-    // = x); the chain then runs one batch of shared-memory loads ahead of its additions, so it
-    // advances at the latency of a dependent DADD (8.2 cycles on B200).
-    __shared__ double list[COUNT_ONLY ? 1 : FIT_WARPS][COUNT_ONLY ? 1 : FIT_CHUNK_WORDS * 32 + 2 * FIT_BATCH];
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t threads)
+{
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// every selection coefficient is 0 (neutral run: lw_j = ln(1) = +0.0 for all j): the sum is +0.0
+// whatever the genome; only the row popcounts are needed
+__global__ void __launch_bounds__(FIT_WARPS * 32) fitness_count_kernel(const uint32_t *acc, uint32_t n_rows,
+                                                                       uint32_t n_genes, uint32_t stride_words,
+                                                                       double *logfit, int32_t *num_genes)
+{
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t row = blockIdx.x * FIT_WARPS + warp;
     if (row >= n_rows) return;
     const uint32_t *r = acc + (uint64_t)row * stride_words;
     const uint32_t n_words = (n_genes + 31u) / 32u;
-    if (COUNT_ONLY) {
-        int32_t cnt = 0;
-        for (uint32_t w = lane; w < n_words; w += 32) cnt += __popc(r[w]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        if (lane == 0) { logfit[row] = 0.0; num_genes[row] = cnt; }
-        return;
-    }
-    double *mine = list[COUNT_ONLY ? 0 : warp];
-    double sum = 0.0;
-    bool neg_inf = false;
     int32_t cnt = 0;
-    for (uint32_t w0 = 0; w0 < n_words; w0 += FIT_CHUNK_WORDS) {
-        const uint32_t w = w0 + lane;
-        uint32_t bits = (w < n_words) ? r[w] : 0u;
-        const uint32_t c = __popc(bits);
-        uint32_t incl = c;
+    for (uint32_t w = lane; w < n_words; w += 32) cnt += __popc(r[w]);
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-            if ((int)lane >= o) incl += v;
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) { logfit[row] = 0.0; num_genes[row] = cnt; }
+}
+
+// Terms of absent genes are ln(1 + s*0) = +0.0: adding them never changes the running sum, so
+// only present genes are added -- in increasing column order, by a single sequential f64 chain
+// per row (bit-exact vs population.rs:303-317). Two warps per row: the PRODUCER compacts the lw
+// values of the present genes of each 1024-gene chunk into one of two shared-memory lists (padded
+// with +0.0 to whole batches: the running sum starts at +0.0 and can never become -0.0, so
+// x + (+0.0) = x); the CONSUMER runs the chain, its loads one batch ahead of the additions, so it
+// advances at the latency of a dependent DADD (8.2 cycles on B200) while the producer prepares
+// the next chunk. Full/empty hand-over through named barriers.
+__global__ void __launch_bounds__(FIT_ROWS * 64) fitness_kernel(const uint32_t *acc, uint32_t n_rows,
+                                                                uint32_t n_genes, uint32_t stride_words,
+                                                                const double *lw, double *logfit,
+                                                                int32_t *num_genes)
+{
+    constexpr int LIST = FIT_CHUNK_WORDS * 32 + 2 * FIT_BATCH;
+    __shared__ double list[FIT_ROWS][2][LIST];
+    __shared__ uint32_t tot_s[FIT_ROWS][2];
+    __shared__ int32_t fin_s[FIT_ROWS][2];           // gene count, -inf seen
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t r_in_cta = warp >> 1;
+    const bool producer = (warp & 1u) != 0u;
+    const uint32_t row = blockIdx.x * FIT_ROWS + r_in_cta;
+    if (row >= n_rows) return;                        // both warps of the row leave together
+    const uint32_t n_words = (n_genes + 31u) / 32u;
+    const uint32_t n_chunks = (n_words + FIT_CHUNK_WORDS - 1) / FIT_CHUNK_WORDS;
+    const uint32_t bar_full = 1u + r_in_cta * 5u, bar_empty = 3u + r_in_cta * 5u, bar_done = 5u + r_in_cta * 5u;
+    if (producer) {
+        const uint32_t *r = acc + (uint64_t)row * stride_words;
+        bool neg_inf = false;
+        int32_t cnt = 0;
+        for (uint32_t ch = 0; ch < n_chunks; ch++) {
+            const uint32_t b = ch & 1u;
+            if (ch >= 2) named_bar_sync(bar_empty + b, 64);          // the consumer is done with this list
+            double *mine = list[r_in_cta][b];
+            const uint32_t w = ch * FIT_CHUNK_WORDS + lane;
+            uint32_t bits = (w < n_words) ? r[w] : 0u;
+            const uint32_t c = __popc(bits);
+            uint32_t incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)lane >= o) incl += v;
+            }
+            uint32_t off = incl - c;
+            const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+            cnt += (int32_t)tot;
+            if (lane < 2 * FIT_BATCH) mine[tot + lane] = 0.0;        // padding behind the last value
+            if (lane == 0) tot_s[r_in_cta][b] = tot;
+            while (bits) {
+                const uint32_t bb = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const double v = lw[w * 32u + bb];
+                neg_inf |= (v == -INFINITY);
+                mine[off++] = v;
+            }
+            named_bar_arrive(bar_full + b, 64);
         }
-        uint32_t off = incl - c;
-        const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
-        cnt += (int32_t)tot;
-        if (lane < 2 * FIT_BATCH) mine[tot + lane] = 0.0;          // padding behind the last value
-        while (bits) {
-            const uint32_t b = __ffs(bits) - 1;
-            bits &= bits - 1;
-            const double v = lw[w * 32u + b];
-            neg_inf |= (v == -INFINITY);
-            mine[off++] = v;
+        neg_inf = __any_sync(0xffffffffu, neg_inf);
+        if (lane == 0) { fin_s[r_in_cta][0] = cnt; fin_s[r_in_cta][1] = neg_inf ? 1 : 0; }
+        named_bar_arrive(bar_done, 64);
+    } else {
+        double sum = 0.0;
+        for (uint32_t ch = 0; ch < n_chunks; ch++) {
+            const uint32_t b = ch & 1u;
+            named_bar_sync(bar_full + b, 64);
+            const double *mine = list[r_in_cta][b];
+            const uint32_t tot = tot_s[r_in_cta][b];
+            // every lane runs the same chain
+            double nx[FIT_BATCH];
+#pragma unroll
+            for (int q = 0; q < FIT_BATCH; q++) nx[q] = mine[q];
+            for (uint32_t t = 0; t < tot; t += FIT_BATCH) {
+                double cu[FIT_BATCH];
+#pragma unroll
+                for (int q = 0; q < FIT_BATCH; q++) cu[q] = nx[q];
+#pragma unroll
+                for (int q = 0; q < FIT_BATCH; q++) nx[q] = mine[t + FIT_BATCH + q];
+#pragma unroll
+                for (int q = 0; q < FIT_BATCH; q++) sum += cu[q];
+            }
+            if (ch + 2 < n_chunks) named_bar_arrive(bar_empty + b, 64);
         }
-        __syncwarp();
-        // every lane runs the same chain
-        double nx[FIT_BATCH];
-#pragma unroll
-        for (int q = 0; q < FIT_BATCH; q++) nx[q] = mine[q];
-        for (uint32_t t = 0; t < tot; t += FIT_BATCH) {
-            double cu[FIT_BATCH];
-#pragma unroll
-            for (int q = 0; q < FIT_BATCH; q++) cu[q] = nx[q];
-#pragma unroll
-            for (int q = 0; q < FIT_BATCH; q++) nx[q] = mine[t + FIT_BATCH + q];
-#pragma unroll
-            for (int q = 0; q < FIT_BATCH; q++) sum += cu[q];
+        named_bar_sync(bar_done, 64);
+        if (lane == 0) {
+            logfit[row] = (n_genes > 0) ? (fin_s[r_in_cta][1] ? 0.0 : sum) : 0.0;
+            num_genes[row] = fin_s[r_in_cta][0];
         }
-        __syncwarp();
-    }
-    neg_inf = __any_sync(0xffffffffu, neg_inf);
-    if (lane == 0) {
-        logfit[row] = (n_genes > 0) ? (neg_inf ? 0.0 : sum) : 0.0;
-        num_genes[row] = cnt;
     }
 }
 
@@ -291,16 +331,20 @@ __global__ void __launch_bounds__(AVG_WARPS * 32) avg_distance_kernel(const uint
     const uint32_t *irow = inter + (uint64_t)i * n_rows;
     double sum = 0.0;
     for (uint32_t j0 = 0; j0 < n_rows; j0 += AVG_RING) {
+        // all loads of the round first (one latency), then the divisions
+        uint32_t in[AVG_RING / 32], kj[AVG_RING / 32];
+#pragma unroll
+        for (int q = 0; q < AVG_RING / 32; q++) {
+            const uint32_t j = min(j0 + q * 32 + lane, n_rows - 1u);
+            in[q] = irow[j];
+            kj[q] = (uint32_t)num_genes[j];
+        }
 #pragma unroll
         for (int q = 0; q < AVG_RING / 32; q++) {
             const uint32_t j = j0 + q * 32 + lane;
-            double d = 0.0;
-            if (j < n_rows && j != i) {
-                const uint32_t in = irow[j];
-                const uint32_t un = ki + (uint32_t)num_genes[j] - in;
-                d = 1.0 - (((double)in + 0.0 + cg) / ((double)un + 0.0 + cg));   // :144-145
-            }
-            mine[q * 32 + lane] = d;
+            const uint32_t un = ki + kj[q] - in[q];
+            const double d = 1.0 - (((double)in[q] + 0.0 + cg) / ((double)un + 0.0 + cg));   // :144-145
+            mine[q * 32 + lane] = (j < n_rows && j != i) ? d : 0.0;
         }
         __syncwarp();
         const uint32_t tot = min((uint32_t)AVG_RING, n_rows - j0);
@@ -377,6 +421,126 @@ struct SelectArgs {
     uint32_t *parents;            // [N] out
     int *err_flag;                // set to 1 if WeightedIndex::new would fail
 };
+
+// N <= 1024: the same computation with every per-individual value in registers (4 per thread) and
+// the cumulative table in shared memory -- the kernel is a chain of dependent passes, so keeping
+// them out of global memory is what makes it short.
+constexpr int SEL_PER = 4;
+constexpr uint32_t SEL_SMALL_MAX = SEL_THREADS * SEL_PER;
+
+__global__ void __launch_bounds__(SEL_THREADS) select_parents_small_kernel(const SelectArgs a)
+{
+    __shared__ double scratch[SEL_WARPS][3];
+    __shared__ double warp_excl[SEL_WARPS + 1];
+    __shared__ double w_s[SEL_SMALL_MAX];
+    __shared__ double cum_s[SEL_SMALL_MAX];
+    __shared__ int bad;
+    const uint32_t n = a.n_rows, tid = threadIdx.x;
+    const bool use_a = a.n_genes > 0, use_b = !a.no_control_genome_size;
+    if (tid == 0) bad = 0;
+    double xa[SEL_PER], xb[SEL_PER], xc[SEL_PER];
+    double ma = -INFINITY, mb = -INFINITY, mc = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < SEL_PER; k++) {
+        const uint32_t i = tid + k * SEL_THREADS;
+        const bool ok = i < n;
+        const uint32_t ii = ok ? i : 0u;
+        const double lf = a.logfit[ii];
+        const int32_t ng = a.num_genes[ii];
+        const double ad = a.avgdist ? a.avgdist[ii] : 1.0;
+        xa[k] = ok ? (use_a ? lf : 0.0) : -INFINITY;
+        xb[k] = ok ? (use_b ? (double)(ng - a.avg_gene_num) * a.log_penalty : 0.0) : -INFINITY;     // :350,355
+        xc[k] = ok ? a.competition_strength * log(ad) : -INFINITY;                                  // :375
+        ma = fmax(ma, xa[k]); mb = fmax(mb, xb[k]); mc = fmax(mc, xc[k]);
+    }
+    block_reduce3<true>(ma, mb, mc, scratch);
+    double sa = 0.0, sb = 0.0, sc = 0.0;
+#pragma unroll
+    for (int k = 0; k < SEL_PER; k++) {        // entries beyond n are -inf: exp(-inf - m) = 0
+        sa += exp(xa[k] - ma); sb += exp(xb[k] - mb); sc += exp(xc[k] - mc);
+    }
+    block_reduce3<false>(sa, sb, sc, scratch);
+    const double la = (ma == -INFINITY) ? -INFINITY : ma + log(sa);
+    const double lb = (mb == -INFINITY) ? -INFINITY : mb + log(sb);
+    const double lc = (mc == -INFINITY) ? -INFINITY : mc + log(sc);
+    double ta = 0.0, tb = 0.0, tc = 0.0;
+#pragma unroll
+    for (int k = 0; k < SEL_PER; k++) {
+        xa[k] = exp(xa[k] - la); xb[k] = exp(xb[k] - lb); xc[k] = exp(xc[k] - lc);
+        ta += xa[k]; tb += xb[k]; tc += xc[k];
+    }
+    block_reduce3<false>(ta, tb, tc, scratch);
+    double w[SEL_PER];
+    double mx = -INFINITY, dummy0 = -INFINITY, dummy1 = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < SEL_PER; k++) {
+        const double wa = use_a ? xa[k] / ta : 1.0;                 // a_i = 1 without an accessory genome (:293-296)
+        const double w0 = use_b ? (xb[k] / tb) * wa : wa;           // :368 / :371
+        w[k] = w0 * (xc[k] / tc);                                   // :391
+        if (tid + k * SEL_THREADS < n) mx = fmax(mx, w[k]);
+    }
+    block_reduce3<true>(mx, dummy0, dummy1, scratch);
+#pragma unroll
+    for (int k = 0; k < SEL_PER; k++) {
+        const uint32_t i = tid + k * SEL_THREADS;
+        if (mx == 0.0) w[k] = 1.0;                                  // :435-437
+        if (i < n) { w_s[i] = w[k]; a.weights[i] = w[k]; }
+    }
+    __syncthreads();
+    // WeightedIndex::new: cumulative sums over contiguous chunks of 4, then a scan of the chunk totals
+    const uint32_t lo = min(n, tid * SEL_PER), hi = min(n, lo + SEL_PER);
+    double s = 0.0;
+    bool mybad = false;
+    for (uint32_t i = lo; i < hi; i++) {
+        const double wi = w_s[i];
+        if (!(wi >= 0.0)) mybad = true;
+        s += wi;
+    }
+    if (mybad) bad = 1;
+    const uint32_t lane = tid & 31, warp = tid >> 5;
+    double v = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, v, o);
+        if ((int)lane >= o) v += t;
+    }
+    if (lane == 31) scratch[warp][0] = v;
+    __syncthreads();
+    if (tid == 0) {
+        double run = 0.0;
+        for (int q = 0; q < SEL_WARPS; q++) { warp_excl[q] = run; run += scratch[q][0]; }
+        warp_excl[SEL_WARPS] = run;
+        if (!(run > 0.0) || isinf(run)) bad = 1;
+    }
+    __syncthreads();
+    const double total = warp_excl[SEL_WARPS];
+    double run = warp_excl[warp] + (v - s);
+    for (uint32_t i = lo; i < hi; i++) {
+        run += w_s[i];
+        cum_s[i] = run;
+        a.cumulative[i] = run;
+    }
+    __syncthreads();
+    if (bad) {
+        if (tid == 0) *a.err_flag = 1;
+        for (uint32_t i = tid; i < n; i += SEL_THREADS) a.parents[i] = i;
+        return;
+    }
+    // N draws: u ~ U[0,total), index = #cumulative[0..n-1) <= u
+#pragma unroll
+    for (int k = 0; k < SEL_PER; k++) {
+        const uint32_t i = tid + k * SEL_THREADS;
+        const uint4 r = philox4x32_10(make_ctr(i, 0u, a.gen, STREAM_PARENTS), a.key);
+        const uint64_t bits = (((uint64_t)r.x << 32) | r.y) >> 11;
+        const double u = (double)bits * 0x1.0p-53 * total;
+        uint32_t l = 0, h = n - 1;
+        while (l < h) {
+            const uint32_t mid = l + ((h - l) >> 1);
+            if (cum_s[mid] <= u) l = mid + 1; else h = mid;
+        }
+        if (i < n) a.parents[i] = l;
+    }
+}
 
 // The three softmaxes of population.rs:325-382 (fitness a, genome size b, competition c) are
 // independent of each other, so each of their passes is made once for all three:

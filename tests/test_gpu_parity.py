@@ -173,12 +173,14 @@ def test_fitness_and_average_distance_bit_exact():
     np.testing.assert_allclose(w / w.sum(), ow / ow.sum(), rtol=1e-12)
 
 
-@pytest.mark.parametrize("N,G,dens", [(200, 4000, 0.25), (131, 1030, 0.5), (65, 31, 0.3), (300, 33, 0.9), (2, 5, 0.5)])
+@pytest.mark.parametrize("N,G,dens", [(200, 4000, 0.25), (131, 1030, 0.5), (65, 31, 0.3), (300, 33, 0.9), (2, 5, 0.5),
+                                      (1100, 70, 0.5), (1024, 2100, 0.75)])
 def test_competition_and_fitness_kernels_over_shapes(N, G, dens):
     """The intersection counts run as an integer MMA over 64x64 pair tiles and 32-word chunks
     (select.cuh K2a), the distances and the fitness sum as per-row sequential f64 chains fed from
     shared memory in rounds of 256 / 1024 values: shapes with several tiles, ragged last tiles,
-    a ragged last word and fewer rows than one tile must all stay bit-exact."""
+    a ragged last word and fewer rows than one tile must all stay bit-exact. Parent selection has a
+    register/shared-memory kernel up to 1024 individuals and a global-memory one above."""
     rng = np.random.default_rng(N + G)
     core, acc = random_state(rng, N, 20, G, dens)
     sel = rng.normal(0, 0.2, G).clip(-0.95, None)
