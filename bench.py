@@ -35,9 +35,11 @@ sys.path.insert(0, ROOT)
 CFG2 = dict(pop_size=1000, core_size=1_200_000, pan_genes=6000, core_genes=2000, n_gen=100,
             max_distances=100_000, prop_positive=0.1, competition_strength=0.5, seed=0)
 PEAK_FALLBACK_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
-# dram__bytes_read.sum + dram__bytes_write.sum of core_mut_kernel from the committed
-# ncu --set full capture (profiles/), per launch at this workload; None until captured
-NCU_CORE_STEP_DRAM_BYTES = None
+# dram__bytes_read.sum + dram__bytes_write.sum of core_mut_kernel (a launch with recombination
+# events pending) from the committed ncu --set full capture (profiles/r01_core_mut_ncu_summary.txt),
+# per launch at this workload. ncu counts 54 MB of reads against 300 MB of algorithmic reads for
+# this kernel (bulk-copy loads); the write side (249 MB) matches.
+NCU_CORE_STEP_DRAM_BYTES = 303.1e6
 
 
 def selection_coefficients(rng, n, prop_positive, pos_lambda=10.0, neg_lambda=10.0):
@@ -252,9 +254,9 @@ def main():
     wall_ms = 1e3 * (time.perf_counter() - t0)
     gen += K
     dev_ms = max_over_ranks(float(tm.total_ms))
-    core_ms = float(tm.core_step_ms) / K            # gather+SNP kernel and the recombination pass
-    hr_ms = float(tm.core_hr_ms) / K                # recombination pass alone (collect + apply)
-    mut_ms = core_ms - hr_ms                        # core_mut_kernel: the kernel that moves the state
+    core_ms = float(tm.core_step_ms) / K            # core_mut_kernel (+ stand-alone recombination launches, if any)
+    hr_ms = float(tm.core_hr_ms) / K                # stand-alone recombination launches: 0 in the deferred mode
+    mut_ms = core_ms - hr_ms                        # core_mut_kernel: gather + deferred recombination + SNPs
     launches = int(tm.launches)
 
     # ---- distance pass (device time of the kernels; pairs resident) ----------
@@ -332,7 +334,8 @@ def main():
         "wall_ms_per_step": wall_ms / K,
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"kernel": "core_mut_kernel<RNG> (gather-by-parent + SNP mutation, TMA bulk pipeline)",
+        "roofline": {"kernel": "core_mut_kernel<RNG> (gather-by-parent + previous generation's recombination events + SNP "
+                               "mutation in one pass, TMA bulk pipeline)",
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": NCU_CORE_STEP_DRAM_BYTES, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": core_bytes, "launch_ms": mut_ms,
@@ -350,7 +353,8 @@ def main():
                       "e2e_h2d_bytes": 8 * P, "e2e_d2h_bytes": 12 * P},
         "e2e": {"value": world / (e2e_ms * 1e-3), "unit": "generations/s",
                 "h2d_bytes_per_step": 12 * N, "d2h_bytes_per_step": 12 * N, "ms_per_step": e2e_ms,
-                "path": "pansim_average_distance -> pansim_sample_indices -> pansim_step_with_parents, host vectors"},
+                "path": "pansim_average_distance -> pansim_sample_indices -> pansim_step_with_parents, host vectors; "
+                        "the step call returns with the core kernel in flight, the loop ends with a device synchronize"},
     }
     if not args.no_cpu_baseline and world == 1:
         pairs_cpu = 2000

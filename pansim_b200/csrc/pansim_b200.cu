@@ -888,9 +888,10 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
         CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, core_mut_kernel<true, false>, CM_THREADS, c->core_smem));
         if (occ < 1) FAIL(c, PANSIM_ERR_CUDA, "core_mut_kernel does not fit on an SM (smem %zu)", c->core_smem);
         c->core_occupancy = occ;
-        // short-lived CTAs (3 items per warp, tuned on B200): many waves over the resident slots
         const uint64_t items = (uint64_t)c->N * c->n_regions;
-        c->core_items_per_warp = 3;
+        // short-lived CTAs (3 items per warp) where the selection chain is on the critical path; longer ones
+        // (up to 12) once the core step has hundreds of items per resident warp and the chain hides under it
+        c->core_items_per_warp = (uint32_t)std::min<uint64_t>(12, std::max<uint64_t>(3, items / ((uint64_t)c->sm_count * occ * CM_WARPS * 40)));
         if (const char *e = getenv("PANSIM_CORE_CTAS_PER_SM")) {
             // long-lived CTAs: a grid of (CTAs per SM) x (SM count), each warp takes its share of the items
             const uint64_t ctas = (uint64_t)std::max(1, atoi(e)) * c->sm_count;
