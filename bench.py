@@ -32,6 +32,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_JSON_OUT = sys.stdout
 CFG2 = dict(pop_size=1000, core_size=1_200_000, pan_genes=6000, core_genes=2000, n_gen=100,
             max_distances=100_000, prop_positive=0.1, competition_strength=0.5, seed=0)
 PEAK_FALLBACK_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
@@ -167,7 +168,7 @@ def run_reference(args, rank, world):
         "distances": {"value": pairs_per_s, "unit": "pairs/s"},
         "e2e": {"value": val, "unit": "generations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 def main():
@@ -179,6 +180,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-gens", type=int, default=2)
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: libraries that print there (NCCL's version banner) are
+    # sent to stderr, and the line is written to the saved descriptor at the end
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -364,7 +371,7 @@ def main():
             "sample": f"{args.cpu_gens} cfg2 generations from the clonal start (oracle C port, OpenMP where the "
                       f"reference uses rayon); distance pass on {pairs_cpu} of the pairs",
             "distances_pairs_per_s": args.cpu_gens * pairs_cpu / t_dist if t_dist > 0 else None}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
     sim.close()
     if world > 1:
         dist.destroy_process_group()
