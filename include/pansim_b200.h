@@ -124,7 +124,14 @@ int pansim_get_weights(pansim_ctx *ctx, double *weights, int32_t *num_genes, dou
 
 /* main.rs:445-464 with parents supplied by the host: next_generation x2 +
  * mutate_alleles x2 + recombine x2 as ONE fused device pass per population
- * (generate mode: events drawn from Philox keyed by seed/gen/row/site-block). */
+ * (generate mode: events drawn from Philox keyed by seed/gen/row/site-block).
+ * The call returns once `parents` has been consumed and the step is enqueued:
+ * the core pass keeps running on the device beside the selection calls of the
+ * next generation. Every entry point that reads or writes the core alignment
+ * (pair counts, downloads, CSV export, uploads, replay steps, timing) waits for
+ * it first, and applies the recombination events the pass defers to the next
+ * generation, so callers always observe the state of
+ * population.rs after recombine(). */
 int pansim_step_with_parents(pansim_ctx *ctx, uint32_t gen, const uint32_t *parents);
 /* whole generation main.rs:435-464 on the device: competition (if
  * competition_strength > 0) -> fitness -> parents -> fused step. */
