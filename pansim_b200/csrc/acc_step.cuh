@@ -104,6 +104,7 @@ __device__ __forceinline__ uint32_t bernoulli_word(uint2 key, uint32_t gen, uint
 template <bool DUMP>
 __global__ void __launch_bounds__(256) acc_gather_flip_kernel(const AccArgs a)
 {
+    pdl_launch_dependents();       // the gain-threshold kernel may take its SM slots now (it waits for this grid)
     const uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint32_t lane = threadIdx.x & 31;
     if (row >= a.n_rows) return;
@@ -159,6 +160,8 @@ __device__ __forceinline__ uint32_t warp_transpose32_rev(uint32_t x, uint32_t la
 
 __global__ void __launch_bounds__(GAIN_WARPS * 32) acc_gain_threshold_kernel(const AccArgs a)
 {
+    pdl_launch_dependents();
+    pdl_wait();                    // rows and 1/K values of acc_gather_flip_kernel
     __shared__ double part[GAIN_WARPS][32];
     const uint32_t w = blockIdx.x;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -206,6 +209,7 @@ __global__ void __launch_bounds__(GAIN_WARPS * 32) acc_gain_threshold_kernel(con
 template <bool DUMP>
 __global__ void __launch_bounds__(256) acc_hgt_apply_kernel(const AccArgs a)
 {
+    pdl_wait();                    // gain thresholds of acc_gain_threshold_kernel
     const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t total = (uint64_t)a.n_rows * a.stride_words;
     if (idx >= total) return;

@@ -208,6 +208,13 @@ __device__ __forceinline__ void bulk_wait()
     asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// Programmatic dependent launch (sm_90+). A kernel that calls pdl_launch_dependents() lets the next
+// kernel of the stream be scheduled while it is still running; that kernel (launched with the
+// programmatic-stream-serialization attribute) blocks in pdl_wait() until this grid has completed
+// and its memory is visible. Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // make generic-proxy shared-memory writes visible to the async proxy (TMA)
 __device__ __forceinline__ void fence_proxy_async()
 {

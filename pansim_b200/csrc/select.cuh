@@ -321,6 +321,7 @@ __global__ void __launch_bounds__(AVG_WARPS * 32) avg_distance_kernel(const uint
     // batch ahead of the additions. Entries with j == i or j >= N are +0.0, which never changes
     // the (non-negative) sum.
     __shared__ double ring[AVG_WARPS][AVG_RING + 2 * AVG_BATCH];
+    pdl_launch_dependents();       // the parent-selection CTA may take its SM slot now (it waits for this grid)
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t i = blockIdx.x * AVG_WARPS + warp;
     if (i >= n_rows) return;
@@ -418,7 +419,7 @@ struct SelectArgs {
     double *tmp_a, *tmp_b;        // [N] scratch
     double *weights;              // [N] out: final weights (population.rs:389-437)
     double *cumulative;           // [N] out
-    uint32_t *parents;            // [N] out
+    uint32_t *parents;            // [N + 1] out: the parents, then a status word (1 = WeightedIndex::new would fail)
     int *err_flag;                // set to 1 if WeightedIndex::new would fail
 };
 
@@ -438,6 +439,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_parents_small_kernel(const
     const uint32_t n = a.n_rows, tid = threadIdx.x;
     const bool use_a = a.n_genes > 0, use_b = !a.no_control_genome_size;
     if (tid == 0) bad = 0;
+    pdl_wait();                    // mean distances of avg_distance_kernel
     double xa[SEL_PER], xb[SEL_PER], xc[SEL_PER];
     double ma = -INFINITY, mb = -INFINITY, mc = -INFINITY;
 #pragma unroll
@@ -521,6 +523,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_parents_small_kernel(const
         a.cumulative[i] = run;
     }
     __syncthreads();
+    if (tid == 0) a.parents[n] = bad ? 1u : 0u;       // status word behind the vector: one read-back serves both
     if (bad) {
         if (tid == 0) *a.err_flag = 1;
         for (uint32_t i = tid; i < n; i += SEL_THREADS) a.parents[i] = i;
@@ -554,6 +557,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_parents_kernel(const Selec
     const bool use_a = a.n_genes > 0, use_b = !a.no_control_genome_size;
     double *va = a.tmp_a, *vb = a.tmp_b, *vc = a.cumulative;      // vc: scratch until the cumulative sums are written
     if (tid == 0) bad = 0;
+    pdl_wait();                    // mean distances of avg_distance_kernel
 
     // pass 0: the three arguments and their maxima
     double ma = -INFINITY, mb = -INFINITY, mc = -INFINITY;
@@ -634,6 +638,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_parents_kernel(const Selec
         a.cumulative[i] = run;
     }
     __syncthreads();
+    if (tid == 0) a.parents[n] = bad ? 1u : 0u;       // status word behind the vector: one read-back serves both
     if (bad) {
         if (tid == 0) *a.err_flag = 1;
         for (uint32_t i = tid; i < n; i += SEL_THREADS) a.parents[i] = i;
