@@ -150,6 +150,12 @@ struct pansim_ctx {
 
     uint32_t *d_parents = nullptr;
     double *d_lw = nullptr, *d_logfit = nullptr, *d_avgdist = nullptr;
+    uint32_t *d_lethal = nullptr;         // bit g: ln(1 + s_g) = -inf (s_g = -1)
+    // PANSIM_FITNESS_MODE: 1 = two warps per row (28 us, but ~500 CTAs resident beside the core kernel),
+    // 2 = one lane per row (44 us, 8 CTAs), 0 = by entry point: two warps per row where the host waits on
+    // the chain (lowest latency), one lane per row in the device-resident batch (the core kernel keeps its
+    // SM slots: +7 % generations/s). All three give the same bits.
+    int fitness_mode = 0;
     int32_t *d_num_genes = nullptr;
     double *d_tmp_a = nullptr, *d_tmp_b = nullptr, *d_weights = nullptr, *d_cum = nullptr;
     int *d_err = nullptr;                // [0] upload / selection errors, [1] recombination list overflow
@@ -371,9 +377,12 @@ int launch_fitness(pansim_ctx *c, cudaStream_t st = nullptr)
     else if (c->fitness_blocked)
         fitness_blocked_kernel<<<div_up64(c->N, FIT_WARPS), FIT_WARPS * 32, 0, st>>>(acc, c->N, c->G, c->acc_stride_words,
                                                                                 c->d_lw, c->d_logfit, c->d_num_genes);
-    else
+    else if (c->fitness_mode == 1 || (c->fitness_mode == 0 && c->pdl_now))
         fitness_kernel<<<div_up64(c->N, FIT_ROWS), FIT_ROWS * 64, 0, st>>>(acc, c->N, c->G, c->acc_stride_words,
                                                                       c->d_lw, c->d_logfit, c->d_num_genes);
+    else
+        fitness_lane_kernel<<<div_up64(c->N, FITL_THREADS), FITL_THREADS, 0, st>>>(acc, c->N, c->G, c->acc_stride_words,
+                                                                              c->d_lw, c->d_lethal, c->d_logfit, c->d_num_genes);
     LAUNCH_CHECK(c);
     c->fitness_valid = true;
     return 0;
@@ -723,7 +732,7 @@ void pansim_destroy(pansim_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->stream_core) cudaStreamSynchronize(c->stream_core);
     if (c->stream_aux) cudaStreamSynchronize(c->stream_aux);
-    void *ptrs[] = {c->core[0], c->core[1], c->d_hr_slots, c->d_hr_counts, c->d_hr_ovf, c->d_hr_ovf_count, c->d_core_img, c->acc[0], c->acc[1], c->d_parents_buf[0], c->d_parents_buf[1], c->d_parents_buf[2], c->d_lw, c->d_logfit, c->d_avgdist,
+    void *ptrs[] = {c->core[0], c->core[1], c->d_hr_slots, c->d_hr_counts, c->d_hr_ovf, c->d_hr_ovf_count, c->d_core_img, c->acc[0], c->acc[1], c->d_parents_buf[0], c->d_parents_buf[1], c->d_parents_buf[2], c->d_lw, c->d_lethal, c->d_logfit, c->d_avgdist,
                     c->d_num_genes, c->d_tmp_a, c->d_tmp_b, c->d_weights, c->d_cum, c->d_err, c->d_inter, c->d_rowInvK, c->d_gain_planes,
                     c->d_gain_thr, c->tab_mut.d_thr, c->tab_hr.d_thr, c->d_r1, c->d_r2, c->d_cd, c->d_in, c->d_un,
                     c->d_replay, c->d_hkeys, c->d_hvals, c->d_stage, c->d_groups, c->d_partner, c->d_orig, c->d_batches, c->d_tile_slots, c->d_tile_orig, c->d_dump_counters, c->d_mut_row, c->d_mut_site,
@@ -886,6 +895,9 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
         c->d_parents = c->d_parents_buf[0];
         CU(c, cudaMalloc(&c->d_lw, (size_t)(c->G ? c->G : 1) * 8));
         CU(c, cudaMemset(c->d_lw, 0, (size_t)(c->G ? c->G : 1) * 8));
+        CU(c, cudaMalloc(&c->d_lethal, (size_t)(c->acc_words ? c->acc_words : 1) * 4));
+        CU(c, cudaMemset(c->d_lethal, 0, (size_t)(c->acc_words ? c->acc_words : 1) * 4));
+        if (const char *e = getenv("PANSIM_FITNESS_MODE")) c->fitness_mode = atoi(e);
         CU(c, cudaMalloc(&c->d_logfit, n * 8));
         CU(c, cudaMalloc(&c->d_avgdist, n * 8));
         CU(c, cudaMalloc(&c->d_num_genes, n * 4));
@@ -1130,6 +1142,10 @@ int pansim_set_selection(pansim_ctx *c, const double *s)
         if (!(lw[j] == 0.0) || std::signbit(lw[j])) neutral = false;
     }
     c->neutral = neutral;
+    std::vector<uint32_t> lethal(c->acc_words ? c->acc_words : 1, 0u);
+    for (uint32_t j = 0; j < c->G; j++)
+        if (std::isinf(lw[j]) && lw[j] < 0) lethal[j >> 5] |= 1u << (j & 31);
+    CU(c, cudaMemcpyAsync(c->d_lethal, lethal.data(), lethal.size() * 4, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaMemcpyAsync(c->d_lw, lw.data(), (size_t)c->G * 8, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     c->fitness_valid = false;

@@ -138,6 +138,85 @@ __global__ void __launch_bounds__(FIT_ROWS * 64) fitness_kernel(const uint32_t *
     }
 }
 
+// The same sequential sum with ONE LANE PER ROW: every lane walks the set bits of its own row in
+// column order and runs its own dependent f64 chain, so a warp advances 32 rows per DADD instead
+// of one. The kernel needs 1/32 of the warps of the row-per-warp-pair kernel above and therefore
+// hardly takes SM slots away from the core kernel it runs beside (measured: the row-per-warp-pair
+// kernel holds ~500 CTAs for ~30 us each and costs the concurrent core kernel 6 %). The warp steps
+// through ALL gene positions (G dependent DADD issues, each predicated on the lane's own bit) with
+// the lw values of a 1024-gene chunk in shared memory. Genes with lw = -inf (s = -1) are given as
+// a bit mask: they are left out of the chain and any of them present sets the result to 0.0
+// (population.rs:312-318).
+constexpr int FITL_THREADS = 128;
+
+// sum += x iff (bits & mask). Written as an unconditional add of (bit ? x : +0.0): the selection of
+// the operand is off the dependent chain (x and bits are known ahead), so the chain is one DADD per
+// position; and x + (+0.0) = x exactly, because the running sum starts at +0.0 and can never
+// become -0.0.
+__device__ __forceinline__ void add_if_bit(double &sum, double x, uint32_t bits, uint32_t mask)
+{
+    sum += (bits & mask) ? x : 0.0;
+}
+
+__global__ void __launch_bounds__(FITL_THREADS) fitness_lane_kernel(const uint32_t *acc, uint32_t n_rows,
+                                                                    uint32_t n_genes, uint32_t stride_words,
+                                                                    const double *lw, const uint32_t *lethal,
+                                                                    double *logfit, int32_t *num_genes)
+{
+    __shared__ double lw_s[FIT_CHUNK_WORDS * 32];
+    __shared__ uint32_t lethal_s[FIT_CHUNK_WORDS];
+    const uint32_t row = blockIdx.x * FITL_THREADS + threadIdx.x;
+    const bool live = row < n_rows;
+    const uint32_t *r = acc + (uint64_t)(live ? row : 0u) * stride_words;
+    const uint32_t n_words = (n_genes + 31u) / 32u;
+    double sum = 0.0;
+    bool neg_inf = false;
+    int32_t cnt = 0;
+    for (uint32_t w0 = 0; w0 < n_words; w0 += FIT_CHUNK_WORDS) {
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < FIT_CHUNK_WORDS * 32; i += FITL_THREADS) {
+            const uint32_t g = w0 * 32u + i;
+            const double v = g < n_genes ? lw[g] : 0.0;
+            lw_s[i] = (v == -INFINITY) ? 0.0 : v;
+        }
+        if (threadIdx.x < FIT_CHUNK_WORDS) lethal_s[threadIdx.x] = (w0 + threadIdx.x < n_words) ? lethal[w0 + threadIdx.x] : 0u;
+        __syncthreads();
+        const uint32_t nw = min((uint32_t)FIT_CHUNK_WORDS, n_words - w0);
+        // The additions of 16 gene positions (one half word) run while the lw values of the next
+        // half word are already on their way from shared memory (same address for every lane:
+        // broadcast; unconditional volatile loads so that they stay ahead of the chain), so the
+        // chain advances at the DADD latency.
+        const uint32_t lw_sa = smem_u32(lw_s);
+        double xa[16], xb[16];
+        auto load_half = [&](double (&x)[16], uint32_t half) {       // half = 2 * word + (0 | 1)
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x[2 * q]), "=d"(x[2 * q + 1])
+                             : "r"(lw_sa + half * 128u + q * 16u));
+        };
+        uint32_t bits_next = live ? r[w0] : 0u;
+        load_half(xa, 0u);
+        for (uint32_t w = 0; w < nw; w++) {
+            uint32_t bits = bits_next;
+            if (w + 1 < nw) bits_next = live ? r[w0 + w + 1] : 0u;
+            cnt += __popc(bits);
+            const uint32_t dead = bits & lethal_s[w];
+            neg_inf |= dead != 0u;
+            bits ^= dead;
+            load_half(xb, 2u * w + 1u);
+#pragma unroll
+            for (int b = 0; b < 16; b++) add_if_bit(sum, xa[b], bits, 1u << b);
+            load_half(xa, min(2u * w + 2u, 2u * FIT_CHUNK_WORDS - 1u));
+#pragma unroll
+            for (int b = 0; b < 16; b++) add_if_bit(sum, xb[b], bits, 1u << (16 + b));
+        }
+    }
+    if (live) {
+        logfit[row] = (n_genes > 0) ? (neg_inf ? 0.0 : sum) : 0.0;
+        num_genes[row] = cnt;
+    }
+}
+
 // Large shapes (N x G above FITNESS_EXACT_CELLS): the strictly sequential chain above costs one
 // issue slot per addition per row and dominates the accessory/selection chain (0.6 ms at
 // N = 10 000, G = 18 000). The blocked variant adds, per row, the present genes of each 32-gene
