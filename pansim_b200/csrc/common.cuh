@@ -87,54 +87,12 @@ __host__ __device__ __forceinline__ uint4 make_ctr(uint32_t block, uint32_t row,
     return make_uint4(block, row, gen, stream << 16);
 }
 
-// Poisson by CDF inversion from one 32-bit uniform: k = #{j : T[j] <= u} with
-// T[j] = round(CDF(j) * 2^32) (built on the host in f64), padded with
-// 0xFFFFFFFF. A 256-entry guide table indexed by the top 8 bits of u holds
-// 2*k0 + impure, where k0 = #{j : T[j] <= (u with the low 24 bits cleared)} and
-// `impure` says a threshold falls inside the bin (then a short forward scan
-// finishes). A mean above the table range is drawn as a sum of n_sub
-// independent Poisson(mean / n_sub) (exact by additivity).
-// Shared-memory image of one table: [256 x u32 guide][size x u32 thresholds]
-constexpr uint32_t GUIDE_ENTRIES = 256;
-constexpr uint32_t GUIDE_SHIFT = 24;
+// Poisson counts are drawn by CDF inversion of one 32-bit uniform: k = #{j : T[j] <= u} with
+// T[j] = round(CDF(j) * 2^32) (built on the host in f64), padded with 0xFFFFFFFF. A mean above the
+// table range is drawn as a sum of n_sub independent Poisson(mean / n_sub) (exact by additivity).
+// core_mut.cuh (SNPs per 256-site block, with a guide table) and core_hr.cuh (recombination
+// events per region, lane-parallel compare) hold the two samplers.
 constexpr uint32_t POISSON_TABLE_MAX = 1024;
-
-__device__ __forceinline__ uint32_t poisson_from_uniform(const uint32_t *tab, uint32_t kmax, uint32_t u)
-{
-    const uint32_t g = tab[u >> GUIDE_SHIFT];
-    uint32_t k = g >> 1;
-    if (g & 1u) {
-        const uint32_t *thr = tab + GUIDE_ENTRIES;
-        while (k < kmax && thr[k] <= u) k++;
-    }
-    return k;
-}
-
-// Poisson count of a stream. Draw 0 uses `first` (word x of Philox call 0); a
-// mean above the table range adds draws from dedicated count calls (exact by
-// additivity).
-__device__ __noinline__ uint32_t stream_count_extra(uint4 ctr, uint2 key, const uint32_t *tab, uint32_t nsub,
-                                                    uint32_t kmax)
-{
-    uint32_t k = 0;
-    for (uint32_t s = 1; s < nsub; s++) {
-        uint4 c = ctr;
-        c.w |= 0x8000u | ((s - 1) >> 2);
-        const uint4 r = philox4x32_10(c, key);
-        const uint32_t sel = (s - 1) & 3u;
-        const uint32_t u = sel == 0 ? r.x : sel == 1 ? r.y : sel == 2 ? r.z : r.w;
-        k += poisson_from_uniform(tab, kmax, u);
-    }
-    return k;
-}
-
-__device__ __forceinline__ uint32_t stream_count(uint4 ctr, uint2 key, uint32_t first, const uint32_t *tab,
-                                                 uint32_t nsub, uint32_t kmax)
-{
-    uint32_t k = poisson_from_uniform(tab, kmax, first);
-    if (nsub > 1) k += stream_count_extra(ctr, key, tab, nsub, kmax);
-    return k;
-}
 
 // ---------------------------------------------------------------------------
 // sm_100a PTX: mbarrier + 1-D bulk async copies (TMA engine, UBLKCP in SASS)

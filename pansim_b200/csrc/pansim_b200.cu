@@ -407,7 +407,7 @@ int launch_competition(pansim_ctx *c)
                                                               c->acc_words, c->d_inter);
     } else {
         const uint32_t nb = div_up64(c->N, IM_TILE);
-        acc_inter_mma_kernel<<<dim3(nb, nb), 256, 0, c->stream>>>(c->acc[c->acc_cur], c->N, c->acc_stride_words,
+        acc_inter_mma_kernel<<<nb * (nb + 1) / 2, 256, 0, c->stream>>>(c->acc[c->acc_cur], c->N, c->acc_stride_words,
                                                                   c->acc_words, c->d_inter);
     }
     LAUNCH_CHECK(c);

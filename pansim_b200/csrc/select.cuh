@@ -334,8 +334,11 @@ __global__ void __launch_bounds__(256) acc_inter_mma_kernel(const uint32_t *acc,
                                                             uint32_t stride_words, uint32_t n_words,
                                                             uint32_t *inter)
 {
-    const uint32_t bi = blockIdx.y, bj = blockIdx.x;
-    if (bj < bi) return;
+    // blockIdx.x enumerates the upper-triangle tiles row by row: (0,0..nb-1), (1,1..nb-1), ...
+    const uint32_t nb = (n_rows + IM_TILE - 1) / IM_TILE;
+    uint32_t t_lin = blockIdx.x, bi = 0;
+    while (t_lin >= nb - bi) { t_lin -= nb - bi; bi++; }
+    const uint32_t bj = bi + t_lin;
     __shared__ uint32_t Ri[IM_TILE][IM_CHUNK + 1];
     __shared__ uint32_t Rj[IM_TILE][IM_CHUNK + 1];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
