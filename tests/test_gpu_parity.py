@@ -571,7 +571,10 @@ def test_deferred_recombination_equals_immediate(monkeypatch, kw):
             sim.run_generations(3, 1)
             cd = sim.pair_counts(r1, r2)[0]              # materialises generation 3's events
             sim.run_generations(4, 1)
-            out[defer] = (mid, cd, sim.download_core(), sim.parents())
+            last, par = sim.download_core(), sim.parents()
+            sim.run_generations(5, 1)                    # events pending again ...
+            sim.next_generation(np.arange(p.pop_size, dtype=np.uint32)[::-1].copy())   # ... when a plain gather follows
+            out[defer] = (mid, cd, last, par, sim.download_core())
     for a, b in zip(out["0"], out["1"]):
         assert (a == b).all()
     assert (out["0"][2] != core).any()

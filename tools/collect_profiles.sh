@@ -10,7 +10,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 python tools/launch_summary.py $out/${tag}_launches_bench_steps5.csv > $out/${tag}_launches_summary.txt
 : > $out/${tag}_ncu_summary.txt
 # launch 7 of core_mut_kernel (0-based) is the first with recombination events pending after a materialised state
-for spec in "core_mut_kernel 7" "hr_collect_kernel 1" "hr_apply_kernel 1" "acc_inter_mma_kernel 5" "fitness_kernel 5" \
+for spec in "core_mut_kernel 7" "hr_collect_kernel 1" "hr_apply_kernel 1" "acc_inter_mma_kernel 5" "fitness_lane_kernel 3" "fitness_kernel 1" \
             "avg_distance_kernel 5" "select_parents_small_kernel 5" "acc_gather_flip_kernel 5" "acc_gain_threshold_kernel 5" \
             "acc_hgt_apply_kernel 5" "pair_core_grouped_kernel 2"; do
     set -- $spec
