@@ -178,6 +178,18 @@ int pansim_pair_counts(pansim_ctx *ctx, const uint32_t *range1, const uint32_t *
  * NCCL all-reduce by the host plumbing; returns after the kernels finished. */
 int pansim_pair_counts_device(pansim_ctx *ctx, const uint32_t *range1, const uint32_t *range2,
                               size_t n_pairs, void *d_core_diff, void *d_inter, void *d_uni);
+/* Exact all-pairs mode (an extension: the reference only samples max_distances
+ * pairs with replacement, main.rs:413-427; BASELINE config 5 asks for all
+ * N(N-1)/2). Counts for every pair (i, j) with row_begin <= i < row_end and
+ * i < j < N, in (i ascending, j ascending) order; the pair list and its plan are
+ * generated on the device. n_pairs_out = sum over i of (N-1-i), at most 2^31-1
+ * per call (walk the rows in blocks). Outputs may be NULL. */
+int pansim_pair_counts_rows(pansim_ctx *ctx, uint32_t row_begin, uint32_t row_end, uint32_t *core_diff,
+                            uint32_t *inter, uint32_t *uni, size_t *n_pairs_out);
+/* same, outputs left in caller-provided DEVICE buffers (for the NCCL all-reduce
+ * of column-sharded contexts) */
+int pansim_pair_counts_rows_device(pansim_ctx *ctx, uint32_t row_begin, uint32_t row_end, void *d_core_diff,
+                                   void *d_inter, void *d_uni, size_t *n_pairs_out);
 /* the two f64 formulas (population.rs:822, :828-830), exported so every host
  * language forms the distances identically */
 double pansim_core_distance(uint32_t core_diff, uint64_t core_size);

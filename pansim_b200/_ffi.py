@@ -20,6 +20,7 @@ EXPORTED = [
     "pansim_average_distance", "pansim_sample_indices", "pansim_get_weights",
     "pansim_step_with_parents", "pansim_step", "pansim_run_generations", "pansim_next_generation",
     "pansim_get_parents", "pansim_step_replay", "pansim_pair_counts", "pansim_pair_counts_device",
+    "pansim_pair_counts_rows", "pansim_pair_counts_rows_device",
     "pansim_core_distance", "pansim_acc_distance", "pansim_gene_counts", "pansim_get_info",
     "pansim_get_timing", "pansim_set_timing", "pansim_enable_event_dump",
     "pansim_fetch_event_dump", "pansim_free_event_dump", "pansim_get_rates",
@@ -140,6 +141,8 @@ def lib():
     sig("pansim_step_replay", cint, vp, C.POINTER(Events))
     sig("pansim_pair_counts", cint, vp, vp, vp, sz, vp, vp, vp)
     sig("pansim_pair_counts_device", cint, vp, vp, vp, sz, vp, vp, vp)
+    sig("pansim_pair_counts_rows", cint, vp, u32, u32, vp, vp, vp, vp)
+    sig("pansim_pair_counts_rows_device", cint, vp, u32, u32, vp, vp, vp, vp)
     sig("pansim_core_distance", dbl, u32, C.c_uint64)
     sig("pansim_acc_distance", dbl, u32, u32, u32)
     sig("pansim_gene_counts", cint, vp, vp)

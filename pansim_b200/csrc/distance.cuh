@@ -133,6 +133,44 @@ __global__ void __launch_bounds__(PAIR_THREADS) pair_core_grouped_kernel(
     }
 }
 
+// Exact all-pairs mode: the pair list of a row block [row_begin, row_end) -- every (i, j) with
+// i < j < N, ordered by i then j -- and its row-stationary groups are generated on the device, so
+// nothing but a small offset table crosses the bus. off[r] = number of pairs of the rows before
+// row_begin + r, goff[r] = number of groups before it (both with nr + 1 entries).
+__device__ __forceinline__ uint32_t upper_row(const uint32_t *off, uint32_t nr, uint32_t k)
+{
+    uint32_t lo = 0, hi = nr;            // last r with off[r] <= k
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (off[mid] <= k) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void rows_pairs_kernel(const uint32_t *off, uint32_t nr, uint32_t row_begin, uint32_t n_pairs,
+                                  uint32_t *range1, uint32_t *range2, uint32_t *partner, uint32_t *orig_index)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_pairs) return;
+    const uint32_t r = upper_row(off, nr, k);
+    const uint32_t i = row_begin + r, j = i + 1u + (k - off[r]);
+    range1[k] = i; range2[k] = j; partner[k] = j; orig_index[k] = k;
+}
+
+// groups of the pairs (i, j) of the row block with j in [jb0, jb1): goff[r] = groups of this
+// column block before row row_begin + r
+__global__ void rows_groups_kernel(const uint32_t *off, const uint32_t *goff, uint32_t nr, uint32_t row_begin,
+                                   uint32_t jb0, uint32_t jb1, uint32_t n_groups, PairGroup *groups)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const uint32_t r = upper_row(goff, nr, g);
+    const uint32_t i = row_begin + r;
+    const uint32_t j_lo = max(i + 1u, jb0);                                      // first partner of row i in this block
+    const uint32_t j = j_lo + (uint32_t)PAIR_GROUP * (g - goff[r]);
+    groups[g] = PairGroup{i, off[r] + (j - (i + 1u)), min((uint32_t)PAIR_GROUP, jb1 - j)};
+}
+
 // v2: shared-memory row tiles. The host plan (cached) buckets the pairs by the pair of
 // 32-row blocks their endpoints fall in. A CTA takes one batch (<= 256 pairs of one
 // block pair), stages the <= 64 rows it needs, 512 B per row per stage, with cp.async

@@ -1515,6 +1515,35 @@ static int ensure_pair_plan(pansim_ctx *c, const uint32_t *r1, const uint32_t *r
     return 0;
 }
 
+// core Hamming counts of the planned pairs (c->plan_batches / c->plan_groups) into d_cd[P];
+// rows_active = number of distinct rows the plan touches (sizes the L2-resident column chunk)
+static int launch_pair_core(pansim_ctx *c, uint32_t *d_cd, size_t P, uint32_t rows_active, bool clear)
+{
+    const uint32_t row_vec4 = (uint32_t)(c->core_stride / 16);
+    // column chunk sized so that rows x chunk stays L2 resident
+    uint64_t chunk_bytes = (48ull << 20) / std::max(1u, rows_active);
+    chunk_bytes = (chunk_bytes / 4096) * 4096;
+    if (chunk_bytes < 4096) chunk_bytes = 4096;
+    if (chunk_bytes > c->core_stride) chunk_bytes = ((c->core_stride + 4095) / 4096) * 4096;
+    uint32_t chunk_vec4 = (uint32_t)(chunk_bytes / 16);
+    uint32_t n_chunks = (row_vec4 + chunk_vec4 - 1) / chunk_vec4;
+    if (n_chunks > 65535) { n_chunks = 65535; chunk_vec4 = (row_vec4 + n_chunks - 1) / n_chunks; chunk_vec4 = ((chunk_vec4 + 255) / 256) * 256; n_chunks = (row_vec4 + chunk_vec4 - 1) / chunk_vec4; }
+    if (clear) CU(c, cudaMemsetAsync(d_cd, 0, P * 4, c->stream));      // both kernels accumulate with integer atomics
+    if (c->plan_batches) {
+        pair_core_tile_kernel<<<(uint32_t)c->plan_batches, TILE_THREADS, tile_smem_bytes(), c->stream>>>(
+            c->core[c->core_cur], c->core_stride, c->N, c->d_batches, c->d_tile_slots, c->d_tile_orig, d_cd);
+        LAUNCH_CHECK(c);
+    }
+    if (c->plan_groups) {
+        const uint32_t gx = (uint32_t)std::min<size_t>(c->plan_groups, 1u << 20);
+        pair_core_grouped_kernel<<<dim3(gx, n_chunks), PAIR_THREADS, 0, c->stream>>>(
+            c->core[c->core_cur], c->core_stride, chunk_vec4, row_vec4, c->d_groups, (uint32_t)c->plan_groups,
+            c->d_partner, c->d_orig, d_cd);
+        LAUNCH_CHECK(c);
+    }
+    return 0;
+}
+
 static int pair_counts_impl(pansim_ctx *c, const uint32_t *r1, const uint32_t *r2, size_t P, uint32_t *d_cd,
                             uint32_t *d_in, uint32_t *d_un)
 {
@@ -1533,28 +1562,7 @@ static int pair_counts_impl(pansim_ctx *c, const uint32_t *r1, const uint32_t *r
         if (c->Ll == 0) {
             CU(c, cudaMemsetAsync(d_cd, 0, P * 4, c->stream));
         } else {
-            const uint32_t row_vec4 = (uint32_t)(c->core_stride / 16);
-            // column chunk sized so that N x chunk stays L2 resident
-            uint64_t chunk_bytes = (48ull << 20) / c->N;
-            chunk_bytes = (chunk_bytes / 4096) * 4096;
-            if (chunk_bytes < 4096) chunk_bytes = 4096;
-            if (chunk_bytes > c->core_stride) chunk_bytes = ((c->core_stride + 4095) / 4096) * 4096;
-            uint32_t chunk_vec4 = (uint32_t)(chunk_bytes / 16);
-            uint32_t n_chunks = (row_vec4 + chunk_vec4 - 1) / chunk_vec4;
-            if (n_chunks > 65535) { n_chunks = 65535; chunk_vec4 = (row_vec4 + n_chunks - 1) / n_chunks; chunk_vec4 = ((chunk_vec4 + 255) / 256) * 256; n_chunks = (row_vec4 + chunk_vec4 - 1) / chunk_vec4; }
-            CU(c, cudaMemsetAsync(d_cd, 0, P * 4, c->stream));      // both kernels accumulate with integer atomics
-            if (c->plan_batches) {
-                pair_core_tile_kernel<<<(uint32_t)c->plan_batches, TILE_THREADS, tile_smem_bytes(), c->stream>>>(
-                    c->core[c->core_cur], c->core_stride, c->N, c->d_batches, c->d_tile_slots, c->d_tile_orig, d_cd);
-                LAUNCH_CHECK(c);
-            }
-            if (c->plan_groups) {
-                const uint32_t gx = (uint32_t)std::min<size_t>(c->plan_groups, 1u << 20);
-                pair_core_grouped_kernel<<<dim3(gx, n_chunks), PAIR_THREADS, 0, c->stream>>>(
-                    c->core[c->core_cur], c->core_stride, chunk_vec4, row_vec4, c->d_groups, (uint32_t)c->plan_groups,
-                    c->d_partner, c->d_orig, d_cd);
-                LAUNCH_CHECK(c);
-            }
+            if (int rc = launch_pair_core(c, d_cd, P, c->N, true)) return rc;
         }
     }
     if (d_in || d_un) {
@@ -1592,6 +1600,130 @@ int pansim_pair_counts_device(pansim_ctx *c, const uint32_t *r1, const uint32_t 
     CU(c, cudaSetDevice(c->cfg.device));
     if (int rc = ensure_pairs(c, P)) return rc;
     if (int rc = pair_counts_impl(c, r1, r2, P, (uint32_t *)d_cd, (uint32_t *)d_in, (uint32_t *)d_un)) return rc;
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// Exact all-pairs extension: every pair (i, j), i in [row_begin, row_end), i < j < N, in (i, j)
+// order; pair list and plan generated on the device (distance.cuh).
+static int pair_counts_rows_impl(pansim_ctx *c, uint32_t row_begin, uint32_t row_end, uint32_t *d_cd, uint32_t *d_in,
+                                 uint32_t *d_un, size_t *n_out)
+{
+    if (row_begin > row_end || row_end > c->N) FAIL(c, PANSIM_ERR_INVALID, "row block [%u, %u) out of range", row_begin, row_end);
+    const uint32_t nr = row_end - row_begin;
+    std::vector<uint32_t> off(nr + 1, 0);
+    uint64_t P = 0;
+    for (uint32_t r = 0; r < nr; r++) {
+        off[r] = (uint32_t)P;
+        P += (uint64_t)c->N - 1u - (row_begin + r);
+        if (P > 0x7FFFFFFFull) FAIL(c, PANSIM_ERR_INVALID, "more than 2^31 pairs in rows [%u, %u): use smaller row blocks", row_begin, row_end);
+    }
+    off[nr] = (uint32_t)P;
+    *n_out = (size_t)P;
+    if (P == 0) return 0;
+    // Partner rows are walked in column blocks of the pair matrix: a launch touches the nr rows of the
+    // block and at most jb partner rows, so a column chunk of those rows (>= 32 KB each) stays in L2
+    // however large N is.
+    const uint32_t jb = std::max(256u, 1536u > nr ? 1536u - nr : 0u);
+    const uint32_t j_first = row_begin + 1u;
+    const uint32_t n_jblocks = (c->N - j_first + jb - 1) / jb;
+    std::vector<uint32_t> goff((size_t)n_jblocks * (nr + 1), 0);
+    std::vector<uint32_t> n_groups(n_jblocks, 0);
+    size_t max_groups = 0;
+    for (uint32_t b = 0; b < n_jblocks; b++) {
+        const uint32_t jb0 = j_first + b * jb, jb1 = std::min(c->N, jb0 + jb);
+        uint32_t *go = goff.data() + (size_t)b * (nr + 1);
+        uint64_t G = 0;
+        for (uint32_t r = 0; r < nr; r++) {
+            go[r] = (uint32_t)G;
+            const uint32_t j_lo = std::max(row_begin + r + 1u, jb0);
+            if (j_lo < jb1) G += (jb1 - j_lo + PAIR_GROUP - 1) / PAIR_GROUP;
+        }
+        go[nr] = (uint32_t)G;
+        n_groups[b] = (uint32_t)G;
+        max_groups = std::max(max_groups, (size_t)G);
+    }
+    if (int rc = ensure_pairs(c, (size_t)P)) return rc;
+    auto grow = [&](void **ptr, size_t &cap, size_t need, size_t elem) -> int {
+        if (need <= cap) return 0;
+        if (*ptr) cudaFree(*ptr);
+        *ptr = nullptr; cap = 0;
+        if (cudaMalloc(ptr, need * elem) != cudaSuccess) return -1;
+        cap = need;
+        return 0;
+    };
+    size_t cap_p2 = c->plan_cap_pairs;
+    if (grow((void **)&c->d_groups, c->plan_cap_groups, max_groups, sizeof(PairGroup)) ||
+        grow((void **)&c->d_partner, c->plan_cap_pairs, (size_t)P, 4) || grow((void **)&c->d_orig, cap_p2, (size_t)P, 4))
+        FAIL(c, PANSIM_ERR_NOMEM, "cudaMalloc for the all-pairs plan failed");
+    if (int rc = ensure_stage(c, ((size_t)(nr + 1) + goff.size()) * 4)) return rc;
+    uint32_t *d_off = reinterpret_cast<uint32_t *>(c->d_stage), *d_goff = d_off + (nr + 1);
+    CU(c, cudaMemcpyAsync(d_off, off.data(), (size_t)(nr + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(d_goff, goff.data(), goff.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));                 // the host vectors go out of scope
+    c->plan_r1.clear(); c->plan_r2.clear();                  // the cached sampled-pair plan is gone
+    c->plan_batches = 0;
+    timing_begin(c);
+    if (c->Ll)
+        if (int rc = core_materialize(c, c->stream)) return rc;
+    rows_pairs_kernel<<<div_up64(P, 256), 256, 0, c->stream>>>(d_off, nr, row_begin, (uint32_t)P, c->d_r1, c->d_r2, c->d_partner, c->d_orig);
+    LAUNCH_CHECK(c);
+    if (d_cd) {
+        ScopedSpan s(c, TG_PAIR_CORE);
+        CU(c, cudaMemsetAsync(d_cd, 0, (size_t)P * 4, c->stream));
+        for (uint32_t b = 0; b < n_jblocks && c->Ll; b++) {
+            if (!n_groups[b]) continue;
+            const uint32_t jb0 = j_first + b * jb, jb1 = std::min(c->N, jb0 + jb);
+            rows_groups_kernel<<<div_up64(n_groups[b], 256), 256, 0, c->stream>>>(d_off, d_goff + (size_t)b * (nr + 1), nr, row_begin,
+                                                                                  jb0, jb1, n_groups[b], c->d_groups);
+            LAUNCH_CHECK(c);
+            c->plan_groups = n_groups[b];
+            if (int rc = launch_pair_core(c, d_cd, (size_t)P, nr + (jb1 - jb0), false)) return rc;
+        }
+    }
+    c->plan_groups = 0;                                      // the device plan is only valid for this call
+    if (d_in || d_un) {
+        ScopedSpan s(c, TG_PAIR_ACC);
+        const uint32_t grid = (uint32_t)std::min<size_t>(((size_t)P + 7) / 8, (size_t)c->sm_count * 16);
+        pair_acc_kernel<<<grid ? grid : 1, 256, 0, c->stream>>>(c->acc[c->acc_cur], c->acc_stride_words, c->acc_words, c->d_r1, c->d_r2, (uint32_t)P, d_in, d_un);
+        LAUNCH_CHECK(c);
+    }
+    timing_end(c);
+    return 0;
+}
+
+int pansim_pair_counts_rows(pansim_ctx *c, uint32_t row_begin, uint32_t row_end, uint32_t *core_diff, uint32_t *inter,
+                            uint32_t *uni, size_t *n_pairs_out)
+{
+    if (!c) return PANSIM_ERR_INVALID;
+    if (int rc = require_state(c)) return rc;
+    CU(c, cudaSetDevice(c->cfg.device));
+    // buffers must exist before their addresses are passed on: size them for this block first
+    uint64_t P0 = 0;
+    for (uint32_t i = row_begin; i < row_end && i < c->N; i++) P0 += (uint64_t)c->N - 1u - i;
+    if (P0 > 0x7FFFFFFFull) FAIL(c, PANSIM_ERR_INVALID, "more than 2^31 pairs in rows [%u, %u): use smaller row blocks", row_begin, row_end);
+    if (P0) if (int rc = ensure_pairs(c, (size_t)P0)) return rc;
+    size_t P = 0;
+    if (int rc = pair_counts_rows_impl(c, row_begin, row_end, core_diff ? c->d_cd : nullptr, (inter || uni) ? c->d_in : nullptr,
+                                       (inter || uni) ? c->d_un : nullptr, &P)) return rc;
+    if (n_pairs_out) *n_pairs_out = P;
+    if (P == 0) return 0;
+    if (core_diff) CU(c, cudaMemcpyAsync(core_diff, c->d_cd, P * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (inter) CU(c, cudaMemcpyAsync(inter, c->d_in, P * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (uni) CU(c, cudaMemcpyAsync(uni, c->d_un, P * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int pansim_pair_counts_rows_device(pansim_ctx *c, uint32_t row_begin, uint32_t row_end, void *d_cd, void *d_in, void *d_un,
+                                   size_t *n_pairs_out)
+{
+    if (!c) return PANSIM_ERR_INVALID;
+    if (int rc = require_state(c)) return rc;
+    CU(c, cudaSetDevice(c->cfg.device));
+    size_t P = 0;
+    if (int rc = pair_counts_rows_impl(c, row_begin, row_end, (uint32_t *)d_cd, (uint32_t *)d_in, (uint32_t *)d_un, &P)) return rc;
+    if (n_pairs_out) *n_pairs_out = P;
     CU(c, cudaStreamSynchronize(c->stream));
     return 0;
 }

@@ -277,23 +277,56 @@ class Pansim:
         cd, it, un = self.pair_counts(range1, range2)
         return self.distances_from_counts(cd, it, un)
 
-    def iter_all_pairs(self, chunk_pairs: int = 4_000_000):
-        """Exact all-pairs mode (extension; the reference only samples pairs with replacement,
-        main.rs:413-427): yields (i, j, core_diff, inter, union) arrays covering every unordered
-        pair i < j exactly once, in chunks of about `chunk_pairs` pairs."""
-        N = self.N
-        i0 = 0
+    def pairs_in_rows(self, row_begin: int, row_end: int) -> int:
+        """Number of pairs (i, j) with row_begin <= i < row_end, i < j < N."""
+        n = row_end - row_begin
+        return n * (self.N - 1) - (row_begin + row_end - 1) * n // 2
+
+    def pair_counts_rows(self, row_begin: int, row_end: int, core: bool = True, acc: bool = True):
+        """Exact all-pairs mode for one block of rows (extension; the reference only samples pairs
+        with replacement, main.rs:413-427): (core_diff, inter, union) of every pair (i, j),
+        row_begin <= i < row_end, i < j < N, ordered by i then j. The pair list is generated on
+        the device."""
+        P = self.pairs_in_rows(row_begin, row_end)
+        cd = np.empty(P, np.uint32) if core else None
+        it = np.empty(P, np.uint32) if acc else None
+        un = np.empty(P, np.uint32) if acc else None
+        n = C.c_size_t(0)
+        self._check(self._lib.pansim_pair_counts_rows(self._h, row_begin, row_end, _ptr(cd), _ptr(it), _ptr(un),
+                                                      C.byref(n)))
+        assert n.value == P
+        return cd, it, un
+
+    def pair_counts_rows_device(self, row_begin: int, row_end: int, d_core_diff: int, d_inter: int, d_uni: int) -> int:
+        """Same, into caller-owned device buffers (raw pointers); returns the number of pairs."""
+        n = C.c_size_t(0)
+        self._check(self._lib.pansim_pair_counts_rows_device(self._h, row_begin, row_end, C.c_void_p(d_core_diff),
+                                                             C.c_void_p(d_inter), C.c_void_p(d_uni), C.byref(n)))
+        return n.value
+
+    def row_blocks(self, chunk_pairs: int = 4_000_000):
+        """Row blocks [i0, i1) of about `chunk_pairs` pairs each covering every i < N - 1."""
+        N, i0 = self.N, 0
         while i0 < N - 1:
-            # rows i0..i1-1 against all j > i
             i1, n = i0, 0
             while i1 < N - 1 and (n == 0 or n + (N - 1 - i1) <= chunk_pairs):
                 n += N - 1 - i1
                 i1 += 1
-            ii = np.repeat(np.arange(i0, i1, dtype=np.uint32), [N - 1 - i for i in range(i0, i1)])
-            jj = np.concatenate([np.arange(i + 1, N, dtype=np.uint32) for i in range(i0, i1)])
-            cd, it, un = self.pair_counts(ii, jj)
-            yield ii, jj, cd, it, un
+            yield i0, i1
             i0 = i1
+
+    def iter_all_pairs(self, chunk_pairs: int = 4_000_000, with_indices: bool = True):
+        """Exact all-pairs mode: yields (i, j, core_diff, inter, union) arrays covering every
+        unordered pair i < j exactly once, in chunks of about `chunk_pairs` pairs (i, j are None
+        with with_indices=False: the order is i ascending, then j ascending)."""
+        N = self.N
+        for i0, i1 in self.row_blocks(chunk_pairs):
+            cd, it, un = self.pair_counts_rows(i0, i1)
+            ii = jj = None
+            if with_indices:
+                ii = np.repeat(np.arange(i0, i1, dtype=np.uint32), [N - 1 - i for i in range(i0, i1)])
+                jj = np.concatenate([np.arange(i + 1, N, dtype=np.uint32) for i in range(i0, i1)])
+            yield ii, jj, cd, it, un
 
     def gene_counts(self) -> np.ndarray:
         out = np.empty(self.G, np.uint32)

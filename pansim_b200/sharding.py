@@ -74,6 +74,20 @@ class ShardedPansim:
         return (d_cd.cpu().numpy().astype(np.uint32), d_in.cpu().numpy().astype(np.uint32),
                 d_un.cpu().numpy().astype(np.uint32))
 
+    def pair_counts_rows(self, row_begin: int, row_end: int):
+        """Exact all-pairs block (Pansim.pair_counts_rows): device partials + NCCL all-reduce."""
+        if self.world == 1:
+            return self.sim.pair_counts_rows(row_begin, row_end)
+        import torch
+        P = self.sim.pairs_in_rows(row_begin, row_end)
+        d_cd = torch.zeros(P, dtype=torch.int32, device="cuda")
+        d_in = torch.zeros(P, dtype=torch.int32, device="cuda")
+        d_un = torch.zeros(P, dtype=torch.int32, device="cuda")
+        self.sim.pair_counts_rows_device(row_begin, row_end, d_cd.data_ptr(), d_in.data_ptr(), d_un.data_ptr())
+        allreduce_pair_counts(d_cd)
+        return (d_cd.cpu().numpy().astype(np.uint32), d_in.cpu().numpy().astype(np.uint32),
+                d_un.cpu().numpy().astype(np.uint32))
+
     def pairwise_distances(self, range1, range2):
         cd, it, un = self.pair_counts(range1, range2)
         return self.sim.distances_from_counts(cd, it, un)

@@ -609,7 +609,39 @@ def test_all_pairs_mode_matches_oracle():
             oi, ou = opan.pair_counts(ii, jj)
             assert (it == oi).all() and (un == ou).all()
             seen += len(ii)
-    assert seen == N * (N - 1) // 2
+        assert seen == N * (N - 1) // 2
+        # the device-generated plan of a row block must not leak into a later sampled-pair call
+        r1, r2 = sample_pairs(rng, N, 500)
+        cd, it, un = sim.pair_counts(r1, r2)
+        assert (cd == ocore.pair_counts(r1, r2)).all()
+        cd2, _, _ = sim.pair_counts_rows(30, 37)
+        assert len(cd2) == sum(N - 1 - i for i in range(30, 37))
+        assert (sim.pair_counts(r1, r2)[0] == cd).all()
+
+
+def test_all_pairs_row_blocks_larger_shape():
+    """Row blocks of the exact all-pairs mode (pair list and row-stationary groups generated on the
+    device): groups of 8 partners with ragged tails, several column chunks, empty last row."""
+    rng = np.random.default_rng(29)
+    N, L, G = 203, 70001, 40
+    core, acc = random_state(rng, N, L, G)
+    ocore, opan = ob.Population(core, True, 0), ob.Population(acc, False, 0)
+    with make(pb.Params(pop_size=N, core_size=L, pan_genes=G, core_genes=0)) as sim:
+        sim.upload(core, acc)
+        blocks = list(sim.row_blocks(6000))
+        assert blocks[0][0] == 0 and blocks[-1][1] == N - 1 and all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+        for i0, i1 in blocks[::3] + [(N - 1, N), (5, 5)]:
+            cd, it, un = sim.pair_counts_rows(i0, i1)
+            ii = np.repeat(np.arange(i0, i1, dtype=np.uint32), [N - 1 - i for i in range(i0, i1)]).astype(np.uint32)
+            jj = (np.concatenate([np.arange(i + 1, N, dtype=np.uint32) for i in range(i0, i1)])
+                  if len(ii) else np.zeros(0, np.uint32))
+            assert len(cd) == len(ii)
+            if len(ii):
+                assert (cd == ocore.pair_counts(ii, jj)).all()
+                oi, ou = opan.pair_counts(ii, jj)
+                assert (it == oi).all() and (un == ou).all()
+        with pytest.raises(pb.PansimError):
+            sim.pair_counts_rows(0, N + 1)
 
 
 def test_no_accessory_genome_and_tiny_shapes():
