@@ -40,6 +40,9 @@ def main():
     ok = (cd == wcd).all() and (it == wit).all() and (un == wun).all()
     ok = ok and (sh.download_acc() == whole.download_acc()).all() and (sh.parents() == whole.parents()).all()
     ok = ok and (sh.download_core() == whole.download_core()[:, b:e]).all()
+    acd, ait, aun = sh.pair_counts_rows(10, 40)          # exact all-pairs block, all-reduced as well
+    wacd, wait_, waun = whole.pair_counts_rows(10, 40)
+    ok = ok and (acd == wacd).all() and (ait == wait_).all() and (aun == waun).all()
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
