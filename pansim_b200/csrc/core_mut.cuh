@@ -50,7 +50,18 @@
 namespace pansim {
 
 constexpr int CM_WARPS = 8;
-constexpr int CM_STAGES = 3;
+#ifndef PANSIM_CM_STAGES
+#define PANSIM_CM_STAGES 3
+#endif
+#ifndef PANSIM_CM_CTAS
+#define PANSIM_CM_CTAS 4
+#endif
+constexpr int CM_STAGES = PANSIM_CM_STAGES;       // 2 KiB stages per warp
+constexpr int CM_CTAS_PER_SM = PANSIM_CM_CTAS;    // launch bound (register budget = 65536 / (256 * CTAs))
+// Two stages: the load of item j+1 is issued early in item j (after its Philox calls), once the bulk
+// store of item j-1 has finished reading the stage it reuses. Three stages: issued at the end of
+// item j-1, two items ahead.
+constexpr bool CM_LATE_LOAD = CM_STAGES == 2;
 constexpr int CM_THREADS = CM_WARPS * 32;
 constexpr uint32_t CM_GUIDE = 512;            // u16 guide entries (= 256 words)
 constexpr uint32_t CM_GUIDE_SHIFT = 23;
@@ -311,7 +322,8 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
     } while (0)
 
     if (lane == 0) {
-        const uint32_t pre = n_my < (uint32_t)(CM_STAGES - 1) ? n_my : (uint32_t)(CM_STAGES - 1);
+        const uint32_t ahead = CM_LATE_LOAD ? 1u : (uint32_t)(CM_STAGES - 1);
+        const uint32_t pre = n_my < ahead ? n_my : ahead;
 #pragma unroll 1
         for (uint32_t jj = 0; jj < pre; jj++) PANSIM_CM_ISSUE_LOAD();
     }
@@ -343,6 +355,10 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
             if (a.mut_nsub > 1) k += mut_count_extra(mctr, a.key, tab, a.mut_nsub, a.mut_kmax);
         }
 
+        if (CM_LATE_LOAD && lane == 0 && j + 1 < n_my) {
+            bulk_wait_read<0>();          // the store of item j-1 has left the stage item j+1 goes into
+            PANSIM_CM_ISSUE_LOAD();
+        }
         mbar_wait(&bars[s], par);
 
         if (hr_on) {
@@ -404,7 +420,7 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
             uint8_t *dst = a.new_state + (uint64_t)row * a.row_stride + (uint64_t)reg * REGION_BYTES;
             bulk_s2g(dst, sw, REGION_BYTES);
             bulk_commit();
-            if (j + CM_STAGES - 1 < n_my) {
+            if (!CM_LATE_LOAD && j + CM_STAGES - 1 < n_my) {
                 bulk_wait_read<1>();      // the store that last used stage (j-1)%S has left smem
                 PANSIM_CM_ISSUE_LOAD();
             }
@@ -422,7 +438,7 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
 // CTAs are short-lived on purpose: SM slots turn over every few tens of microseconds, so the
 // (higher-priority) accessory/selection kernels of the next generation can slip in between.
 template <bool RNG, bool DUMP>
-__global__ void __launch_bounds__(CM_THREADS, 4) core_mut_kernel(const CoreMutArgs a)
+__global__ void __launch_bounds__(CM_THREADS, CM_CTAS_PER_SM) core_mut_kernel(const CoreMutArgs a)
 {
     extern __shared__ uint8_t smem_dyn[];
     const MutSmem m = mut_smem_carve(smem_dyn, a.mut_size, a.hr_nsub ? a.hr_size : 0u);
