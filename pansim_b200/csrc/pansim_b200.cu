@@ -157,6 +157,8 @@ struct pansim_ctx {
     // SM slots: +7 % generations/s). All three give the same bits.
     int fitness_mode = 0;
     int32_t *d_num_genes = nullptr;
+    int32_t *d_inter_diag = nullptr;      // gene counts as the diagonal of the intersection matrix (select.cuh K2a)
+    bool fitness_join_pending = false;    // a fitness kernel is running on stream_aux that `stream` has not been ordered after
     double *d_tmp_a = nullptr, *d_tmp_b = nullptr, *d_weights = nullptr, *d_cum = nullptr;
     int *d_err = nullptr;                // [0] upload / selection errors, [1] recombination list overflow
     uint32_t *d_inter = nullptr;
@@ -226,6 +228,7 @@ struct pansim_ctx {
     uint32_t launches = 0;
 
     uint32_t core_grid = 0, core_items_per_warp = 1;
+    uint32_t core_items_batch = 0;        // items per warp in the device-resident batch (0 = same as core_items_per_warp)
     size_t core_smem = 0;
     int core_occupancy = 0;
 };
@@ -366,9 +369,19 @@ int check_device_flag(pansim_ctx *c, int code, const char *what)
 
 // ---- kernel group launchers (asynchronous on ctx->stream) -----------------
 
+// order `stream` after the fitness kernel that launch_competition started on the aux stream
+int join_fitness(pansim_ctx *c)
+{
+    if (!c->fitness_join_pending) return 0;
+    CU(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    c->fitness_join_pending = false;
+    return 0;
+}
+
 int launch_fitness(pansim_ctx *c, cudaStream_t st = nullptr)
 {
     if (c->fitness_valid) return 0;
+    if (int rc = join_fitness(c)) return rc;        // an earlier one still writes the same outputs
     if (!st) st = c->stream;
     const uint32_t *acc = c->acc[c->acc_cur];
     if (c->neutral)          // every ln(1 + s_j) is +0.0: the sum is +0.0, only the row popcounts are needed
@@ -392,29 +405,30 @@ int launch_competition(pansim_ctx *c)
 {
     if (c->N < 2) FAIL(c, PANSIM_ERR_INVALID, "average_distance needs pop_size >= 2");
     if (!c->d_inter) CU(c, cudaMalloc(&c->d_inter, (size_t)c->N * c->N * sizeof(uint32_t)));
-    // the fitness sum (also the row popcounts the distances need) runs beside the intersection counts
+    // the fitness sum runs on the aux stream beside the intersection counts AND the distance kernel (which
+    // takes the gene counts from the diagonal of the intersection matrix); whoever needs log-fitness or
+    // d_num_genes joins it (join_fitness)
     FineSpan *fs = new FineSpan(c, TG_D_INTER);
-    const bool fork = !c->fitness_valid;
-    if (fork) {
+    if (!c->fitness_valid) {
         CU(c, cudaEventRecord(c->ev_fork, c->stream));
         CU(c, cudaStreamWaitEvent(c->stream_aux, c->ev_fork, 0));
         if (launch_fitness(c, c->stream_aux)) return PANSIM_ERR_CUDA;
         CU(c, cudaEventRecord(c->ev_join, c->stream_aux));
+        c->fitness_join_pending = true;
     }
     if (c->inter_popc) {     // PANSIM_INTER_POPC=1: the AND/popcount tile kernel instead of the tensor-core one
         const uint32_t nb = div_up64(c->N, 32);
         acc_inter_kernel<<<dim3(nb, nb), 256, 0, c->stream>>>(c->acc[c->acc_cur], c->N, c->acc_stride_words,
-                                                              c->acc_words, c->d_inter);
+                                                              c->acc_words, c->d_inter, c->d_inter_diag);
     } else {
         const uint32_t nb = div_up64(c->N, IM_TILE);
         acc_inter_mma_kernel<<<nb * (nb + 1) / 2, 256, 0, c->stream>>>(c->acc[c->acc_cur], c->N, c->acc_stride_words,
-                                                                  c->acc_words, c->d_inter);
+                                                                  c->acc_words, c->d_inter, c->d_inter_diag);
     }
     LAUNCH_CHECK(c);
-    if (fork) CU(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
     delete fs;
     FineSpan fs2(c, TG_D_AVG);
-    avg_distance_kernel<<<div_up64(c->N, AVG_WARPS), AVG_WARPS * 32, 0, c->stream>>>(c->d_inter, c->d_num_genes, c->N,
+    avg_distance_kernel<<<div_up64(c->N, AVG_WARPS), AVG_WARPS * 32, 0, c->stream>>>(c->d_inter, c->d_inter_diag, c->N,
                                                                     c->cfg.core_genes, c->d_avgdist);
     LAUNCH_CHECK(c);
     c->avgdist_valid = true;
@@ -424,6 +438,7 @@ int launch_competition(pansim_ctx *c)
 int launch_select(pansim_ctx *c, uint32_t gen, bool use_avgdist)
 {
     if (launch_fitness(c)) return PANSIM_ERR_CUDA;
+    if (int rc = join_fitness(c)) return rc;
     SelectArgs a;
     a.logfit = c->d_logfit;
     a.num_genes = c->d_num_genes;
@@ -477,6 +492,7 @@ void fill_acc_args(pansim_ctx *c, AccArgs &a, uint32_t gen)
 int launch_acc_step(pansim_ctx *c, uint32_t gen)
 {
     if (c->G == 0) return 0;
+    if (int rc = join_fitness(c)) return rc;        // it reads the accessory buffers this step recycles
     AccArgs a;
     fill_acc_args(c, a, gen);
     const uint32_t rows_per_cta = 8;
@@ -522,7 +538,7 @@ void fill_core_args(pansim_ctx *c, CoreMutArgs &a, uint32_t gen)
     a.n_regions = c->n_regions;
     a.row_stride = c->core_stride;
     a.region0 = c->region0;
-    a.items_per_warp = c->core_items_per_warp;
+    a.items_per_warp = (!c->pdl_now && c->core_items_batch) ? c->core_items_batch : c->core_items_per_warp;
     a.site_limit = c->site_end;
     a.key = make_uint2((uint32_t)c->cfg.seed, (uint32_t)(c->cfg.seed >> 32));
     a.rk = philox_key_schedule(a.key);
@@ -617,12 +633,14 @@ int launch_core_step(pansim_ctx *c, uint32_t gen, bool rng, cudaStream_t st)
         if (int rc = core_materialize(c, st)) return rc;
     CoreMutArgs a;
     fill_core_args(c, a, gen);
+    const uint64_t per_cta = (uint64_t)CM_WARPS * a.items_per_warp;
+    const uint32_t grid = (uint32_t)std::max<uint64_t>(1, ((uint64_t)c->N * c->n_regions + per_cta - 1) / per_cta);
     if (!rng || (!a.mut_nsub && !a.hr_nsub))
-        core_mut_kernel<false, false><<<c->core_grid, CM_THREADS, c->core_smem, st>>>(a);
+        core_mut_kernel<false, false><<<grid, CM_THREADS, c->core_smem, st>>>(a);
     else if (c->dump_enabled)
-        core_mut_kernel<true, true><<<c->core_grid, CM_THREADS, c->core_smem, st>>>(a);
+        core_mut_kernel<true, true><<<grid, CM_THREADS, c->core_smem, st>>>(a);
     else
-        core_mut_kernel<true, false><<<c->core_grid, CM_THREADS, c->core_smem, st>>>(a);
+        core_mut_kernel<true, false><<<grid, CM_THREADS, c->core_smem, st>>>(a);
     LAUNCH_CHECK(c);
     c->core_cur ^= 1;
     c->hr_pending = false;
@@ -733,7 +751,7 @@ void pansim_destroy(pansim_ctx *c)
     if (c->stream_core) cudaStreamSynchronize(c->stream_core);
     if (c->stream_aux) cudaStreamSynchronize(c->stream_aux);
     void *ptrs[] = {c->core[0], c->core[1], c->d_hr_slots, c->d_hr_counts, c->d_hr_ovf, c->d_hr_ovf_count, c->d_core_img, c->acc[0], c->acc[1], c->d_parents_buf[0], c->d_parents_buf[1], c->d_parents_buf[2], c->d_lw, c->d_lethal, c->d_logfit, c->d_avgdist,
-                    c->d_num_genes, c->d_tmp_a, c->d_tmp_b, c->d_weights, c->d_cum, c->d_err, c->d_inter, c->d_rowInvK, c->d_gain_planes,
+                    c->d_num_genes, c->d_inter_diag, c->d_tmp_a, c->d_tmp_b, c->d_weights, c->d_cum, c->d_err, c->d_inter, c->d_rowInvK, c->d_gain_planes,
                     c->d_gain_thr, c->tab_mut.d_thr, c->tab_hr.d_thr, c->d_r1, c->d_r2, c->d_cd, c->d_in, c->d_un,
                     c->d_replay, c->d_hkeys, c->d_hvals, c->d_stage, c->d_groups, c->d_partner, c->d_orig, c->d_batches, c->d_tile_slots, c->d_tile_orig, c->d_dump_counters, c->d_mut_row, c->d_mut_site,
                     c->d_mut_seq, c->d_mut_allele, c->d_hr_rec, c->d_hr_locus, c->d_hr_donor, c->d_hr_seq,
@@ -901,6 +919,7 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
         CU(c, cudaMalloc(&c->d_logfit, n * 8));
         CU(c, cudaMalloc(&c->d_avgdist, n * 8));
         CU(c, cudaMalloc(&c->d_num_genes, n * 4));
+        CU(c, cudaMalloc(&c->d_inter_diag, n * 4));
         CU(c, cudaMalloc(&c->d_tmp_a, n * 8));
         CU(c, cudaMalloc(&c->d_tmp_b, n * 8));
         CU(c, cudaMalloc(&c->d_weights, n * 8));
@@ -934,6 +953,11 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
             c->core_items_per_warp = (uint32_t)std::max<uint64_t>(1, (items + ctas * CM_WARPS - 1) / (ctas * CM_WARPS));
         }
         if (const char *e = getenv("PANSIM_CORE_ITEMS_PER_WARP")) c->core_items_per_warp = (uint32_t)std::max(1, atoi(e));
+        // In the device-resident batch nobody waits on the selection chain, so the CTAs may live longer
+        // (measured at cfg2: 3 -> 12 items per warp, +2 % generations/s; through the host-driven calls the
+        // same change costs 12 % because the chain kernels queue longer for SM slots).
+        c->core_items_batch = std::max(c->core_items_per_warp, 12u);
+        if (const char *e = getenv("PANSIM_CORE_ITEMS_BATCH")) c->core_items_batch = (uint32_t)std::max(0, atoi(e));
         const uint64_t per_cta = (uint64_t)CM_WARPS * c->core_items_per_warp;
         c->core_grid = (uint32_t)std::max<uint64_t>(1, (items + per_cta - 1) / per_cta);
         if (c->tab_hr.nsub && core_bytes && c->hr_smem > 48 * 1024) {
@@ -1033,6 +1057,7 @@ int pansim_upload_acc(pansim_ctx *c, const uint8_t *bytes)
 {
     if (!c || (!bytes && c->G)) return PANSIM_ERR_INVALID;
     CU(c, cudaSetDevice(c->cfg.device));
+    if (int rc = join_fitness(c)) return rc;
     if (c->G) {
         if (int rc = ensure_stage(c, (size_t)c->N * c->G)) return rc;
         CU(c, cudaMemcpyAsync(c->d_stage, bytes, (size_t)c->N * c->G, cudaMemcpyHostToDevice, c->stream));
@@ -1135,6 +1160,7 @@ int pansim_set_selection(pansim_ctx *c, const double *s)
     if (!c || (!s && c->G)) return PANSIM_ERR_INVALID;
     CU(c, cudaSetDevice(c->cfg.device));
     if (c->G == 0) return 0;
+    if (int rc = join_fitness(c)) return rc;
     std::vector<double> lw(c->G);
     bool neutral = true;
     for (uint32_t j = 0; j < c->G; j++) {
@@ -1206,6 +1232,7 @@ int pansim_get_weights(pansim_ctx *c, double *weights, int32_t *num_genes, doubl
 {
     if (!c) return PANSIM_ERR_INVALID;
     CU(c, cudaSetDevice(c->cfg.device));
+    if (int rc = join_fitness(c)) return rc;
     if (weights) CU(c, cudaMemcpyAsync(weights, c->d_weights, (size_t)c->N * 8, cudaMemcpyDeviceToHost, c->stream));
     if (num_genes) CU(c, cudaMemcpyAsync(num_genes, c->d_num_genes, (size_t)c->N * 4, cudaMemcpyDeviceToHost, c->stream));
     if (logfit) CU(c, cudaMemcpyAsync(logfit, c->d_logfit, (size_t)c->N * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -1274,6 +1301,7 @@ int pansim_next_generation(pansim_ctx *c, const uint32_t *parents)
     if (int rc = next_parents_buffer(c)) return rc;
     if (int rc = upload_parents(c, parents)) return rc;
     timing_begin(c);
+    if (int rc = join_fitness(c)) return rc;
     if (c->G) {
         const uint64_t total = (uint64_t)c->N * c->acc_stride_words;
         acc_gather_kernel<<<div_up64(total, 256), 256, 0, c->stream>>>(c->acc[c->acc_cur], c->acc[c->acc_cur ^ 1], c->d_parents, c->N, c->acc_stride_words);

@@ -278,7 +278,7 @@ constexpr int INTER_CHUNK = 32;   // words per shared-memory chunk
 
 __global__ void __launch_bounds__(256) acc_inter_kernel(const uint32_t *acc, uint32_t n_rows,
                                                         uint32_t stride_words, uint32_t n_words,
-                                                        uint32_t *inter)
+                                                        uint32_t *inter, int32_t *diag)
 {
     const uint32_t bi = blockIdx.y, bj = blockIdx.x;
     if (bj < bi) return;
@@ -307,6 +307,7 @@ __global__ void __launch_bounds__(256) acc_inter_kernel(const uint32_t *acc, uin
         if (i < n_rows && j < n_rows) {
             inter[(uint64_t)i * n_rows + j] = acc4[q];
             inter[(uint64_t)j * n_rows + i] = acc4[q];
+            if (i == j) diag[i] = (int32_t)acc4[q];           // |row_i|: the gene count the distances need
         }
     }
 }
@@ -318,7 +319,9 @@ __global__ void __launch_bounds__(256) acc_inter_kernel(const uint32_t *acc, uin
 // both operands agree, so the expansion is the cheapest one: the thread with t = lane % 4 takes
 // bits {t, t+8, t+16, t+24} ((w >> t) & 0x01010101) for the low k half of the fragment and bits
 // {t+4, ...} for the high half -- over t = 0..3 every bit of the word exactly once.
-// CTA = 64 x 64 pairs, 8 warps of 16 x 32; upper-triangle tiles only, mirrored on store.
+// CTA = 64 x 64 pairs, 8 warps of 16 x 32; upper-triangle tiles only, mirrored on store. The
+// diagonal I[i][i] = |row_i| is also written as a compact vector: the distance kernel takes its
+// gene counts from there, so it does not have to wait for the (much longer) fitness kernel.
 constexpr int IM_TILE = 64;
 constexpr int IM_CHUNK = 32;      // words per shared-memory chunk
 
@@ -332,7 +335,7 @@ __device__ __forceinline__ void imma_16832_u8(int (&c)[4], uint32_t a0, uint32_t
 
 __global__ void __launch_bounds__(256) acc_inter_mma_kernel(const uint32_t *acc, uint32_t n_rows,
                                                             uint32_t stride_words, uint32_t n_words,
-                                                            uint32_t *inter)
+                                                            uint32_t *inter, int32_t *diag)
 {
     // blockIdx.x enumerates the upper-triangle tiles row by row: (0,0..nb-1), (1,1..nb-1), ...
     const uint32_t nb = (n_rows + IM_TILE - 1) / IM_TILE;
@@ -383,6 +386,7 @@ __global__ void __launch_bounds__(256) acc_inter_mma_kernel(const uint32_t *acc,
             if (i < n_rows && j < n_rows) {
                 inter[(uint64_t)i * n_rows + j] = (uint32_t)c[n][q];
                 inter[(uint64_t)j * n_rows + i] = (uint32_t)c[n][q];
+                if (i == j) diag[i] = c[n][q];                // |row_i|: the gene count the distances need
             }
         }
 }
