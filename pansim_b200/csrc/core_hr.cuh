@@ -106,8 +106,14 @@ __device__ __forceinline__ HrEvent hr_event(uint32_t greg, uint32_t row, uint32_
     const uint4 r = philox4x32_10(make_uint4(greg, row, gen, HR_EVENT_W0 + e), key);
     HrEvent ev;
     ev.pos = r.x >> 19;                                                                   // uniform site of the region
-    ev.donor = (uint32_t)__umul64hi(((uint64_t)r.y << 32) | r.z, (uint64_t)n_other);      // bias <= N / 2^64
-    ev.donor += ev.donor >= row ? 1u : 0u;
+    // uniform on the other N - 1 rows: multiply-high of a 32-bit word with Lemire's rejection test; a
+    // rejected word (probability < N / 2^32) is replaced by the next one (residual bias < (N / 2^32)^2)
+    uint64_t m = (uint64_t)r.y * n_other;
+    if ((uint32_t)m < n_other) {
+        if ((uint32_t)m < (0u - n_other) % n_other) m = (uint64_t)r.z * n_other;
+    }
+    ev.donor = (uint32_t)(m >> 32);
+    ev.donor += ev.donor >= row ? 1u : 0u;                                                // population.rs:616-619
     ev.w = r.w;
     return ev;
 }

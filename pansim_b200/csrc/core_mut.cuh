@@ -81,6 +81,7 @@ struct CoreMutArgs {
     uint32_t region0;         // global index of local region 0
     uint32_t items_per_warp;
     uint64_t site_limit;      // global site index one past the last valid site of this shard
+    uint32_t last_greg, lim_last;   // the region that holds site_limit - 1 and its number of valid sites (1..8192)
     uint2 key;
     PhiloxKeys rk;            // round keys of `key`
     uint32_t gen;
@@ -171,7 +172,11 @@ struct MutChunk {
         const bool rej = d >= 243u;
         uint32_t v = rej ? (res & 255u) : d;
         res = rej ? __funnelshift_r(res, 0xFFFFFFFFu, 8) : res;
-        if (v >= 243u) v = mut_digit_fallback(ctr, key, ev0 >> 2);
+        if (v >= 243u) {                              // a second reserve byte before the (costly) fallback call
+            v = res & 255u;
+            res = __funnelshift_r(res, 0xFFFFFFFFu, 8);
+            if (v >= 243u) v = mut_digit_fallback(ctr, key, ev0 >> 2);
+        }
         uint32_t c0, c1, c2, c3;
         asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(c0), "=r"(c1), "=r"(c2), "=r"(c3) : "r"(lut_s + v * 16u));
         const uint32_t cc[4] = {c0, c1, c2, c3};
@@ -214,8 +219,7 @@ __device__ __forceinline__ HrWindow hr_window_fetch(const CoreMutArgs &a, const 
                                                     uint32_t lane, uint32_t base, uint32_t K_known)
 {
     const uint32_t greg = a.region0 + reg;
-    const uint64_t rem_sites = a.site_limit - (uint64_t)greg * REGION_SITES;
-    const uint32_t lim = rem_sites < REGION_SITES ? (uint32_t)rem_sites : REGION_SITES;
+    const uint32_t lim = greg == a.last_greg ? a.lim_last : REGION_SITES;
     const HrEvent ev = hr_event(greg, prow, a.hr_gen, a.rk, base + lane, a.n_rows - 1u);
     HrWindow h;
     h.K = K_known;
@@ -340,9 +344,8 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
 
         // RNG work that does not need the data is done before waiting for the TMA load
         const uint32_t greg = a.region0 + reg;
-        const uint64_t reg_site0 = (uint64_t)greg * REGION_SITES;
-        const uint64_t rem_sites = a.site_limit - reg_site0;
-        const uint32_t lim = rem_sites < REGION_SITES ? (uint32_t)rem_sites : REGION_SITES;
+        const uint64_t reg_site0 = (uint64_t)greg * REGION_SITES;          // event dump only
+        const uint32_t lim = greg == a.last_greg ? a.lim_last : REGION_SITES;
         const uint4 mctr = make_ctr(greg * 32u + lane, row, a.gen, STREAM_CORE_MUT);
         uint4 c0 = make_uint4(0, 0, 0, 0), c1 = make_uint4(0, 0, 0, 0);
         uint32_t k = 0;

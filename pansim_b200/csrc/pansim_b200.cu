@@ -540,6 +540,8 @@ void fill_core_args(pansim_ctx *c, CoreMutArgs &a, uint32_t gen)
     a.region0 = c->region0;
     a.items_per_warp = (!c->pdl_now && c->core_items_batch) ? c->core_items_batch : c->core_items_per_warp;
     a.site_limit = c->site_end;
+    a.last_greg = (uint32_t)((c->site_end - 1) / REGION_SITES);
+    a.lim_last = (uint32_t)(c->site_end - (uint64_t)a.last_greg * REGION_SITES);
     a.key = make_uint2((uint32_t)c->cfg.seed, (uint32_t)(c->cfg.seed >> 32));
     a.rk = philox_key_schedule(a.key);
     a.gen = gen;
@@ -954,9 +956,9 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
         }
         if (const char *e = getenv("PANSIM_CORE_ITEMS_PER_WARP")) c->core_items_per_warp = (uint32_t)std::max(1, atoi(e));
         // In the device-resident batch nobody waits on the selection chain, so the CTAs may live longer
-        // (measured at cfg2: 3 -> 12 items per warp, +2 % generations/s; through the host-driven calls the
+        // (measured at cfg2: 3 -> 8 items per warp, +1.6 % generations/s; 12 makes the chain the critical path; through the host-driven calls the
         // same change costs 12 % because the chain kernels queue longer for SM slots).
-        c->core_items_batch = std::max(c->core_items_per_warp, 12u);
+        c->core_items_batch = std::max(c->core_items_per_warp, 8u);
         if (const char *e = getenv("PANSIM_CORE_ITEMS_BATCH")) c->core_items_batch = (uint32_t)std::max(0, atoi(e));
         const uint64_t per_cta = (uint64_t)CM_WARPS * c->core_items_per_warp;
         c->core_grid = (uint32_t)std::max<uint64_t>(1, (items + per_cta - 1) / per_cta);
