@@ -43,6 +43,7 @@ constexpr uint32_t HR_APPLY_ITEMS = 32;                  // items per apply task
 struct HrArgs {
     uint32_t *state;          // packed core rows (gathered + mutated), words
     uint32_t n_rows, n_regions, region0;
+    uint32_t lemire_t;        // 2^32 mod (n_rows - 1): rejection threshold of the donor draw
     uint64_t row_stride_words;
     uint64_t site_limit;
     uint2 key;
@@ -74,11 +75,11 @@ static inline size_t hr_collect_smem_bytes(uint32_t tab_words)
 __device__ __forceinline__ uint32_t hr_count_from_uniform(const uint32_t *thr, uint32_t size, uint32_t kmax, uint32_t u,
                                                           uint32_t lane)
 {
+    // size is a multiple of 32 (host pads with 0xFFFFFFFF; those only compare <= u for u = 2^32 - 1,
+    // which the cap at kmax absorbs)
     uint32_t k = 0;
-    for (uint32_t j0 = 0; j0 < size; j0 += 32) {
-        const uint32_t j = j0 + lane;
-        k += (uint32_t)__popc(__ballot_sync(0xffffffffu, j < size && thr[j] <= u));
-    }
+#pragma unroll 1
+    for (uint32_t j0 = 0; j0 < size; j0 += 32) k += (uint32_t)__popc(__ballot_sync(0xffffffffu, thr[j0 + lane] <= u));
     return min(k, kmax);
 }
 
@@ -101,7 +102,8 @@ __device__ __noinline__ uint32_t hr_count_extra(uint32_t greg, uint32_t row, uin
 // event e of item (global region greg, row): site of the region and donor row (population.rs:616-619)
 struct HrEvent { uint32_t pos, donor, w; };
 template <typename Key>      // uint2 key or precomputed PhiloxKeys
-__device__ __forceinline__ HrEvent hr_event(uint32_t greg, uint32_t row, uint32_t gen, const Key &key, uint32_t e, uint32_t n_other)
+__device__ __forceinline__ HrEvent hr_event(uint32_t greg, uint32_t row, uint32_t gen, const Key &key, uint32_t e, uint32_t n_other,
+                                            uint32_t lemire_t)      // lemire_t = 2^32 mod n_other (host)
 {
     const uint4 r = philox4x32_10(make_uint4(greg, row, gen, HR_EVENT_W0 + e), key);
     HrEvent ev;
@@ -110,7 +112,7 @@ __device__ __forceinline__ HrEvent hr_event(uint32_t greg, uint32_t row, uint32_
     // rejected word (probability < N / 2^32) is replaced by the next one (residual bias < (N / 2^32)^2)
     uint64_t m = (uint64_t)r.y * n_other;
     if ((uint32_t)m < n_other) {
-        if ((uint32_t)m < (0u - n_other) % n_other) m = (uint64_t)r.z * n_other;
+        if ((uint32_t)m < lemire_t) m = (uint64_t)r.z * n_other;
     }
     ev.donor = (uint32_t)(m >> 32);
     ev.donor += ev.donor >= row ? 1u : 0u;                                                // population.rs:616-619
@@ -150,7 +152,7 @@ __device__ __forceinline__ void hr_collect_item(const HrArgs &a, uint32_t *claim
         uint32_t pos = 0, donor = 0;
         bool valid = false;
         if (e < K) {
-            const HrEvent ev = hr_event(greg, row, a.gen, a.key, e, n_other);
+            const HrEvent ev = hr_event(greg, row, a.gen, a.key, e, n_other, a.lemire_t);
             pos = ev.pos; donor = ev.donor;
             valid = pos < lim;                                                 // ragged last region: thinned away
         }
@@ -216,7 +218,7 @@ __device__ __forceinline__ void hr_collect_task(const HrArgs &a, const uint32_t 
         const uint32_t row = q * R + i;
         K[i] = 0; pos[i] = 0; donor[i] = 0;
         if (row < a.n_rows) {
-            const HrEvent ev = hr_event(greg, row, a.gen, a.key, lane, n_other);      // first window: event `lane`
+            const HrEvent ev = hr_event(greg, row, a.gen, a.key, lane, n_other, a.lemire_t);      // first window: event `lane`
             pos[i] = ev.pos; donor[i] = ev.donor;
             K[i] = hr_count_from_uniform(tab, a.tab_words, a.kmax, __shfl_sync(0xffffffffu, ev.w, 0), lane);   // warp-uniform
             if (a.nsub > 1) K[i] += hr_count_extra(greg, row, a.gen, a.key, tab, a.tab_words, a.nsub, a.kmax, lane);

@@ -92,6 +92,7 @@ struct CoreMutArgs {
     uint32_t mut_size, mut_nsub, mut_kmax;
     // recombination events of generation hr_gen still pending on old_state (hr_nsub = 0: none)
     uint32_t hr_size, hr_nsub, hr_kmax, hr_gen;
+    uint32_t hr_lemire_t;     // 2^32 mod (n_rows - 1), see hr_event
     // optional event dump (parity instrumentation)
     uint32_t *dump_counters;  // [0] = SNP events
     uint32_t dump_cap;
@@ -220,7 +221,7 @@ __device__ __forceinline__ HrWindow hr_window_fetch(const CoreMutArgs &a, const 
 {
     const uint32_t greg = a.region0 + reg;
     const uint32_t lim = greg == a.last_greg ? a.lim_last : REGION_SITES;
-    const HrEvent ev = hr_event(greg, prow, a.hr_gen, a.rk, base + lane, a.n_rows - 1u);
+    const HrEvent ev = hr_event(greg, prow, a.hr_gen, a.rk, base + lane, a.n_rows - 1u, a.hr_lemire_t);
     HrWindow h;
     h.K = K_known;
     if (base == 0u) {

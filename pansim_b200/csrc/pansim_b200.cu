@@ -546,7 +546,8 @@ void fill_core_args(pansim_ctx *c, CoreMutArgs &a, uint32_t gen)
     a.rk = philox_key_schedule(a.key);
     a.gen = gen;
     a.const_img = c->d_core_img; a.mut_size = c->tab_mut.size; a.mut_nsub = c->tab_mut.nsub; a.mut_kmax = c->tab_mut.kmax;
-    a.hr_size = c->tab_hr.size; a.hr_kmax = c->tab_hr.kmax; a.hr_gen = c->hr_pending_gen;
+    a.hr_size = c->tab_hr.size;
+    a.hr_lemire_t = c->N > 1 ? (uint32_t)((1ull << 32) % (c->N - 1)) : 0u; a.hr_kmax = c->tab_hr.kmax; a.hr_gen = c->hr_pending_gen;
     a.hr_nsub = c->hr_pending ? c->tab_hr.nsub : 0u;
     a.dump_counters = c->d_dump_counters;
     a.dump_cap = c->dump_cap;
@@ -559,6 +560,7 @@ void fill_hr_args(pansim_ctx *c, HrArgs &h, uint32_t gen, uint8_t *state)
     h.state = reinterpret_cast<uint32_t *>(state);
     h.n_rows = c->N;
     h.n_regions = c->n_regions;
+    h.lemire_t = c->N > 1 ? (uint32_t)((1ull << 32) % (c->N - 1)) : 0u;
     h.region0 = c->region0;
     h.row_stride_words = c->core_stride / 4;
     h.site_limit = c->site_end;
@@ -841,6 +843,7 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
         c->p_hr_site = -std::expm1(-rate_hr);
         build_poisson_table(rate_mut * BLOCK_SITES, c->tab_mut);
         build_poisson_table(rate_hr * REGION_SITES, c->tab_hr);
+        if (c->tab_hr.size < 32) { c->tab_hr.size = 32; c->tab_hr.thr.resize(32, 0xFFFFFFFFu); }      // whole warps of thresholds (core_hr.cuh)
         if ((double)c->tab_hr.nsub * c->tab_hr.kmax > 1.5e7) FAIL(c, PANSIM_ERR_INVALID, "recombination rate too high (more than ~1e7 events per 8192-site region)");
         {
             // constant image of the core kernel: allele-digit table, SNP count table, recombination thresholds
