@@ -40,7 +40,7 @@ PEAK_FALLBACK_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
 # events pending) from the committed ncu --set full capture (profiles/r01_core_mut_ncu_summary.txt),
 # per launch at this workload. ncu counts 54 MB of reads against 300 MB of algorithmic reads for
 # this kernel (bulk-copy loads); the write side (249 MB) matches.
-NCU_CORE_STEP_DRAM_BYTES = 303.1e6
+NCU_CORE_STEP_DRAM_BYTES = 299.9e6
 
 
 def selection_coefficients(rng, n, prop_positive, pos_lambda=10.0, neg_lambda=10.0):
