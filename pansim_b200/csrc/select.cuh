@@ -149,13 +149,17 @@ __global__ void __launch_bounds__(FIT_ROWS * 64) fitness_kernel(const uint32_t *
 // (population.rs:312-318).
 constexpr int FITL_THREADS = 128;
 
-// sum += x iff (bits & mask). Written as an unconditional add of (bit ? x : +0.0): the selection of
-// the operand is off the dependent chain (x and bits are known ahead), so the chain is one DADD per
-// position; and x + (+0.0) = x exactly, because the running sum starts at +0.0 and can never
-// become -0.0.
+// sum += x iff (bits & mask). Written as the fused multiply-add sum = x * b + sum with b = 1.0 or +0.0
+// built from the bit (one select for the high word of b; the low word is zero): x * 1.0 = x and
+// x * 0.0 = +-0.0 are exact, so the single rounding of the FMA is the rounding of the plain addition,
+// and sum + (+-0.0) = sum because the running sum starts at +0.0 and can never become -0.0. The
+// operand selection is off the dependent chain (x and bits are known ahead): one DFMA per position.
 __device__ __forceinline__ void add_if_bit(double &sum, double x, uint32_t bits, uint32_t mask)
 {
-    sum += (bits & mask) ? x : 0.0;
+    int hi;
+    asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tand.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\tselp.b32 %0, 0x3FF00000, 0, p;\n\t}"
+        : "=r"(hi) : "r"(bits), "r"(mask));
+    sum = fma(x, __hiloint2double(hi, 0), sum);
 }
 
 __global__ void __launch_bounds__(FITL_THREADS) fitness_lane_kernel(const uint32_t *acc, uint32_t n_rows,
