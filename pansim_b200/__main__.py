@@ -4,7 +4,7 @@ Same long flags (underscores, capitalised --HR_rate / --HGT_rate), same defaults
 same parsing quirks: pop_size/core_size/pan_genes/core_genes/n_gen are parsed as
 f64 and rounded (main.rs:155-167) so `--pop_size 1e3` works; max_distances,
 threads and seed are parsed as integers (main.rs:169, 177, 180). --threads is
-accepted and ignored (the work runs on the GPU). Extra flag: --device.
+accepted and ignored (the work runs on the GPU). Extra flags: --device, --all_pairs.
 """
 from __future__ import annotations
 
@@ -53,14 +53,17 @@ def build_parser() -> argparse.ArgumentParser:
     ap.add_argument("--genome_size_penalty", type=float, default=d.genome_size_penalty)
     ap.add_argument("--competition_strength", type=float, default=d.competition_strength)
     ap.add_argument("--device", type=int, default=0, help="(extension) CUDA device ordinal")
+    ap.add_argument("--all_pairs", action="store_true",
+                    help="(extension) <outpref>.tsv holds every pair i < j in (i, j) order instead of max_distances sampled pairs")
     return ap
 
 
 def main(argv=None) -> int:
     ns = vars(build_parser().parse_args(argv))
     device = ns.pop("device")
+    all_pairs = ns.pop("all_pairs")
     p = Params(**ns)
-    run(p, outpref=p.outpref, device=device)
+    run(p, outpref=p.outpref, device=device, all_pairs=all_pairs)
     return 0                       # the reference exits 0 even when validation fails (main.rs:195-247)
 
 

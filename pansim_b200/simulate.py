@@ -63,8 +63,10 @@ class RunResult:
     stdout: list = field(default_factory=list)
 
 
-def run(p: Params, outpref: str | None = None, device: int = 0, out=None) -> RunResult | None:
-    """main.rs:15-564. Returns None where the reference prints a validation message and exits 0."""
+def run(p: Params, outpref: str | None = None, device: int = 0, out=None, all_pairs: bool = False) -> RunResult | None:
+    """main.rs:15-564. Returns None where the reference prints a validation message and exits 0.
+    all_pairs (extension, BASELINE config 5): `<outpref>.tsv` holds the distances of every pair i < j
+    in (i, j) order instead of the max_distances sampled pairs; res.core/acc_distances stay None."""
     out = out or sys.stdout
     msgs = validate(p)
     if msgs:
@@ -89,21 +91,32 @@ def run(p: Params, outpref: str | None = None, device: int = 0, out=None) -> Run
     with Pansim.from_params(p, device=device) as sim:
         sim.set_initial(core_row, acc_row)
         sim.set_selection(sel)
-        for j in range(p.n_gen):                                                 # main.rs:429
+        # nothing is read back between generations unless --print_dist / --verbose ask for it: the whole
+        # run is then one device-resident batch (same states, tests/test_gpu_parity.py)
+        batched = not p.print_dist and not p.verbose and p.n_gen > 1
+        if batched:
+            sim.run_generations(0, p.n_gen - 1)
+        for j in range(p.n_gen - 1 if batched else 0, p.n_gen):                  # main.rs:429
             sim.step(j)                                                          # main.rs:435-464
             if j == p.n_gen - 1:                                                 # main.rs:467-499
-                res.core_distances, res.acc_distances = sim.pairwise_distances(r1, r2)
+                if not all_pairs:
+                    res.core_distances, res.acc_distances = sim.pairwise_distances(r1, r2)
                 res.gene_freqs = sim.gene_frequencies()
                 if outpref:
                     with open(outpref + ".tsv", "w") as f:
-                        f.write("".join(f"{fmt_f64(float(c))}\t{fmt_f64(float(a))}\n"
-                                        for c, a in zip(res.core_distances, res.acc_distances)))
+                        if all_pairs:
+                            for _, _, cd_, it_, un_ in sim.iter_all_pairs(with_indices=False):
+                                c_, a_ = sim.distances_from_counts(cd_, it_, un_)
+                                f.write("".join(f"{fmt_f64(float(c))}\t{fmt_f64(float(a))}\n" for c, a in zip(c_, a_)))
+                        else:
+                            f.write("".join(f"{fmt_f64(float(c))}\t{fmt_f64(float(a))}\n"
+                                            for c, a in zip(res.core_distances, res.acc_distances)))
                     with open(outpref + "_freqs.txt", "w") as f:
                         f.write("".join(fmt_f64(float(x)) + "\n" for x in res.gene_freqs))
             if p.print_dist:                                                     # main.rs:502-519
                 # the reference recomputes both passes here even on the last generation;
                 # the result is identical, so the last one is reused
-                if j == p.n_gen - 1:
+                if j == p.n_gen - 1 and not all_pairs:
                     cd, ad = res.core_distances, res.acc_distances
                 else:
                     cd, ad = sim.pairwise_distances(r1, r2)

@@ -126,3 +126,28 @@ def test_same_seed_same_result_and_device_runs_are_reproducible():
     b = simulate.run(pb.Params(**kw))
     assert (a.core_distances == b.core_distances).all() and (a.acc_distances == b.acc_distances).all()
     assert (a.gene_freqs == b.gene_freqs).all()
+
+
+def test_all_pairs_extension_and_batched_run(tmp_path):
+    """--all_pairs (extension for BASELINE config 5): <outpref>.tsv holds every pair i < j in (i, j)
+    order. Without --print_dist / --verbose the host runs the generations as one device-resident
+    batch; the matrices it writes must equal those of the generation-by-generation run."""
+    kw = dict(pop_size=23, core_size=700, pan_genes=90, core_genes=10, n_gen=4, max_distances=40, seed=11,
+              print_matrices=True)
+    pa, pb_ = str(tmp_path / "a"), str(tmp_path / "b")
+    simulate.run(pb.Params(**kw), outpref=pa, all_pairs=True)                      # batched, all pairs
+    simulate.run(pb.Params(print_dist=True, **kw), outpref=pb_)                    # per-generation loop, sampled pairs
+    assert open(pa + "_core_genome.csv").read() == open(pb_ + "_core_genome.csv").read()
+    assert open(pa + "_pangenome.csv").read() == open(pb_ + "_pangenome.csv").read()
+    letters = np.array([l.split(",") for l in open(pa + "_core_genome.csv").read().splitlines()])
+    pan = np.array([l.split(",") for l in open(pa + "_pangenome.csv").read().splitlines()]).astype(int)[:, 10:]
+    rows = [l.split("\t") for l in open(pa + ".tsv").read().splitlines()]
+    assert len(rows) == 23 * 22 // 2
+    k = 0
+    for i in range(23):
+        for j in range(i + 1, 23):
+            core_d = (letters[i] != letters[j]).sum() / 700
+            inter, uni = (pan[i] & pan[j]).sum(), (pan[i] | pan[j]).sum()
+            acc_d = 1.0 - ((inter + 10.0) / (uni + 10.0))
+            assert rows[k][0] == pb.fmt_f64(float(core_d)) and rows[k][1] == pb.fmt_f64(float(acc_d))
+            k += 1
