@@ -41,7 +41,8 @@ const char *VALUE_FLAGS[] = {"pop_size", "core_size", "pan_genes", "core_genes",
                              "max_distances", "core_mu", "HR_rate", "HGT_rate", "rate_genes1", "rate_genes2",
                              "prop_genes2", "prop_positive", "pos_lambda", "neg_lambda", "seed", "outpref",
                              "threads", "genome_size_penalty", "competition_strength", "device"};
-const char *SWITCH_FLAGS[] = {"print_dist", "print_matrices", "print_selection", "verbose", "no_control_genome_size"};
+const char *SWITCH_FLAGS[] = {"print_dist", "print_matrices", "print_selection", "verbose", "no_control_genome_size",
+                              "all_pairs"};   // all_pairs: extension (every pair i < j in <outpref>.tsv)
 
 bool parse(int argc, char **argv, Flags &f)
 {
@@ -123,6 +124,7 @@ int main(int argc, char **argv)
     const double pos_lambda = as_f64(fl, "pos_lambda"), neg_lambda = as_f64(fl, "neg_lambda");
     const uint64_t seed = std::strtoull(fl.val["seed"].c_str(), nullptr, 10);
     const bool verbose = fl.sw["verbose"], print_dist = fl.sw["print_dist"], print_matrices = fl.sw["print_matrices"];
+    const bool all_pairs = fl.sw["all_pairs"];
     const bool print_selection = fl.sw["print_selection"], no_control = fl.sw["no_control_genome_size"];
     const double genome_size_penalty = as_f64(fl, "genome_size_penalty"), competition_strength = as_f64(fl, "competition_strength");
 
@@ -211,12 +213,30 @@ int main(int argc, char **argv)
         pops.set_selection(selection);
         std::vector<double> avg_core(n_gen, 0.0), avg_acc(n_gen, 0.0), std_core(n_gen, 0.0), std_acc(n_gen, 0.0);
         std::vector<double> core_d, acc_d;
-        for (int j = 0; j < n_gen; j++) {
+        // nothing is read back between generations unless --print_dist / --verbose ask for it: the run is
+        // then one device-resident batch (same states)
+        const bool batched = !print_dist && !verbose && n_gen > 1;
+        if (batched) pops.run_generations(0, (uint32_t)(n_gen - 1));
+        for (int j = batched ? n_gen - 1 : 0; j < n_gen; j++) {
             pops.step((uint32_t)j);                                         // main.rs:435-464
             if (j == n_gen - 1) {                                           // main.rs:467-499
-                pops.pairwise_distances(range1, range2, core_d, acc_d);
                 std::ofstream f(outpref + ".tsv");
-                for (size_t k = 0; k < max_distances; k++) f << fmt(core_d[k]) << "\t" << fmt(acc_d[k]) << "\n";
+                if (all_pairs) {
+                    // row blocks of about 4 million pairs, (i, j) order
+                    const uint32_t N = cfg.pop_size;
+                    uint32_t i0 = 0;
+                    while (N > 1 && i0 < N - 1) {
+                        uint32_t i1 = i0;
+                        size_t n = 0;
+                        while (i1 < N - 1 && (n == 0 || n + (N - 1 - i1) <= 4000000)) { n += N - 1 - i1; i1++; }
+                        std::vector<double> c_, a_;
+                        pops.pairwise_distances_rows(i0, i1, c_, a_);
+                        for (size_t k = 0; k < c_.size(); k++) f << fmt(c_[k]) << "\t" << fmt(a_[k]) << "\n";
+                        i0 = i1;
+                    }
+                }
+                pops.pairwise_distances(range1, range2, core_d, acc_d);
+                for (size_t k = 0; k < max_distances && !all_pairs; k++) f << fmt(core_d[k]) << "\t" << fmt(acc_d[k]) << "\n";
                 std::ofstream g(outpref + "_freqs.txt");
                 for (double x : pops.gene_frequencies()) g << fmt(x) << "\n";
             }

@@ -96,6 +96,25 @@ public:
             acc_out[k] = pansim_acc_distance(in[k], un[k], cfg_.core_genes);
         }
     }
+    // (extension) exact all-pairs mode: distances of every pair (i, j), row_begin <= i < row_end, i < j < N,
+    // ordered by i then j; at most 2^31 - 1 pairs per call
+    void pairwise_distances_rows(uint32_t row_begin, uint32_t row_end, std::vector<double> &core_out,
+                                 std::vector<double> &acc_out)
+    {
+        size_t P = 0;
+        for (uint32_t i = row_begin; i < row_end && i < cfg_.pop_size; i++) P += cfg_.pop_size - 1 - i;
+        std::vector<uint32_t> cd(P ? P : 1), in(P ? P : 1), un(P ? P : 1);
+        size_t n = 0;
+        check(pansim_pair_counts_rows(ctx_, row_begin, row_end, cd.data(), in.data(), un.data(), &n));
+        core_out.resize(n);
+        acc_out.resize(n);
+        for (size_t k = 0; k < n; k++) {
+            core_out[k] = pansim_core_distance(cd[k], cfg_.core_size);
+            acc_out[k] = pansim_acc_distance(in[k], un[k], cfg_.core_genes);
+        }
+    }
+    // main.rs:435-464 for generations gen0 .. gen0+n-1 as one device-resident batch
+    void run_generations(uint32_t gen0, uint32_t n) { check(pansim_run_generations(ctx_, gen0, n)); }
     // population.rs:840-863: accessory gene frequencies, then core_genes x 1.0
     std::vector<double> gene_frequencies()
     {

@@ -62,3 +62,29 @@ def test_cpp_host_end_to_end(binary, tmp_path):
     assert len(core) == 20 and all(len(l.split(",")) == 700 and set(l.split(",")) <= set("ACGT") for l in core)
     pan = [l.split(",") for l in open(pref + "_pangenome.csv").read().splitlines()]
     assert len(pan) == 20 and all(len(x) == 80 and x[:30] == ["1"] * 30 for x in pan)
+
+
+@pytest.mark.gpu
+def test_cpp_host_all_pairs_and_batched_run(binary, tmp_path):
+    """--all_pairs (extension): <outpref>.tsv holds every pair i < j in (i, j) order. Without
+    --print_dist / --verbose the generations run as one device-resident batch and must leave the
+    same matrices as the generation-by-generation loop."""
+    import numpy as np
+    common = ["--pop_size", "21", "--core_size", "900", "--pan_genes", "70", "--core_genes", "10", "--n_gen", "4",
+              "--max_distances", "30", "--print_matrices", "--seed", "5"]
+    pa, pb = str(tmp_path / "a"), str(tmp_path / "b")
+    assert run(binary, *common, "--outpref", pa, "--all_pairs").returncode == 0
+    assert run(binary, *common, "--outpref", pb, "--print_dist").returncode == 0
+    assert open(pa + "_core_genome.csv").read() == open(pb + "_core_genome.csv").read()
+    assert open(pa + "_pangenome.csv").read() == open(pb + "_pangenome.csv").read()
+    letters = np.array([l.split(",") for l in open(pa + "_core_genome.csv").read().splitlines()])
+    pan = np.array([l.split(",") for l in open(pa + "_pangenome.csv").read().splitlines()]).astype(int)[:, 10:]
+    rows = [l.split("\t") for l in open(pa + ".tsv").read().splitlines()]
+    assert len(rows) == 21 * 20 // 2 and len(open(pb + ".tsv").read().splitlines()) == 30
+    k = 0
+    for i in range(21):
+        for j in range(i + 1, 21):
+            assert float(rows[k][0]) == (letters[i] != letters[j]).sum() / 900
+            inter, uni = (pan[i] & pan[j]).sum(), (pan[i] | pan[j]).sum()
+            assert float(rows[k][1]) == 1.0 - ((inter + 10.0) / (uni + 10.0))
+            k += 1
