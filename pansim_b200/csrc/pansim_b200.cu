@@ -214,7 +214,7 @@ struct pansim_ctx {
 
     // timing
     bool timing_enabled = true;
-    bool use_pdl = true;                 // PANSIM_PDL=0: no programmatic dependent launches in the selection chain
+    int use_pdl = 1;                     // PANSIM_PDL: 0 = never, 1 = host-driven entry points only (default), 2 = always
     // Dependents that wait inside an SM slot take that slot from the core kernel: worth it when the host
     // waits on the chain every generation (step_with_parents / sample_indices / average_distance), not in
     // the device-resident batch of run_generations, which is bound by the core kernel (measured: -21 us of
@@ -294,7 +294,7 @@ void launch_dependent(pansim_ctx *c, void (*kernel)(KArgs...), dim3 grid, dim3 b
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = (c->use_pdl && c->pdl_now) ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = (c->use_pdl == 2 || (c->use_pdl == 1 && c->pdl_now)) ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
@@ -892,7 +892,7 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
         if (const char *e = getenv("PANSIM_FITNESS_BLOCKED")) c->fitness_blocked = atoi(e) != 0;
         if (const char *e = getenv("PANSIM_INTER_POPC")) c->inter_popc = atoi(e) != 0;
         if (const char *e = getenv("PANSIM_FINE_TIMING")) c->fine_timing = atoi(e) != 0;
-        if (const char *e = getenv("PANSIM_PDL")) c->use_pdl = atoi(e) != 0;
+        if (const char *e = getenv("PANSIM_PDL")) c->use_pdl = atoi(e);
         if (c->tab_hr.nsub && core_bytes) {
             // recombination slots: per (region, row) item room for mean + 6 sigma changed cells (a multiple of 32,
             // 32 when the mean is small); the rare item that needs more spills to the overflow list
