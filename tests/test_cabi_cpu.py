@@ -103,3 +103,22 @@ def test_standard_deviation_sequential_matches_oracle():
     rng = np.random.default_rng(3)
     v = rng.random(100000)
     assert pb.standard_deviation(v) == ob.standard_deviation(v)
+
+
+def test_all_pairs_row_block_helpers():
+    """Pure host logic of the exact all-pairs mode: pair counts of a row block and the row-block
+    partition used by Pansim.iter_all_pairs (no device needed)."""
+    from pansim_b200.population import Pansim
+
+    class Stub:
+        N = 57
+    s = Stub()
+    for b, e in [(0, 57), (0, 1), (56, 57), (10, 10), (3, 29)]:
+        assert Pansim.pairs_in_rows(s, b, e) == sum(57 - 1 - i for i in range(b, e))
+    blocks = list(Pansim.row_blocks(s, 200))
+    assert blocks[0][0] == 0 and blocks[-1][1] == 56
+    assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+    assert sum(Pansim.pairs_in_rows(s, b, e) for b, e in blocks) == 57 * 56 // 2
+    assert all(Pansim.pairs_in_rows(s, b, e) <= 200 or e == b + 1 for b, e in blocks)
+    s.N = 1
+    assert list(Pansim.row_blocks(s, 10)) == []

@@ -33,6 +33,7 @@ def test_validation_messages_and_exit_code_zero(binary):
     assert r.returncode == 0 and r.stdout.splitlines()[1] == "avg_gene_freq: 0"
     r = run(binary, "--help")
     assert r.returncode == 0 and "--HGT_rate" in r.stdout and "--no_control_genome_size" in r.stdout
+    assert "--all_pairs" in r.stdout                          # extension flag
 
 
 def test_no_gpu_fails_loudly(binary):
