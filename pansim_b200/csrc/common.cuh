@@ -136,6 +136,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     while (!mbar_try_wait(bar, parity)) {}
 }
 
+// the same on a 32-bit shared-space address
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar_s, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar_s), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
 // global -> shared bulk copy, completion signalled on an mbarrier (bytes % 16 == 0)
 __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
 {

@@ -133,6 +133,37 @@ __device__ __forceinline__ uint32_t poisson_fast(const uint32_t *tab, uint32_t k
     return k;
 }
 
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// the same sampler on a 32-bit shared-space address of the table image (hot path: no generic pointers)
+__device__ __forceinline__ uint32_t poisson_fast_s(uint32_t tab_s, uint32_t kmax, uint32_t u)
+{
+    uint32_t g;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(g) : "r"(tab_s + (u >> CM_GUIDE_SHIFT) * 2u));
+    const uint32_t thr_s = tab_s + CM_GUIDE_WORDS * 4u;
+    uint32_t k = g >> 1;
+    k += lds_u32(thr_s + k * 4u) <= u ? 1u : 0u;
+    if (g & 1u) {
+        while (k < kmax && lds_u32(thr_s + k * 4u) <= u) k++;
+    }
+    return k;
+}
+
+// hr_count_from_uniform (core_hr.cuh) on a shared-space address
+__device__ __forceinline__ uint32_t hr_count_from_uniform_s(uint32_t thr_s, uint32_t size, uint32_t kmax, uint32_t u,
+                                                            uint32_t lane)
+{
+    uint32_t k = 0;
+#pragma unroll 1
+    for (uint32_t j0 = 0; j0 < size; j0 += 32) k += (uint32_t)__popc(__ballot_sync(0xffffffffu, lds_u32(thr_s + (j0 + lane) * 4u) <= u));
+    return min(k, kmax);
+}
+
 // means above the table range: extra draws from dedicated count calls (exact by additivity)
 __device__ __noinline__ uint32_t mut_count_extra(uint4 ctr, uint2 key, const uint32_t *tab, uint32_t nsub, uint32_t kmax)
 {
@@ -216,8 +247,8 @@ struct MutChunk {
 // marks the last event of its cell within the window (population.rs:745), dw = the donor's word.
 struct HrWindow { uint32_t K, pk, dw; };
 
-__device__ __forceinline__ HrWindow hr_window_fetch(const CoreMutArgs &a, const uint32_t *hr_thr, uint32_t prow, uint32_t reg,
-                                                    uint32_t lane, uint32_t base, uint32_t K_known)
+__device__ __forceinline__ HrWindow hr_window_fetch(const CoreMutArgs &a, const uint32_t *hr_thr, uint32_t hr_thr_s, uint32_t prow,
+                                                    uint32_t reg, uint32_t lane, uint32_t base, uint32_t K_known)
 {
     const uint32_t greg = a.region0 + reg;
     const uint32_t lim = greg == a.last_greg ? a.lim_last : REGION_SITES;
@@ -225,7 +256,7 @@ __device__ __forceinline__ HrWindow hr_window_fetch(const CoreMutArgs &a, const 
     HrWindow h;
     h.K = K_known;
     if (base == 0u) {
-        h.K = hr_count_from_uniform(hr_thr, a.hr_size, a.hr_kmax, __shfl_sync(0xffffffffu, ev.w, 0), lane);
+        h.K = hr_count_from_uniform_s(hr_thr_s, a.hr_size, a.hr_kmax, __shfl_sync(0xffffffffu, ev.w, 0), lane);
         if (a.hr_nsub > 1) h.K += hr_count_extra(greg, prow, a.hr_gen, a.key, hr_thr, a.hr_size, a.hr_nsub, a.hr_kmax, lane);
     }
     const bool valid = base + lane < h.K && ev.pos < lim;                  // ragged last region: thinned away
@@ -239,13 +270,17 @@ __device__ __forceinline__ HrWindow hr_window_fetch(const CoreMutArgs &a, const 
     return h;
 }
 
-// kept cells of one window are distinct, so the XOR of a lane touches bits no other lane reads or writes
-__device__ __forceinline__ void hr_window_apply(uint32_t *sw, const HrWindow &h)
+// kept cells of one window are distinct, so the XOR of a lane touches bits no other lane reads or writes.
+// sw_s = shared-space address of the stage (32-bit addressing: no generic-pointer conversion per item)
+__device__ __forceinline__ void hr_window_apply(uint32_t sw_s, const HrWindow &h)
 {
     if (h.pk & 0x80000000u) {
         const uint32_t pos = h.pk & 0x1FFFu;
-        const uint32_t delta = (sw[pos >> 4] ^ h.dw) & (3u << ((pos & 15u) * 2u));
-        if (delta) atomicXor(&sw[pos >> 4], delta);
+        const uint32_t addr = sw_s + (pos >> 4) * 4u;
+        uint32_t w;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(addr));
+        const uint32_t delta = (w ^ h.dw) & (3u << ((pos & 15u) * 2u));
+        if (delta) asm volatile("red.shared.xor.b32 [%0], %1;" ::"r"(addr), "r"(delta) : "memory");
     }
     __syncwarp();
 }
@@ -311,7 +346,11 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
 
     // the load side runs CM_STAGES-1 items ahead with its own (row, reg, stage) cursor (lane 0 only)
     uint32_t l_row = gw / blk_regs, l_reg = gw % blk_regs, l_stage = 0;
-    const uint32_t stages_s = smem_u32(stages), bars_s = smem_u32(bars);
+    // shared-space addresses, computed once and made opaque so that they stay in registers (otherwise
+    // they are re-derived from %cluster_ctaid and the carve-up arithmetic at every use)
+    uint32_t stages_s = smem_u32(stages), bars_s = smem_u32(bars), lut_s = smem_u32(m.lut);
+    asm volatile("" : "+r"(stages_s), "+r"(bars_s), "+r"(lut_s));
+    const uint32_t tab_s = lut_s + CM_LUT_BYTES, hr_thr_s = tab_s + (CM_GUIDE_WORDS + a.mut_size) * 4u;
     const uint8_t *old_blk = a.old_state + (uint64_t)blk_reg0 * REGION_BYTES;
 #define PANSIM_CM_ISSUE_LOAD()                                                                               \
     do {                                                                                                     \
@@ -337,10 +376,11 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
     if (RNG) mut_const_wait(m);
     const bool hr_on = RNG && a.hr_nsub != 0u;
     HrWindow hw_cur{0u, 0u, 0u};
-    if (hr_on) hw_cur = hr_window_fetch(a, m.hr_thr, a.parents ? __ldg(a.parents + row) : row, blk_reg0 + breg, lane, 0u, 0u);
+    if (hr_on) hw_cur = hr_window_fetch(a, m.hr_thr, hr_thr_s, a.parents ? __ldg(a.parents + row) : row, blk_reg0 + breg, lane, 0u, 0u);
     uint32_t s = 0, par = 0;                 // stage of item j and the phase parity of its mbarrier
     for (uint32_t j = 0; j < n_my; j++) {
-        uint32_t *sw = reinterpret_cast<uint32_t *>(stages + s * REGION_BYTES);
+        uint32_t *sw = reinterpret_cast<uint32_t *>(stages + s * REGION_BYTES);     // generic pointer: ragged edge only
+        const uint32_t sw_s = stages_s + s * REGION_BYTES;
         const uint32_t reg = blk_reg0 + breg;
 
         // RNG work that does not need the data is done before waiting for the TMA load
@@ -355,7 +395,7 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
             uint4 t = mctr;
             t.w += 1u;
             c1 = philox4x32_10(t, a.rk);
-            k = poisson_fast(tab, a.mut_kmax, c0.x);
+            k = poisson_fast_s(tab_s, a.mut_kmax, c0.x);
             if (a.mut_nsub > 1) k += mut_count_extra(mctr, a.key, tab, a.mut_nsub, a.mut_kmax);
         }
 
@@ -363,30 +403,30 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
             bulk_wait_read<0>();          // the store of item j-1 has left the stage item j+1 goes into
             PANSIM_CM_ISSUE_LOAD();
         }
-        mbar_wait(&bars[s], par);
+        mbar_wait_s(bars_s + s * 8u, par);
 
         if (hr_on) {
             // ---- recombination of the previous generation on the parent's row (population.rs:725-748):
             // windows in draw order, so a later event of a cell overwrites an earlier one ----
             if (hw_cur.K) {
-                hr_window_apply(sw, hw_cur);
+                hr_window_apply(sw_s, hw_cur);
 #pragma unroll 1
                 for (uint32_t base = 32u; base < hw_cur.K; base += 32u)
-                    hr_window_apply(sw, hr_window_fetch(a, m.hr_thr, a.parents ? __ldg(a.parents + row) : row, reg, lane, base, hw_cur.K));
+                    hr_window_apply(sw_s, hr_window_fetch(a, m.hr_thr, hr_thr_s, a.parents ? __ldg(a.parents + row) : row, reg, lane, base, hw_cur.K));
             }
             // first window of the NEXT item, fetched into the registers just consumed: its donor
             // loads are in flight while this item's SNP events are applied
             if (j + 1 < n_my) {
                 uint32_t nrow = row + d_row, nreg = breg + d_reg;
                 if (nreg >= blk_regs) { nreg -= blk_regs; nrow++; }
-                hw_cur = hr_window_fetch(a, m.hr_thr, a.parents ? __ldg(a.parents + nrow) : nrow, blk_reg0 + nreg, lane, 0u, 0u);
+                hw_cur = hr_window_fetch(a, m.hr_thr, hr_thr_s, a.parents ? __ldg(a.parents + nrow) : nrow, blk_reg0 + nreg, lane, 0u, 0u);
             }
         }
 
         if (RNG && a.mut_nsub) {
             // ---- SNP mutation (population.rs:512-539) ----
             const uint32_t kw = __reduce_max_sync(0xffffffffu, k);      // warp-uniform trip counts
-            const MutChunk<DUMP> f{smem_u32(sw) | (lane * 4u), smem_u32(m.lut), k, lane, row, lim, reg_site0, mctr, a.key, &a};
+            const MutChunk<DUMP> f{sw_s | (lane * 4u), lut_s, k, lane, row, lim, reg_site0, mctr, a.key, &a};
             // calls 0,1:  c0.x count | c0.y digit bytes of chunks 0-3 | c0.z digit byte of chunk 4 + 3 reserve bytes |
             //             c0.w, c1.x, c1.y, c1.z, c1.w position bytes of events 0..19
             if (kw > 0u) {
@@ -422,7 +462,7 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
 
         if (lane == 0) {
             uint8_t *dst = a.new_state + (uint64_t)row * a.row_stride + (uint64_t)reg * REGION_BYTES;
-            bulk_s2g(dst, sw, REGION_BYTES);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(sw_s), "n"(REGION_BYTES) : "memory");
             bulk_commit();
             if (!CM_LATE_LOAD && j + CM_STAGES - 1 < n_my) {
                 bulk_wait_read<1>();      // the store that last used stage (j-1)%S has left smem
