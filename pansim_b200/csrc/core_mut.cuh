@@ -335,7 +335,9 @@ template <bool RNG, bool DUMP>
 __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSmem &m, uint32_t item_begin,
                                               uint32_t item_end, uint32_t blk_regs, uint32_t blk_reg0)
 {
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t warp = threadIdx.x >> 5;
+    uint32_t lane = threadIdx.x & 31;
+    asm volatile("" : "+r"(lane));          // keep it in a register (otherwise %tid.x is re-read at every use)
     uint8_t *stages = m.stages + (size_t)warp * CM_STAGES * REGION_BYTES;
     uint64_t *bars = m.bars + warp * CM_STAGES;
     const uint32_t *tab = m.tab;
