@@ -79,6 +79,38 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, const PhiloxKeys &rk)
     return make_uint4(c0, c1, c2, c3);
 }
 
+// Core-genome streams (SNP positions / allele digits / counts, recombination sites / donors) use
+// Philox4x32-7: the same bijection with seven rounds, the smallest round count of the family that is
+// Crush-resistant (Salmon et al., SC'11, table 2: Philox4x32-7 passes BigCrush; ten rounds is the
+// paper's safety margin). The core kernel is instruction-issue bound and makes 3.5 calls per lane per
+// 2 KiB region, so three rounds fewer are ~5 % of its instructions. Parent draws and the accessory
+// streams keep ten rounds. PANSIM_CORE_PHILOX_ROUNDS=10 at compile time restores the margin.
+#ifndef PANSIM_CORE_PHILOX_ROUNDS
+#define PANSIM_CORE_PHILOX_ROUNDS 7
+#endif
+constexpr int CORE_PHILOX_ROUNDS = PANSIM_CORE_PHILOX_ROUNDS;
+
+__host__ __device__ __forceinline__ uint4 philox_core(uint4 ctr, uint2 key)
+{
+    uint32_t c0 = ctr.x, c1 = ctr.y, c2 = ctr.z, c3 = ctr.w;
+    uint32_t k0 = key.x, k1 = key.y;
+#pragma unroll
+    for (int r = 0; r < CORE_PHILOX_ROUNDS; r++) {
+        philox_round(c0, c1, c2, c3, k0, k1);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ uint4 philox_core(uint4 ctr, const PhiloxKeys &rk)
+{
+    uint32_t c0 = ctr.x, c1 = ctr.y, c2 = ctr.z, c3 = ctr.w;
+#pragma unroll
+    for (int r = 0; r < CORE_PHILOX_ROUNDS; r++) philox_round(c0, c1, c2, c3, rk.k0[r], rk.k1[r]);
+    return make_uint4(c0, c1, c2, c3);
+}
+
 // Counter layout used everywhere:  x = column block id (site block / gene word),
 // y = individual (row), z = generation, w = (stream << 16) | refill index.
 __host__ __device__ __forceinline__ uint4 make_ctr(uint32_t block, uint32_t row, uint32_t gen,

@@ -22,9 +22,10 @@
 //            8192-bit claim map over windows visited last to first.
 //   apply    atomicXor of the collected deltas (cells are distinct, so the
 //            order of application is irrelevant).
-// The steps run either as two kernels after core_mut_kernel (this file) or
-// inside the fused generation kernel of core_gen.cuh, column block by column
-// block while the gather+SNP pass is still streaming the next blocks.
+// The steps run as two kernels after core_mut_kernel whenever a reader needs the
+// materialised state (distances, downloads, replay steps, the event dump). In the
+// default generate-mode loop the same events are instead recomputed and applied
+// by the NEXT generation's core_mut_kernel (core_mut.cuh, hr_window_fetch/apply).
 #pragma once
 #include "common.cuh"
 
@@ -91,7 +92,7 @@ __device__ __noinline__ uint32_t hr_count_extra(uint32_t greg, uint32_t row, uin
     for (uint32_t s = 1; s < nsub; s++) {
         uint4 c = make_ctr(greg, row, gen, STREAM_CORE_HR_EXTRA);
         c.w |= 0x8000u | ((s - 1) >> 2);
-        const uint4 r = philox4x32_10(c, key);
+        const uint4 r = philox_core(c, key);
         const uint32_t sel = (s - 1) & 3u;
         const uint32_t u = sel == 0 ? r.x : sel == 1 ? r.y : sel == 2 ? r.z : r.w;
         k += hr_count_from_uniform(thr, size, kmax, u, lane);
@@ -105,7 +106,7 @@ template <typename Key>      // uint2 key or precomputed PhiloxKeys
 __device__ __forceinline__ HrEvent hr_event(uint32_t greg, uint32_t row, uint32_t gen, const Key &key, uint32_t e, uint32_t n_other,
                                             uint32_t lemire_t)      // lemire_t = 2^32 mod n_other (host)
 {
-    const uint4 r = philox4x32_10(make_uint4(greg, row, gen, HR_EVENT_W0 + e), key);
+    const uint4 r = philox_core(make_uint4(greg, row, gen, HR_EVENT_W0 + e), key);
     HrEvent ev;
     ev.pos = r.x >> 19;                                                                   // uniform site of the region
     // uniform on the other N - 1 rows: multiply-high of a 32-bit word with Lemire's rejection test; a

@@ -92,6 +92,7 @@ struct CoreMutArgs {
     uint32_t mut_size, mut_nsub, mut_kmax;
     // recombination events of generation hr_gen still pending on old_state (hr_nsub = 0: none)
     uint32_t hr_size, hr_nsub, hr_kmax, hr_gen;
+    uint32_t hr_k0;           // first threshold of the 32-wide window hr_count_from_uniform_s tries first (<= hr_size - 32)
     uint32_t hr_lemire_t;     // 2^32 mod (n_rows - 1), see hr_event
     // optional event dump (parity instrumentation)
     uint32_t *dump_counters;  // [0] = SNP events
@@ -154,10 +155,15 @@ __device__ __forceinline__ uint32_t poisson_fast_s(uint32_t tab_s, uint32_t kmax
     return k;
 }
 
-// hr_count_from_uniform (core_hr.cuh) on a shared-space address
-__device__ __forceinline__ uint32_t hr_count_from_uniform_s(uint32_t thr_s, uint32_t size, uint32_t kmax, uint32_t u,
+// hr_count_from_uniform (core_hr.cuh) on a shared-space address. k = #{j : T[j] <= u} with T
+// non-decreasing: one ballot over the 32 thresholds T[k0 .. k0+31] that carry nearly all of the
+// probability mass settles it (0 < c < 32 matches in the window means every earlier threshold is
+// <= u and every later one is > u, so k = k0 + c); otherwise the whole table is scanned.
+__device__ __forceinline__ uint32_t hr_count_from_uniform_s(uint32_t thr_s, uint32_t size, uint32_t kmax, uint32_t k0, uint32_t u,
                                                             uint32_t lane)
 {
+    const uint32_t c = (uint32_t)__popc(__ballot_sync(0xffffffffu, lds_u32(thr_s + (k0 + lane) * 4u) <= u));
+    if (c - 1u < 31u) return min(k0 + c, kmax);
     uint32_t k = 0;
 #pragma unroll 1
     for (uint32_t j0 = 0; j0 < size; j0 += 32) k += (uint32_t)__popc(__ballot_sync(0xffffffffu, lds_u32(thr_s + (j0 + lane) * 4u) <= u));
@@ -171,7 +177,7 @@ __device__ __noinline__ uint32_t mut_count_extra(uint4 ctr, uint2 key, const uin
     for (uint32_t s = 1; s < nsub; s++) {
         uint4 c = ctr;
         c.w |= 0x8000u | ((s - 1) >> 2);
-        const uint4 r = philox4x32_10(c, key);
+        const uint4 r = philox_core(c, key);
         const uint32_t sel = (s - 1) & 3u;
         const uint32_t u = sel == 0 ? r.x : sel == 1 ? r.y : sel == 2 ? r.z : r.w;
         k += poisson_fast(tab, kmax, u);
@@ -184,7 +190,7 @@ __device__ __noinline__ uint32_t mut_digit_fallback(uint4 ctr, uint2 key, uint32
 {
     ctr.w |= 0x2000u;
     ctr.x ^= 0x5bd1e995u * (tag + 1u);
-    return __umulhi(philox4x32_10(ctr, key).x, 243u);
+    return __umulhi(philox_core(ctr, key).x, 243u);
 }
 
 template <bool DUMP>
@@ -253,15 +259,21 @@ __device__ __forceinline__ HrWindow hr_window_fetch(const CoreMutArgs &a, const 
     const uint32_t greg = a.region0 + reg;
     const uint32_t lim = greg == a.last_greg ? a.lim_last : REGION_SITES;
     const HrEvent ev = hr_event(greg, prow, a.hr_gen, a.rk, base + lane, a.n_rows - 1u, a.hr_lemire_t);
+    // lanes that drew the same site: asked for before the count is known (the match unit is slow and
+    // the count needs a shared-memory round trip of its own), validity is folded in afterwards
+    const uint32_t same = __match_any_sync(0xffffffffu, ev.pos);
     HrWindow h;
     h.K = K_known;
     if (base == 0u) {
-        h.K = hr_count_from_uniform_s(hr_thr_s, a.hr_size, a.hr_kmax, __shfl_sync(0xffffffffu, ev.w, 0), lane);
+        h.K = hr_count_from_uniform_s(hr_thr_s, a.hr_size, a.hr_kmax, a.hr_k0, __shfl_sync(0xffffffffu, ev.w, 0), lane);
         if (a.hr_nsub > 1) h.K += hr_count_extra(greg, prow, a.hr_gen, a.key, hr_thr, a.hr_size, a.hr_nsub, a.hr_kmax, lane);
     }
-    const bool valid = base + lane < h.K && ev.pos < lim;                  // ragged last region: thinned away
-    const uint32_t same = __match_any_sync(0xffffffffu, valid ? ev.pos : (0x80000000u | lane));
-    const bool keep = valid && ((same >> lane) >> 1) == 0u;
+    // events base .. K-1 exist: they sit in the lanes below K - base. A site beyond the ragged end of the
+    // alignment is thinned away (the same site in every lane of its match group, so the group drops as a whole).
+    const uint32_t n_here = h.K - min(h.K, base);
+    const uint32_t live = n_here >= 32u ? 0xffffffffu : ((1u << n_here) - 1u);
+    const bool valid = ((live >> lane) & 1u) != 0u && ev.pos < lim;
+    const bool keep = valid && (((same & live) >> lane) >> 1) == 0u;        // the last event of a cell wins (population.rs:745)
     h.pk = ev.pos | (keep ? 0x80000000u : 0u);
     h.dw = 0;
     if (keep)   // the old buffer is read-only during this launch: the snapshot the donor cell is taken from (:693-695)
@@ -348,6 +360,10 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
 
     // the load side runs CM_STAGES-1 items ahead with its own (row, reg, stage) cursor (lane 0 only)
     uint32_t l_row = gw / blk_regs, l_reg = gw % blk_regs, l_stage = 0;
+    // parent rows are kept in registers and re-read only when a cursor moves on to another row (a warp
+    // stays on one row for many items when the row has more regions than the CTA has warps)
+#define PANSIM_CM_PARENT(r_) (a.parents ? __ldg(a.parents + (r_)) : (r_))
+    uint32_t l_prow = PANSIM_CM_PARENT(l_row);
     // shared-space addresses, computed once and made opaque so that they stay in registers (otherwise
     // they are re-derived from %cluster_ctaid and the carve-up arithmetic at every use)
     uint32_t stages_s = smem_u32(stages), bars_s = smem_u32(bars), lut_s = smem_u32(m.lut);
@@ -356,15 +372,19 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
     const uint8_t *old_blk = a.old_state + (uint64_t)blk_reg0 * REGION_BYTES;
 #define PANSIM_CM_ISSUE_LOAD()                                                                               \
     do {                                                                                                     \
-        const uint8_t *src_ = old_blk + (uint64_t)(a.parents ? __ldg(a.parents + l_row) : l_row) * a.row_stride + \
-                              l_reg * REGION_BYTES;                                                          \
+        const uint8_t *src_ = old_blk + (uint64_t)l_prow * a.row_stride + l_reg * REGION_BYTES;              \
         const uint32_t bar_ = bars_s + l_stage * 8u;                                                         \
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_), "n"(REGION_BYTES) : "memory"); \
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" \
                      ::"r"(stages_s + l_stage * REGION_BYTES), "l"(src_), "n"(REGION_BYTES), "r"(bar_) : "memory"); \
         l_stage = l_stage == (uint32_t)(CM_STAGES - 1) ? 0u : l_stage + 1u;                                  \
-        l_row += d_row; l_reg += d_reg;                                                                      \
-        if (l_reg >= blk_regs) { l_reg -= blk_regs; l_row++; }                                               \
+        uint32_t nr_ = l_row + d_row;                                                                        \
+        l_reg += d_reg;                                                                                      \
+        if (l_reg >= blk_regs) { l_reg -= blk_regs; nr_++; }                                                 \
+        if (nr_ != l_row) {          /* the parent of the next row, one load ahead of its use */             \
+            l_row = nr_;                                                                                     \
+            if (l_row < a.n_rows) l_prow = PANSIM_CM_PARENT(l_row);                                          \
+        }                                                                                                    \
     } while (0)
 
     if (lane == 0) {
@@ -378,7 +398,8 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
     if (RNG) mut_const_wait(m);
     const bool hr_on = RNG && a.hr_nsub != 0u;
     HrWindow hw_cur{0u, 0u, 0u};
-    if (hr_on) hw_cur = hr_window_fetch(a, m.hr_thr, hr_thr_s, a.parents ? __ldg(a.parents + row) : row, blk_reg0 + breg, lane, 0u, 0u);
+    uint32_t prow = hr_on ? PANSIM_CM_PARENT(row) : 0u, nprow = prow;      // parent of `row` / of the next item's row
+    if (hr_on) hw_cur = hr_window_fetch(a, m.hr_thr, hr_thr_s, prow, blk_reg0 + breg, lane, 0u, 0u);
     uint32_t s = 0, par = 0;                 // stage of item j and the phase parity of its mbarrier
     for (uint32_t j = 0; j < n_my; j++) {
         uint32_t *sw = reinterpret_cast<uint32_t *>(stages + s * REGION_BYTES);     // generic pointer: ragged edge only
@@ -393,10 +414,10 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
         uint4 c0 = make_uint4(0, 0, 0, 0), c1 = make_uint4(0, 0, 0, 0);
         uint32_t k = 0;
         if (RNG && a.mut_nsub) {
-            c0 = philox4x32_10(mctr, a.rk);
+            c0 = philox_core(mctr, a.rk);
             uint4 t = mctr;
             t.w += 1u;
-            c1 = philox4x32_10(t, a.rk);
+            c1 = philox_core(t, a.rk);
             k = poisson_fast_s(tab_s, a.mut_kmax, c0.x);
             if (a.mut_nsub > 1) k += mut_count_extra(mctr, a.key, tab, a.mut_nsub, a.mut_kmax);
         }
@@ -414,14 +435,15 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
                 hr_window_apply(sw_s, hw_cur);
 #pragma unroll 1
                 for (uint32_t base = 32u; base < hw_cur.K; base += 32u)
-                    hr_window_apply(sw_s, hr_window_fetch(a, m.hr_thr, hr_thr_s, a.parents ? __ldg(a.parents + row) : row, reg, lane, base, hw_cur.K));
+                    hr_window_apply(sw_s, hr_window_fetch(a, m.hr_thr, hr_thr_s, prow, reg, lane, base, hw_cur.K));
             }
             // first window of the NEXT item, fetched into the registers just consumed: its donor
             // loads are in flight while this item's SNP events are applied
             if (j + 1 < n_my) {
                 uint32_t nrow = row + d_row, nreg = breg + d_reg;
                 if (nreg >= blk_regs) { nreg -= blk_regs; nrow++; }
-                hw_cur = hr_window_fetch(a, m.hr_thr, hr_thr_s, a.parents ? __ldg(a.parents + nrow) : nrow, blk_reg0 + nreg, lane, 0u, 0u);
+                nprow = nrow == row ? prow : PANSIM_CM_PARENT(nrow);
+                hw_cur = hr_window_fetch(a, m.hr_thr, hr_thr_s, nprow, blk_reg0 + nreg, lane, 0u, 0u);
             }
         }
 
@@ -444,7 +466,7 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
             for (uint32_t base = CM_GROUP0, call = 2u; base < kw; base += CM_TAIL, call++) {
                 uint4 t = mctr;
                 t.w += call;
-                const uint4 c = philox4x32_10(t, a.rk);
+                const uint4 c = philox_core(t, a.rk);
                 uint32_t res = (c.x >> 16) | 0xFFFF0000u;
                 f.run(base, c.x & 255u, c.y, res);
                 if (kw > base + 4u) f.run(base + 4u, (c.x >> 8) & 255u, c.z, res);
@@ -474,10 +496,12 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
         __syncwarp();
         row += d_row; breg += d_reg;
         if (breg >= blk_regs) { breg -= blk_regs; row++; }
+        prow = nprow;
         if (++s == (uint32_t)CM_STAGES) { s = 0; par ^= 1u; }
     }
     if (lane == 0) bulk_wait<0>();
 #undef PANSIM_CM_ISSUE_LOAD
+#undef PANSIM_CM_PARENT
 }
 
 // Stand-alone launch: CTA b covers items [b*C, (b+1)*C) of the whole shard, C = CM_WARPS*items_per_warp.

@@ -8,12 +8,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
 #include "acc_step.cuh"
 #include "common.cuh"
-#include "core_mut.cuh"
 #include "core_hr.cuh"
 #include "core_mut.cuh"
 #include "distance.cuh"
@@ -117,9 +117,15 @@ struct pansim_ctx {
     cudaEvent_t ev_parents[3] = {nullptr, nullptr, nullptr};    // parents[i] written
     cudaEvent_t ev_core_done[3] = {nullptr, nullptr, nullptr};  // core step that read parents[i] finished
     bool core_done_valid[3] = {false, false, false};
+    cudaEvent_t ev_core_last = nullptr;   // the most recently launched core step finished (independent of the parents rotation)
     bool core_unjoined = false;           // a core step is in flight on stream_core that `stream` has not been ordered after
     uint32_t *d_parents_buf[3] = {nullptr, nullptr, nullptr};
     uint32_t *h_parents = nullptr;        // pinned [N + 1]: parents + status word read back by pansim_sample_indices
+    uint32_t *h_parents_up[3] = {nullptr, nullptr, nullptr};   // pinned staging of host-supplied parents (one per rotating buffer)
+    cudaEvent_t ev_h2d[3] = {nullptr, nullptr, nullptr};        // the upload out of h_parents_up[i] has completed
+    bool h2d_valid[3] = {false, false, false};
+    double *h_avg = nullptr;              // pinned [N]: staging of avg_pairwise_dists in both directions
+    int *h_err = nullptr;                 // pinned [2]: read-back of d_err
     int parents_idx = 0;
     int sm_count = 0;
 
@@ -172,6 +178,7 @@ struct pansim_ctx {
     bool fitness_blocked = false; // large shapes: blocked (fixed-association) fitness sum instead of the sequential chain
 
     HostPoissonTable tab_mut, tab_hr;    // per 256-site block (SNPs), per 8192-site region (HR)
+    uint32_t hr_k0 = 0;                  // 32-threshold window of tab_hr that is tried first (core_mut.cuh)
     uint8_t *d_core_img = nullptr;       // constant image of the core kernel (core_mut.cuh)
     uint32_t flip_thr[2] = {0, 0};
     double flip_p[2] = {0, 0};
@@ -341,14 +348,32 @@ int ensure_stage(pansim_ctx *c, size_t bytes)
     return 0;
 }
 
-// the recombination list is sized 12 sigma above its mean; an overflow (which would drop events) is an error
+// d_err[0]: input / selection errors (meaning given by the caller). d_err[1]: the recombination
+// overflow list (sized 12 sigma above its mean) was full, i.e. events were dropped. Both are read
+// back together wherever a call synchronises anyway.
+int flags_enqueue_readback(pansim_ctx *c)
+{
+    CU(c, cudaMemcpyAsync(c->h_err, c->d_err, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+}
+
+// after the stream has been synchronised behind flags_enqueue_readback
+int flags_inspect(pansim_ctx *c, int code, const char *what)
+{
+    const int f0 = c->h_err[0], f1 = c->h_err[1];
+    if (f0 || f1) cudaMemsetAsync(c->d_err, 0, 2 * sizeof(int), c->stream);
+    if (f1) FAIL(c, PANSIM_ERR_STATE, "recombination overflow list full: events were dropped in an earlier generation");
+    if (f0) FAIL(c, code, "%s", what);
+    return 0;
+}
+
 int check_hr_flag(pansim_ctx *c)
 {
     if (!c->d_hr_slots) return 0;
-    int flag = 0;
-    CU(c, cudaMemcpyAsync(&flag, c->d_err + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (int rc = flags_enqueue_readback(c)) return rc;
     CU(c, cudaStreamSynchronize(c->stream));
-    if (flag) {
+    const int f1 = c->h_err[1];
+    if (f1) {
         cudaMemsetAsync(c->d_err + 1, 0, sizeof(int), c->stream);
         FAIL(c, PANSIM_ERR_STATE, "recombination overflow list full: events were dropped in an earlier generation");
     }
@@ -357,14 +382,9 @@ int check_hr_flag(pansim_ctx *c)
 
 int check_device_flag(pansim_ctx *c, int code, const char *what)
 {
-    int flag = 0;
-    CU(c, cudaMemcpyAsync(&flag, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (int rc = flags_enqueue_readback(c)) return rc;
     CU(c, cudaStreamSynchronize(c->stream));
-    if (flag) {
-        cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream);
-        FAIL(c, code, "%s", what);
-    }
-    return 0;
+    return flags_inspect(c, code, what);
 }
 
 // ---- kernel group launchers (asynchronous on ctx->stream) -----------------
@@ -408,7 +428,7 @@ int launch_competition(pansim_ctx *c)
     // the fitness sum runs on the aux stream beside the intersection counts AND the distance kernel (which
     // takes the gene counts from the diagonal of the intersection matrix); whoever needs log-fitness or
     // d_num_genes joins it (join_fitness)
-    FineSpan *fs = new FineSpan(c, TG_D_INTER);
+    std::unique_ptr<FineSpan> fs(new FineSpan(c, TG_D_INTER));
     if (!c->fitness_valid) {
         CU(c, cudaEventRecord(c->ev_fork, c->stream));
         CU(c, cudaStreamWaitEvent(c->stream_aux, c->ev_fork, 0));
@@ -426,7 +446,7 @@ int launch_competition(pansim_ctx *c)
                                                                   c->acc_words, c->d_inter, c->d_inter_diag);
     }
     LAUNCH_CHECK(c);
-    delete fs;
+    fs.reset();
     FineSpan fs2(c, TG_D_AVG);
     avg_distance_kernel<<<div_up64(c->N, AVG_WARPS), AVG_WARPS * 32, 0, c->stream>>>(c->d_inter, c->d_inter_diag, c->N,
                                                                     c->cfg.core_genes, c->d_avgdist);
@@ -549,6 +569,7 @@ void fill_core_args(pansim_ctx *c, CoreMutArgs &a, uint32_t gen)
     a.hr_size = c->tab_hr.size;
     a.hr_lemire_t = c->N > 1 ? (uint32_t)((1ull << 32) % (c->N - 1)) : 0u; a.hr_kmax = c->tab_hr.kmax; a.hr_gen = c->hr_pending_gen;
     a.hr_nsub = c->hr_pending ? c->tab_hr.nsub : 0u;
+    a.hr_k0 = c->hr_k0;
     a.dump_counters = c->d_dump_counters;
     a.dump_cap = c->dump_cap;
     a.d_mut_row = c->d_mut_row; a.d_mut_site = c->d_mut_site; a.d_mut_seq = c->d_mut_seq; a.d_mut_allele = c->d_mut_allele;
@@ -606,8 +627,9 @@ int launch_core_hr(pansim_ctx *c, uint32_t gen, uint8_t *state, cudaStream_t st)
 int ensure_core_joined(pansim_ctx *c)
 {
     if (!c->core_unjoined) return 0;
-    const int i = c->parents_idx;
-    if (c->core_done_valid[i]) CU(c, cudaStreamWaitEvent(c->stream, c->ev_core_done[i], 0));
+    // ev_core_last, not ev_core_done[parents_idx]: sample_indices / next_generation rotate the parents
+    // buffers without launching a core step, so the indexed event may belong to an older step
+    CU(c, cudaStreamWaitEvent(c->stream, c->ev_core_last, 0));
     c->core_unjoined = false;
     return 0;
 }
@@ -690,6 +712,7 @@ int launch_population_steps(pansim_ctx *c, uint32_t gen)
         if (int rc = launch_core_step(c, gen, true, c->stream_core)) return rc;
     }
     CU(c, cudaEventRecord(c->ev_core_done[i], c->stream_core));
+    CU(c, cudaEventRecord(c->ev_core_last, c->stream_core));
     c->core_done_valid[i] = true;
     c->core_unjoined = true;
     {
@@ -763,11 +786,18 @@ void pansim_destroy(pansim_ctx *c)
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (c->h_parents) cudaFreeHost(c->h_parents);
+    for (int i = 0; i < 3; i++) {
+        if (c->h_parents_up[i]) cudaFreeHost(c->h_parents_up[i]);
+        if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
+    }
+    if (c->h_avg) cudaFreeHost(c->h_avg);
+    if (c->h_err) cudaFreeHost(c->h_err);
     c->pool.destroy();
     for (int i = 0; i < 3; i++) {
         if (c->ev_parents[i]) cudaEventDestroy(c->ev_parents[i]);
         if (c->ev_core_done[i]) cudaEventDestroy(c->ev_core_done[i]);
     }
+    if (c->ev_core_last) cudaEventDestroy(c->ev_core_last);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->stream_aux) cudaStreamDestroy(c->stream_aux);
@@ -831,6 +861,7 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
             CU(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
             CU(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
         }
+        CU(c, cudaEventCreateWithFlags(&c->ev_core_last, cudaEventDisableTiming));
         for (int i = 0; i < 3; i++) {
             CU(c, cudaEventCreateWithFlags(&c->ev_parents[i], cudaEventDisableTiming));
             CU(c, cudaEventCreateWithFlags(&c->ev_core_done[i], cudaEventDisableTiming));
@@ -844,6 +875,13 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
         build_poisson_table(rate_mut * BLOCK_SITES, c->tab_mut);
         build_poisson_table(rate_hr * REGION_SITES, c->tab_hr);
         if (c->tab_hr.size < 32) { c->tab_hr.size = 32; c->tab_hr.thr.resize(32, 0xFFFFFFFFu); }      // whole warps of thresholds (core_hr.cuh)
+        {
+            // window of 32 thresholds around the median of the count distribution
+            uint32_t med = 0;
+            while (med < c->tab_hr.kmax && c->tab_hr.thr[med] < 0x80000000u) med++;
+            c->hr_k0 = med > 16u ? med - 16u : 0u;
+            if (c->hr_k0 + 32u > c->tab_hr.size) c->hr_k0 = c->tab_hr.size - 32u;
+        }
         if ((double)c->tab_hr.nsub * c->tab_hr.kmax > 1.5e7) FAIL(c, PANSIM_ERR_INVALID, "recombination rate too high (more than ~1e7 events per 8192-site region)");
         {
             // constant image of the core kernel: allele-digit table, SNP count table, recombination thresholds
@@ -915,6 +953,13 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
         const size_t n = c->N;
         for (int i = 0; i < 3; i++) CU(c, cudaMalloc(&c->d_parents_buf[i], (n + 1) * 4));   // + status word (select.cuh)
         CU(c, cudaMallocHost(&c->h_parents, (n + 1) * 4));
+        for (int i = 0; i < 3; i++) {
+            CU(c, cudaMallocHost(&c->h_parents_up[i], n * 4));
+            CU(c, cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
+        }
+        CU(c, cudaMallocHost(&c->h_avg, n * 8));
+        CU(c, cudaMallocHost(&c->h_err, 2 * sizeof(int)));
+        c->h_err[0] = c->h_err[1] = 0;
         c->d_parents = c->d_parents_buf[0];
         CU(c, cudaMalloc(&c->d_lw, (size_t)(c->G ? c->G : 1) * 8));
         CU(c, cudaMemset(c->d_lw, 0, (size_t)(c->G ? c->G : 1) * 8));
@@ -933,7 +978,9 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
         CU(c, cudaMemset(c->d_err, 0, 2 * sizeof(int)));
         CU(c, cudaMalloc(&c->d_rowInvK, 2 * n * 8));
         CU(c, cudaMalloc(&c->d_gain_thr, (size_t)(c->G ? c->G : 1) * 4));
-        CU(c, cudaMalloc(&c->d_gain_planes, (size_t)(c->acc_words ? c->acc_words : 1) * 32 * 4));
+        // one 32-word plane block per word of the row STRIDE: acc_hgt_apply_kernel runs over the padded rows
+        CU(c, cudaMalloc(&c->d_gain_planes, (size_t)c->acc_stride_words * 32 * 4));
+        CU(c, cudaMemset(c->d_gain_planes, 0, (size_t)c->acc_stride_words * 32 * 4));
         CU(c, cudaMalloc(&c->d_dump_counters, 2 * sizeof(uint32_t)));
         CU(c, cudaMemset(c->d_dump_counters, 0, 2 * sizeof(uint32_t)));
 
@@ -1133,6 +1180,7 @@ int pansim_export_core_csv(pansim_ctx *c, uint32_t row_begin, uint32_t row_end, 
     CU(c, cudaSetDevice(c->cfg.device));
     if (c->Ll == 0) return 0;
     if (int rc = core_materialize(c, c->stream)) return rc;
+    if (int rc = check_hr_flag(c)) return rc;
     const size_t row_bytes = 2 * (size_t)c->Ll;
     uint32_t rows_per = (uint32_t)std::max<uint64_t>(1, (256ull << 20) / row_bytes);
     if (int rc = ensure_stage(c, (size_t)std::min<uint32_t>(rows_per, std::max(1u, row_end - row_begin)) * row_bytes)) return rc;
@@ -1254,11 +1302,24 @@ int pansim_get_parents(pansim_ctx *c, uint32_t *out)
     return 0;
 }
 
+// The caller's vector is copied into the context's own pinned staging buffer of the current
+// parents slot, so it is consumed when this returns whatever kind of host memory it lives in
+// (a pageable source would make cudaMemcpyAsync host-synchronous, a pinned one would not).
 static int upload_parents(pansim_ctx *c, const uint32_t *parents)
 {
-    for (uint32_t i = 0; i < c->N; i++)
-        if (parents[i] >= c->N) FAIL(c, PANSIM_ERR_INVALID, "parents[%u] = %u out of range", i, parents[i]);
-    CU(c, cudaMemcpyAsync(c->d_parents, parents, (size_t)c->N * 4, cudaMemcpyHostToDevice, c->stream));
+    const int i = c->parents_idx;
+    if (c->h2d_valid[i]) CU(c, cudaEventSynchronize(c->ev_h2d[i]));      // the upload of three steps ago: long done
+    uint32_t *stage = c->h_parents_up[i];
+    uint32_t bad = 0xFFFFFFFFu;
+    for (uint32_t k = 0; k < c->N; k++) {
+        const uint32_t v = parents[k];
+        stage[k] = v;
+        if (v >= c->N && bad == 0xFFFFFFFFu) bad = k;
+    }
+    if (bad != 0xFFFFFFFFu) FAIL(c, PANSIM_ERR_INVALID, "parents[%u] = %u out of range", bad, parents[bad]);
+    CU(c, cudaMemcpyAsync(c->d_parents, stage, (size_t)c->N * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaEventRecord(c->ev_h2d[i], c->stream));
+    c->h2d_valid[i] = true;
     return 0;
 }
 
@@ -1275,8 +1336,8 @@ int pansim_step_with_parents(pansim_ctx *c, uint32_t gen, const uint32_t *parent
     if (int rc = launch_population_steps(c, gen)) return rc;
     timing_end(c);
     c->avgdist_valid = false;
-    // Returns with the step enqueued (the parents vector has been consumed: the upload from pageable
-    // host memory is synchronous for the host). The core kernel keeps running beside the next
+    // Returns with the step enqueued (the parents vector has been consumed: it was copied into the
+    // context's pinned staging buffer). The core kernel keeps running beside the next
     // generation's selection chain; every call that reads or writes the core state joins it first.
     return 0;
 }
@@ -1623,8 +1684,9 @@ int pansim_pair_counts(pansim_ctx *c, const uint32_t *r1, const uint32_t *r2, si
     if (core_diff) CU(c, cudaMemcpyAsync(core_diff, c->d_cd, P * 4, cudaMemcpyDeviceToHost, c->stream));
     if (inter) CU(c, cudaMemcpyAsync(inter, c->d_in, P * 4, cudaMemcpyDeviceToHost, c->stream));
     if (uni) CU(c, cudaMemcpyAsync(uni, c->d_un, P * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (int rc = flags_enqueue_readback(c)) return rc;
     CU(c, cudaStreamSynchronize(c->stream));
-    return 0;
+    return flags_inspect(c, PANSIM_ERR_WEIGHTS, "WeightedIndex::new would fail: a weight is negative/NaN or the total is not positive (population.rs:440)");
 }
 
 int pansim_pair_counts_device(pansim_ctx *c, const uint32_t *r1, const uint32_t *r2, size_t P, void *d_cd,
@@ -1636,8 +1698,9 @@ int pansim_pair_counts_device(pansim_ctx *c, const uint32_t *r1, const uint32_t 
     CU(c, cudaSetDevice(c->cfg.device));
     if (int rc = ensure_pairs(c, P)) return rc;
     if (int rc = pair_counts_impl(c, r1, r2, P, (uint32_t *)d_cd, (uint32_t *)d_in, (uint32_t *)d_un)) return rc;
+    if (int rc = flags_enqueue_readback(c)) return rc;
     CU(c, cudaStreamSynchronize(c->stream));
-    return 0;
+    return flags_inspect(c, PANSIM_ERR_WEIGHTS, "WeightedIndex::new would fail: a weight is negative/NaN or the total is not positive (population.rs:440)");
 }
 
 // Exact all-pairs extension: every pair (i, j), i in [row_begin, row_end), i < j < N, in (i, j)
@@ -1747,8 +1810,9 @@ int pansim_pair_counts_rows(pansim_ctx *c, uint32_t row_begin, uint32_t row_end,
     if (core_diff) CU(c, cudaMemcpyAsync(core_diff, c->d_cd, P * 4, cudaMemcpyDeviceToHost, c->stream));
     if (inter) CU(c, cudaMemcpyAsync(inter, c->d_in, P * 4, cudaMemcpyDeviceToHost, c->stream));
     if (uni) CU(c, cudaMemcpyAsync(uni, c->d_un, P * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (int rc = flags_enqueue_readback(c)) return rc;
     CU(c, cudaStreamSynchronize(c->stream));
-    return 0;
+    return flags_inspect(c, PANSIM_ERR_WEIGHTS, "WeightedIndex::new would fail: a weight is negative/NaN or the total is not positive (population.rs:440)");
 }
 
 int pansim_pair_counts_rows_device(pansim_ctx *c, uint32_t row_begin, uint32_t row_end, void *d_cd, void *d_in, void *d_un,
@@ -1760,8 +1824,9 @@ int pansim_pair_counts_rows_device(pansim_ctx *c, uint32_t row_begin, uint32_t r
     size_t P = 0;
     if (int rc = pair_counts_rows_impl(c, row_begin, row_end, (uint32_t *)d_cd, (uint32_t *)d_in, (uint32_t *)d_un, &P)) return rc;
     if (n_pairs_out) *n_pairs_out = P;
+    if (int rc = flags_enqueue_readback(c)) return rc;
     CU(c, cudaStreamSynchronize(c->stream));
-    return 0;
+    return flags_inspect(c, PANSIM_ERR_WEIGHTS, "WeightedIndex::new would fail: a weight is negative/NaN or the total is not positive (population.rs:440)");
 }
 
 int pansim_gene_counts(pansim_ctx *c, uint32_t *counts)
@@ -1784,13 +1849,20 @@ int pansim_enable_event_dump(pansim_ctx *c, size_t max_core_events)
     CU(c, cudaSetDevice(c->cfg.device));
     if (c->dump_enabled) FAIL(c, PANSIM_ERR_STATE, "event dump already enabled");
     const size_t n = max_core_events;
-    CU(c, cudaMalloc(&c->d_mut_row, n * 4)); CU(c, cudaMalloc(&c->d_mut_site, n * 4));
-    CU(c, cudaMalloc(&c->d_mut_seq, n * 4)); CU(c, cudaMalloc(&c->d_mut_allele, n));
-    CU(c, cudaMalloc(&c->d_hr_rec, n * 4)); CU(c, cudaMalloc(&c->d_hr_locus, n * 4));
-    CU(c, cudaMalloc(&c->d_hr_donor, n * 4)); CU(c, cudaMalloc(&c->d_hr_seq, n * 4));
-    CU(c, cudaMalloc(&c->d_hr_value, n));
     const size_t accw = (size_t)c->N * c->acc_stride_words * 4;
-    CU(c, cudaMalloc(&c->d_dump_flip, accw)); CU(c, cudaMalloc(&c->d_dump_gain, accw));
+    struct Want { void **p; size_t bytes; };
+    const Want want[] = {{(void **)&c->d_mut_row, n * 4}, {(void **)&c->d_mut_site, n * 4}, {(void **)&c->d_mut_seq, n * 4},
+                         {(void **)&c->d_mut_allele, n}, {(void **)&c->d_hr_rec, n * 4}, {(void **)&c->d_hr_locus, n * 4},
+                         {(void **)&c->d_hr_donor, n * 4}, {(void **)&c->d_hr_seq, n * 4}, {(void **)&c->d_hr_value, n},
+                         {(void **)&c->d_dump_flip, accw}, {(void **)&c->d_dump_gain, accw}};
+    for (const Want &w : want) {
+        if (cudaMalloc(w.p, w.bytes) != cudaSuccess) {
+            *w.p = nullptr;
+            for (const Want &u : want) { if (*u.p) cudaFree(*u.p); *u.p = nullptr; }      // nothing stays half-allocated
+            cudaGetLastError();
+            FAIL(c, PANSIM_ERR_NOMEM, "cudaMalloc for the event dump (%zu events) failed", n);
+        }
+    }
     CU(c, cudaMemset(c->d_dump_flip, 0, accw)); CU(c, cudaMemset(c->d_dump_gain, 0, accw));
     c->dump_cap = (uint32_t)n;
     c->dump_enabled = true;

@@ -718,3 +718,142 @@ def test_zero_core_mutation_rate_is_pure_gather():
         sim.run_generations(0, 1)
         parents = sim.parents()
         assert (sim.download_core() == core[parents]).all()
+
+
+# ------------------------------------------------ the benchmarked kernel instance vs the oracle chain
+@pytest.mark.parametrize("kw", [
+    dict(pop_size=48, core_size=30000, HR_rate=0.05),
+    dict(pop_size=64, core_size=8192 * 9 + 17, HR_rate=1.0, core_mu=0.2),      # several windows of 32 events per item
+    dict(pop_size=33, core_size=8192 * 3 + 999, HR_rate=4.0, core_mu=0.6, prop_positive=0.1, competition_strength=0.5),
+])
+def test_event_dump_run_equals_default_run(kw):
+    """bench.py times core_mut_kernel<RNG, no dump> with recombination deferred into the next launch
+    (hr_window_fetch/apply); the oracle replay tests above pin core_mut_kernel<RNG, DUMP> +
+    hr_collect_kernel<DUMP> (the event dump forces the immediate mode). Same Params and seed with and
+    without the dump must leave identical states and parents: this ties the benchmarked instance to
+    the oracle-verified one."""
+    p = small_params(n_gen=3, **kw)
+    d = pb.derive(p)
+    rng = np.random.default_rng(41)
+    core, acc = random_state(rng, p.pop_size, p.core_size, d.pan_size)
+    sel = rng.normal(0, 0.05, d.pan_size)
+    out = []
+    for dump in (False, True):
+        with make(p) as sim:
+            sim.upload(core, acc)
+            sim.set_selection(sel)
+            if dump:
+                sim.enable_event_dump(6_000_000)
+            per_gen = []
+            for g in range(3):
+                sim.step(g)
+                per_gen.append(sim.parents())
+            out.append((sim.download_core(), sim.download_acc(), np.stack(per_gen)))
+    for a, b in zip(*out):
+        assert (a == b).all()
+    assert (out[0][0] != core).any()
+
+
+@pytest.mark.parametrize("name,kw", [
+    ("cfg1", dict()),
+    ("cfg3", dict(HR_rate=1.0, HGT_rate=1.0, rate_genes2=1000.0)),
+])
+def test_parity_at_the_benchmark_shape(monkeypatch, name, kw):
+    """N = 1000, L = 1.2 Mbp, G = 4000 (BASELINE configs 1-3): the row-stationary pair plan, the
+    L2-sized column chunks and the batch launch shape (8 items per warp) only exist at this size.
+    Two generations, then (i) pair counts of 500 sampled pairs against the oracle's byte-per-site
+    popcount path on the downloaded state, (ii) deferred == immediate recombination, (iii) event
+    dump run == default run (the oracle-pinned instance, see test_event_dump_run_equals_default_run)."""
+    p = pb.Params(pop_size=1000, core_size=1_200_000, pan_genes=6000, core_genes=2000, n_gen=2, max_distances=500,
+                  seed=7, **kw)
+    d = pb.derive(p)
+    rng = np.random.default_rng(5)
+    core_row = (1 << rng.integers(0, 4, p.core_size)).astype(np.uint8)
+    acc_row = (rng.random(d.pan_size) < d.avg_gene_freq_adj).astype(np.uint8)
+    r1, r2 = sample_pairs(rng, p.pop_size, p.max_distances)
+
+    def run(defer, dump=False):
+        monkeypatch.setenv("PANSIM_HR_DEFER", defer)
+        with make(p) as sim:
+            sim.set_initial(core_row, acc_row)
+            if dump:
+                sim.enable_event_dump(140_000_000 if name == "cfg3" else 70_000_000)
+                for g in range(2):
+                    sim.step(g)
+            else:
+                sim.run_generations(0, 2)
+            cd, it, un = sim.pair_counts(r1, r2)
+            return sim.download_core(), sim.download_acc(), cd, it, un
+
+    core, acc, cd, it, un = run("1")
+    assert (core != core_row[None, :]).any()
+    ocore = ob.Population(core, True, p.core_genes)
+    assert (cd == ocore.pair_counts(r1, r2)).all()
+    oi, ou = ob.Population(acc, False, p.core_genes).pair_counts(r1, r2)
+    assert (it == oi).all() and (un == ou).all()
+    del ocore
+    core0, acc0, cd0, _, _ = run("0")
+    assert (cd0 == cd).all() and (acc0 == acc).all()
+    assert np.array_equal(core0, core)
+    del core0
+    if name == "cfg1":
+        cored, accd, cdd, _, _ = run("1", dump=True)
+        assert (cdd == cd).all() and (accd == acc).all()
+        assert np.array_equal(cored, core)
+
+
+def test_entry_point_orders_that_rotate_parents_without_a_core_step():
+    """A generate-mode step returns with the core kernel still in flight; every later reader must
+    join THAT launch even when pansim_sample_indices / pansim_next_generation have rotated the
+    parents buffers in between (the join event is per launch, not per parents slot)."""
+    p = small_params(pop_size=300, core_size=8192 * 60 + 5, n_gen=3, HR_rate=0.5)
+    d = pb.derive(p)
+    rng = np.random.default_rng(61)
+    core, acc = random_state(rng, p.pop_size, p.core_size, d.pan_size)
+    par = [rng.integers(0, p.pop_size, p.pop_size).astype(np.uint32) for _ in range(3)]
+    rev = np.arange(p.pop_size, dtype=np.uint32)[::-1].copy()
+
+    def reference_run():
+        with make(p) as sim:
+            sim.upload(core, acc)
+            sim.step_with_parents(0, par[0])
+            a = sim.download_core()                       # joins right after the step
+            sim.step_with_parents(1, par[1])
+            b = sim.download_core()
+            sim.next_generation(rev)
+            return a, b, sim.download_core()
+
+    a, b, c3 = reference_run()
+    with make(p) as sim:
+        sim.upload(core, acc)
+        sim.step_with_parents(0, par[0])
+        sim.sample_indices(7)                             # rotates the parents slot, launches no core step
+        assert (sim.download_core() == a).all()
+        sim.step_with_parents(1, par[1])
+        sim.sample_indices(8)
+        sim.sample_indices(9)
+        cd = sim.pair_counts([0, 5], [1, 6])[0]
+        assert cd[0] == (b[0] != b[1]).sum() and cd[1] == (b[5] != b[6]).sum()
+        assert (sim.download_core() == b).all()
+    with make(p) as sim:
+        sim.upload(core, acc)
+        sim.step_with_parents(0, par[0])
+        sim.step_with_parents(1, par[1])
+        sim.next_generation(rev)                          # plain gather right behind an in-flight generate step
+        assert (sim.download_core() == c3).all()
+
+
+def test_step_with_parents_consumes_the_vector_before_returning():
+    """The header's 'valid for the call' contract: the parents vector may be overwritten as soon as
+    the call returns (it is staged through the context's pinned buffer)."""
+    p = small_params(pop_size=500, core_size=8192 * 30, n_gen=2, HR_rate=0.0)
+    d = pb.derive(p)
+    rng = np.random.default_rng(62)
+    core, acc = random_state(rng, p.pop_size, p.core_size, d.pan_size)
+    par = rng.integers(0, p.pop_size, p.pop_size).astype(np.uint32)
+    with make(dataclasses.replace(p, core_mu=0.0)) as sim:
+        sim.upload(core, acc)
+        buf = par.copy()
+        sim.step_with_parents(0, buf)
+        buf[:] = 0                                        # scribble over it immediately
+        assert (sim.download_core() == core[par]).all()
