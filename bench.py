@@ -15,7 +15,15 @@ N > 1 (torchrun, one rank per GPU): weak scaling over columns -- every rank hold
 all individuals for its own 1.2 Mbp slice of an N x 1.2 Mbp alignment (accessory
 matrix replicated), so the job processes N cfg2-shaped slabs per step and `value`
 counts slab-generations per second. The generation step needs no collective; the
-distance pass all-reduces the per-pair partial core counts over NCCL.
+distance pass sums the per-pair partial core counts with NCCL inside the library
+(pansim_comm_init_rank; torch.distributed only carries the 128-byte unique id).
+
+Also in the line:
+  repeats        the K-step batch is timed R >= 10 times; value / ms_per_step are the median batch
+  shard_parity   (N > 1) a small column-sharded run equals the unsharded one bit for bit; the run
+                 fails when it does not
+  cfg2_print_dist  the cfg2 step WITH its per-generation distance pass and on-device statistics
+  cfg4_strong    BASELINE configs[3] (10 000 x 5 Mbp x 18 000) column-sharded over the N ranks
 """
 from __future__ import annotations
 
@@ -36,11 +44,17 @@ _JSON_OUT = sys.stdout
 CFG2 = dict(pop_size=1000, core_size=1_200_000, pan_genes=6000, core_genes=2000, n_gen=100,
             max_distances=100_000, prop_positive=0.1, competition_strength=0.5, seed=0)
 PEAK_FALLBACK_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
-# dram__bytes_read.sum + dram__bytes_write.sum of core_mut_kernel (a launch with recombination
-# events pending) from the committed ncu --set full capture (profiles/r01_core_mut_ncu_summary.txt),
-# per launch at this workload. ncu counts 54 MB of reads against 300 MB of algorithmic reads for
-# this kernel (bulk-copy loads); the write side (249 MB) matches.
-NCU_CORE_STEP_DRAM_BYTES = 299.9e6
+
+
+def ncu_traffic(kernel: str):
+    """DRAM bytes per launch of a kernel from the committed ncu capture (profiles/r02_dram_traffic.json,
+    made from the CSV files beside it); None when the file or the kernel is missing."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_dram_traffic.json")) as f:
+            e = json.load(f)[kernel]
+        return e
+    except Exception:
+        return None
 
 
 def selection_coefficients(rng, n, prop_positive, pos_lambda=10.0, neg_lambda=10.0):
@@ -160,8 +174,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "generations/sec", "value": val, "unit": "generations/s",
         "n_gpus": args.gpus, "steps": steps_run, "warmup": 1, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "cfg2", "pop_size": 1000, "core_size": 1200000, "pan_genes": 6000,
-                   "selection": "prop_positive=0.1", "competition_strength": 0.5},
+        "config": {"workload": "cfg2", "pop_size": 1000, "core_size": 1200000, "pan_genes": 6000, "accessory_genes": 4000,
+                   "selection": "prop_positive=0.1", "competition_strength": 0.5, "pairs": 100000},
         "cpu_baseline": {"value": val, "unit": "generations/s", "cores": threads, "kind": "port",
                          "sample": f"{steps_run} full cfg2 generations (oracle C port of population.rs, OpenMP over rows/pairs "
                                    f"where the reference uses rayon); distance pass on {pairs} pairs"},
@@ -174,11 +188,13 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-gens", type=int, default=2)
+    ap.add_argument("--repeats", type=int, default=10, help="batches of --steps generations; the median batch is reported")
+    ap.add_argument("--no-cfg4", action="store_true", help="skip the cfg4 strong-scaling record")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: libraries that print there (NCCL's version banner) are
     # sent to stderr, and the line is written to the saved descriptor at the end
@@ -223,8 +239,9 @@ def main():
 
     W = max(3, args.warmup)
     K = max(1, args.steps)
+    R = max(1, args.repeats)
     # this rank's slab: columns [rank*L, (rank+1)*L) of a (world*L)-site alignment
-    from pansim_b200.sharding import SITE_ALIGN, column_shards
+    from pansim_b200.sharding import SITE_ALIGN, ShardedPansim, broadcast_unique_id, column_shards
     L = CFG2["core_size"]
     Lslab = L if world == 1 else ((L + SITE_ALIGN - 1) // SITE_ALIGN) * SITE_ALIGN   # whole regions per rank
     total_L = L if world == 1 else Lslab * world
@@ -233,8 +250,16 @@ def main():
     # keep the per-site rates of cfg2: lambda scales with the alignment length (main.rs:275)
     p = pb.Params(**kw)
     d = pb.derive(p)
+
+    # ---- multi-GPU parity, visible to the driver: a small column-sharded run must equal the unsharded one
+    shard_parity = None
+    if world > 1:
+        shard_parity = check_shard_parity(pb, ShardedPansim, rank, world, local_rank, dist, torch)
+
     site_begin, site_end = (0, 0) if world == 1 else column_shards(total_L, world)[rank]
     sim = pb.Pansim.from_params(p, device=local_rank, site_begin=site_begin, site_end=site_end)
+    if world > 1:
+        sim.comm_init_rank(world, rank, broadcast_unique_id(rank))      # NCCL communicator inside the library
     info = sim.info()
 
     rng = np.random.default_rng(CFG2["seed"])           # identical on every rank
@@ -245,6 +270,14 @@ def main():
     sim.set_initial(core_row, acc_row)
     sim.set_selection(sel)
 
+    def gather_ranks(x: float):
+        if world == 1:
+            return [x]
+        t = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t[rank] = x
+        dist.all_reduce(t)
+        return [float(v) for v in t.tolist()]
+
     # ---- warm-up (also diversifies the clonal start) -------------------------
     t_load0 = time.time()
     gen = 0
@@ -252,66 +285,86 @@ def main():
     gen += W
     sim.pair_counts(r1, r2)
 
-    # ---- timed region: device-resident, K generations ------------------------
-    barrier()
-    t0 = time.perf_counter()
-    sim.run_generations(gen, K)                 # K x (competition, fitness, parents, acc step, core step)
-    tm = sim.timing()                            # synchronises the context's stream
-    barrier()
-    wall_ms = 1e3 * (time.perf_counter() - t0)
-    gen += K
-    dev_ms = max_over_ranks(float(tm.total_ms))
-    core_ms = float(tm.core_step_ms) / K            # core_mut_kernel (+ stand-alone recombination launches, if any)
+    # ---- timed region: device-resident, R batches of exactly K generations ----
+    batch_ms, batch_rank_ms, wall_ms_list = [], [], []
+    tm = None
+    for _ in range(R):
+        barrier()
+        t0 = time.perf_counter()
+        sim.run_generations(gen, K)             # K x (competition, fitness, parents, acc step, core step)
+        tm = sim.timing()                        # synchronises the context's streams
+        barrier()
+        wall_ms_list.append(1e3 * (time.perf_counter() - t0))
+        gen += K
+        per_rank = gather_ranks(float(tm.total_ms))
+        batch_rank_ms.append(per_rank)
+        batch_ms.append(max(per_rank))           # max over ranks
+    order = sorted(range(R), key=lambda i: batch_ms[i])
+    med = order[R // 2]
+    dev_ms = batch_ms[med]
+    wall_ms = wall_ms_list[med]
+    core_ms = float(tm.core_step_ms) / K            # last batch: core_mut_kernel (+ stand-alone recombination launches, if any)
     hr_ms = float(tm.core_hr_ms) / K                # stand-alone recombination launches: 0 in the deferred mode
     mut_ms = core_ms - hr_ms                        # core_mut_kernel: gather + deferred recombination + SNPs
     launches = int(tm.launches)
+    select_ms, acc_ms = tm.select_ms / K, tm.acc_step_ms / K
 
-    # ---- distance pass (device time of the kernels; pairs resident) ----------
+    # ---- distance pass (device time of the kernels; pairs resident; N > 1: + ncclAllReduce in the library) ----
     n_dist = max(3, min(10, K))
     pair_core_ms = pair_acc_ms = 0.0
+    pair_total = []
     barrier()
-    if world == 1:
-        for _ in range(n_dist):
-            sim.pair_counts(r1, r2)
-            t = sim.timing()
-            pair_core_ms += t.pair_core_ms
-            pair_acc_ms += t.pair_acc_ms
-            launches_dist = int(t.launches)
-    else:
-        d_cd = torch.zeros(p.max_distances, dtype=torch.int32, device="cuda")
-        d_in = torch.zeros_like(d_cd)
-        d_un = torch.zeros_like(d_cd)
-        for _ in range(n_dist):
-            sim.pair_counts_device(r1, r2, d_cd.data_ptr(), d_in.data_ptr(), d_un.data_ptr())
-            t = sim.timing()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            dist.all_reduce(d_cd)                # partial core counts summed over column shards
-            e1.record()
-            torch.cuda.synchronize()
-            pair_core_ms += t.pair_core_ms + e0.elapsed_time(e1)
-            pair_acc_ms += t.pair_acc_ms
-            launches_dist = int(t.launches)
+    for _ in range(n_dist):
+        sim.pair_counts(r1, r2)
+        t = sim.timing()
+        pair_core_ms += t.pair_core_ms
+        pair_acc_ms += t.pair_acc_ms
+        pair_total.append(float(t.total_ms))     # kernels + all-reduce, CUDA events on the library stream
     barrier()
-    pair_ms = max_over_ranks((pair_core_ms + pair_acc_ms) / n_dist)
+    pair_ms = max_over_ranks(float(np.median(pair_total)))
+
+    # ---- true cfg2: the step WITH its per-generation distance pass (main.rs:502-519) ----
+    # recombination materialised for the reader every generation, mean / std on the device
+    Kp = max(3, min(20, K))
+    barrier()
+    sim.run_generations_stats(gen, 2, r1, r2)
+    gen += 2
+    barrier()
+    stats = sim.run_generations_stats(gen, Kp, r1, r2)
+    tp = sim.timing()
+    gen += Kp
+    print_dist_ms = max_over_ranks(float(tp.total_ms)) / Kp
 
     # ---- end to end through the reference-facing API with HOST buffers --------
-    # per generation, exactly the calls main.rs:435-464 makes, vectors crossing the boundary
+    # per generation the calls main.rs:435-464 makes, vectors crossing the boundary
     Ke = min(K, 50)
-    barrier()
-    t0 = time.perf_counter()
-    for g in range(Ke):
-        avg = sim.average_distance()                       # d2h N f64
-        parents = sim.sample_indices(gen + g, avg)         # h2d N f64, d2h N u32
-        sim.step_with_parents(gen + g, parents)            # h2d N u32
-    barrier()
-    e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0) / Ke)
-    gen += Ke
+    e2e_runs = []
+    for _ in range(min(R, 5)):
+        barrier()
+        t0 = time.perf_counter()
+        for g in range(Ke):
+            avg, parents = sim.select_parents(gen + g)         # average_distance + sample_indices: d2h N f64 + N u32
+            sim.step_with_parents(gen + g, parents)            # h2d N u32
+        barrier()
+        e2e_runs.append(max_over_ranks(1e3 * (time.perf_counter() - t0) / Ke))
+        gen += Ke
+    e2e_ms = float(np.median(e2e_runs))
     t0 = time.perf_counter()
     for _ in range(3):
-        cd, it, un = sim.pair_counts(r1, r2)               # h2d 2 x P u32, d2h 3 x P u32
+        cd, it, un = sim.pair_counts(r1, r2)               # h2d 2 x P u32 (first call), d2h 3 x P u32
     e2e_pair_ms = 1e3 * (time.perf_counter() - t0) / 3
+    t0 = time.perf_counter()
+    for _ in range(3):
+        st1 = sim.pair_stats(r1, r2)                       # d2h 4 f64
+    e2e_stats_ms = 1e3 * (time.perf_counter() - t0) / 3
     clocks = sampler.stop(t_load0, time.time()) if sampler else None
+    sim.close()
+
+    # ---- cfg4: strong scaling of the SAME 10 000 x 5 Mbp x 18 000 problem over the ranks ----
+    cfg4 = None
+    if not args.no_cfg4:
+        cfg4 = run_cfg4_strong(pb, rank, world, local_rank, barrier, max_over_ranks, gather_ranks,
+                               column_shards, broadcast_unique_id)
 
     if rank != 0:
         if world > 1:
@@ -327,42 +380,74 @@ def main():
     value = world * K / (dev_ms * 1e-3)
     pair_bytes = int(info.algorithmic_bytes_per_pair)
     pairs_per_s = world * P / (pair_ms * 1e-3)
+    tr_core = ncu_traffic("core_mut_kernel")
+    tr_pair = ncu_traffic("pair_core_kernel")
+    words_per_pair = (info.local_sites + 15) // 16 + 2 * ((d.pan_size + 31) // 32)      # 32-bit word-compares
+    popc_peak = 16 * 148 * 1.965e9                                                    # POPC: 16 / clk / SM at 1965 MHz
+    compulsory = N * ((info.local_sites + 3) // 4 + (d.pan_size + 7) // 8)
 
     line = {
         "metric": "generations/sec", "value": value, "unit": "generations/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": "cfg2", "pop_size": N, "core_size_per_gpu": int(info.local_sites),
-                   "pan_genes": p.pan_genes, "accessory_genes": d.pan_size, "selection": "prop_positive=0.1",
+        "config": {"workload": "cfg2", "pop_size": N, "core_size": int(info.local_sites), "pan_genes": p.pan_genes,
+                   "accessory_genes": d.pan_size, "selection": "prop_positive=0.1",
                    "competition_strength": p.competition_strength, "pairs": P,
-                   "sharding": "columns; accessory replicated; no collective in the generation step",
+                   "core_size_per_gpu": int(info.local_sites),
+                   "sharding": "columns; accessory replicated; no collective in the generation step; "
+                               "distance pass: ncclAllReduce of the core counts inside the library",
                    "l2": "inputs larger than L2 (2 x %.0f MB packed state, double buffered)" % (info.core_state_bytes / 1e6),
-                   "timing": "CUDA events on the library stream around K generations, max over ranks"},
+                   "timing": "CUDA events on the library stream around each batch of K generations, max over ranks, "
+                             "median of the R batches"},
+        "repeats": {"n": R, "ms_per_step_min": min(batch_ms) / K, "ms_per_step_median": dev_ms / K,
+                    "ms_per_step_max": max(batch_ms) / K, "busy_ms": sum(batch_ms),
+                    "per_rank_ms_per_step_median_batch": [x / K for x in batch_rank_ms[med]]},
         "wall_ms_per_step": wall_ms / K,
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"kernel": "core_mut_kernel<RNG> (gather-by-parent + previous generation's recombination events + SNP "
                                "mutation in one pass, TMA bulk pipeline)",
                      "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": NCU_CORE_STEP_DRAM_BYTES, "peak_source": peak_src,
+                     "frac": achieved / peak,
+                     "traffic": (tr_core["dram_read_bytes"] + tr_core["dram_write_bytes"]) if tr_core else None,
+                     "traffic_source": tr_core["source"] if tr_core else None,
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": core_bytes, "launch_ms": mut_ms,
                      "core_genome_frac": core_bytes / (core_ms * 1e-3) / 1e9 / peak if core_ms > 0 else None,
                      "step_algorithmic_bytes": gen_bytes,
                      "step_frac": gen_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
                      "kernel_share_of_step": mut_ms / ms_per_step if ms_per_step > 0 else None,
-                     "breakdown_ms": {"select": tm.select_ms / K, "acc_step": tm.acc_step_ms / K, "core_step": core_ms,
+                     "breakdown_ms": {"select": select_ms, "acc_step": acc_ms, "core_step": core_ms,
                                       "core_mut": mut_ms, "core_hr": hr_ms}},
         "distances": {"value": pairs_per_s, "unit": "pairs/s", "ms_per_pass": pair_ms, "pairs": P,
                       "core_ms": pair_core_ms / n_dist, "acc_ms": pair_acc_ms / n_dist,
                       "streaming_GBps": pair_bytes * P / (pair_ms * 1e-3) / 1e9,
                       "streaming_frac_of_hbm_peak": pair_bytes * P / (pair_ms * 1e-3) / 1e9 / peak,
+                      "word_compares_per_pair": words_per_pair,
+                      "popc_pipe_frac": (P / (pair_ms * 1e-3)) * words_per_pair / popc_peak,
+                      "compulsory_dram_bytes": compulsory,
+                      "dram_bytes_per_pass": (tr_pair["dram_read_bytes"] + tr_pair["dram_write_bytes"]) if tr_pair else None,
+                      "dram_over_compulsory": ((tr_pair["dram_read_bytes"] + tr_pair["dram_write_bytes"]) / compulsory) if tr_pair else None,
+                      "dram_source": tr_pair["source"] if tr_pair else None,
                       "e2e_pairs_per_s": P / (e2e_pair_ms * 1e-3),
-                      "e2e_h2d_bytes": 8 * P, "e2e_d2h_bytes": 12 * P},
+                      "e2e_h2d_bytes": 0, "e2e_d2h_bytes": 12 * P,
+                      "e2e_note": "pair list unchanged since the previous call: validated and uploaded once (8 x P bytes), then cached",
+                      "e2e_stats_ms": e2e_stats_ms, "e2e_stats_d2h_bytes": 32},
+        "cfg2_print_dist": {"value": world / (print_dist_ms * 1e-3), "unit": "generations/s", "ms_per_generation": print_dist_ms,
+                            "generations": Kp, "d2h_bytes_per_generation": 32,
+                            "what": "pansim_run_generations_stats: generation step + recombination materialised + distance pass over "
+                                    "%d pairs + mean/std on the device, every generation (main.rs:435-519 with --print_dist)" % P,
+                            "last_stats": [float(x) for x in stats[-1]]},
         "e2e": {"value": world / (e2e_ms * 1e-3), "unit": "generations/s",
-                "h2d_bytes_per_step": 12 * N, "d2h_bytes_per_step": 12 * N, "ms_per_step": e2e_ms,
-                "path": "pansim_average_distance -> pansim_sample_indices -> pansim_step_with_parents, host vectors; "
-                        "the step call returns with the core kernel in flight, the loop ends with a device synchronize"},
+                "h2d_bytes_per_step": 4 * N, "d2h_bytes_per_step": 12 * N, "ms_per_step": e2e_ms,
+                "runs_ms_per_step": e2e_runs,
+                "path": "pansim_select_parents (average_distance + sample_indices, one read-back) -> pansim_step_with_parents, "
+                        "host vectors; the step call returns with the core kernel in flight, each run ends with a device synchronize"},
     }
+    if shard_parity is not None:
+        line["shard_parity"] = bool(shard_parity)
+    if cfg4 is not None:
+        line["cfg4_strong"] = cfg4
     if not args.no_cpu_baseline and world == 1:
         pairs_cpu = 2000
         threads, t_gen, t_dist = cpu_baseline_sample(args.cpu_gens, True, pairs_cpu)
@@ -372,9 +457,94 @@ def main():
                       f"reference uses rayon); distance pass on {pairs_cpu} of the pairs",
             "distances_pairs_per_s": args.cpu_gens * pairs_cpu / t_dist if t_dist > 0 else None}
     print(json.dumps(line), file=_JSON_OUT, flush=True)
-    sim.close()
     if world > 1:
         dist.destroy_process_group()
+    if shard_parity is False:
+        raise SystemExit("bench.py: column-sharded run differs from the unsharded run (shard_parity false)")
+
+
+def check_shard_parity(pb, ShardedPansim, rank, world, local_rank, dist, torch) -> bool:
+    """tests/multi_gpu_worker.py in short: sharded state, parents, all-reduced pair counts and
+    on-device statistics equal those of an unsharded context on the same device."""
+    p = pb.Params(pop_size=96, core_size=8192 * 9 + 123, pan_genes=700, core_genes=200, n_gen=3, max_distances=400,
+                  seed=5, prop_positive=0.1, competition_strength=0.3, HR_rate=0.5)
+    d = pb.derive(p)
+    rng = np.random.default_rng(1)
+    core_row = (1 << rng.integers(0, 4, p.core_size)).astype(np.uint8)
+    acc_row = (rng.random(d.pan_size) < 0.25).astype(np.uint8)
+    sel = rng.normal(0, 0.05, d.pan_size)
+    r1, r2 = sample_pairs(rng, p.pop_size, p.max_distances)
+    sh = ShardedPansim(p, rank, world, device=local_rank)
+    whole = pb.Pansim.from_params(p, device=local_rank)
+    for s in (sh, whole):
+        s.set_initial(core_row, acc_row)
+        s.set_selection(sel)
+        s.run_generations(0, p.n_gen)
+    b, e = sh.shards[rank]
+    ok = all((x == y).all() for x, y in zip(sh.pair_counts(r1, r2), whole.pair_counts(r1, r2)))
+    ok = ok and (sh.download_acc() == whole.download_acc()).all() and (sh.parents() == whole.parents()).all()
+    ok = ok and (sh.download_core() == whole.download_core()[:, b:e]).all()
+    ok = ok and sh.pair_stats(r1, r2) == whole.pair_stats(r1, r2)
+    sh.sim.close()
+    whole.close()
+    t = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return int(t.item()) == 1
+
+
+def run_cfg4_strong(pb, rank, world, local_rank, barrier, max_over_ranks, gather_ranks, column_shards, broadcast_unique_id):
+    """BASELINE configs[3]: pop_size 10 000, core 5 Mbp, 20 000 pan genes (18 000 accessory), defaults
+    otherwise (neutral, no competition), column-sharded over the ranks: STRONG scaling, every N runs
+    the same problem. Reports ms per generation (max over ranks) and the pieces that do not shrink."""
+    import torch
+    kw = dict(pop_size=10_000, core_size=5_000_000, pan_genes=20_000, core_genes=2_000, n_gen=500, max_distances=20_000, seed=0)
+    p = pb.Params(**kw)
+    d = pb.derive(p)
+    b, e = (0, 0) if world == 1 else column_shards(p.core_size, world)[rank]
+    try:
+        sim = pb.Pansim.from_params(p, device=local_rank, site_begin=b, site_end=e)
+    except Exception as ex:            # e.g. not enough memory beside another tenant
+        return {"error": str(ex)[:200]} if rank == 0 else None
+    if world > 1:
+        sim.comm_init_rank(world, rank, broadcast_unique_id(rank))
+    rng = np.random.default_rng(0)
+    core_row = (1 << rng.integers(0, 4, p.core_size)).astype(np.uint8)
+    acc_row = (rng.random(d.pan_size) < d.avg_gene_freq_adj).astype(np.uint8)
+    r1, r2 = sample_pairs(rng, p.pop_size, p.max_distances)
+    sim.set_initial(core_row, acc_row)
+    sim.set_selection(np.zeros(d.pan_size))
+    sim.run_generations(0, 3)
+    G = 10
+    runs = []
+    tm = None
+    for rep in range(3):
+        barrier()
+        sim.run_generations(3 + rep * G, G)
+        tm = sim.timing()
+        barrier()
+        runs.append(max(gather_ranks(float(tm.total_ms))) / G)
+    ms = float(np.median(runs))
+    core_ms = max_over_ranks(float(tm.core_step_ms) / G)
+    select_ms = max_over_ranks(float(tm.select_ms) / G)
+    acc_ms = max_over_ranks(float(tm.acc_step_ms) / G)
+    sim.pair_counts(r1, r2)
+    barrier()
+    sim.pair_counts(r1, r2)
+    tp = sim.timing()
+    pair_ms = max_over_ranks(float(tp.total_ms))
+    info = sim.info()
+    sim.close()
+    peak, _ = measured_peak()
+    total_bytes = 2 * p.pop_size * ((p.core_size + 3) // 4) + 2 * p.pop_size * ((d.pan_size + 7) // 8)
+    return {"workload": "cfg4", "pop_size": p.pop_size, "core_size": p.core_size, "accessory_genes": d.pan_size,
+            "n_gpus": world, "scaling": "strong", "generations": G, "ms_per_generation": ms, "runs_ms": runs,
+            "generations_per_s": 1e3 / ms, "local_sites": int(info.local_sites),
+            "hbm_frac_all_gpus": total_bytes / (ms * 1e-3) / 1e9 / (peak * world),
+            "core_step_ms": core_ms, "replicated_chain_ms": {"select": select_ms, "acc_step": acc_ms},
+            "note": "the selection chain and the accessory step are replicated on every rank (they do not shrink with N); "
+                    "they run on their own streams beside the core step",
+            "pairs": p.max_distances, "pair_pass_ms_incl_allreduce": pair_ms,
+            "pairs_per_s": p.max_distances / (pair_ms * 1e-3)}
 
 
 if __name__ == "__main__":

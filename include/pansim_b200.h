@@ -118,6 +118,9 @@ int pansim_average_distance(pansim_ctx *ctx, double *out);
  * Philox(seed, gen, individual). */
 int pansim_sample_indices(pansim_ctx *ctx, uint32_t gen, const double *avg_pairwise_dists,
                           uint32_t *parents_out);
+/* main.rs:435-443 in one call: average_distance when competition_strength > 0 (else all 1.0), then
+ * sample_indices; both vectors come back behind a single synchronisation. Either output may be NULL. */
+int pansim_select_parents(pansim_ctx *ctx, uint32_t gen, double *avg_pairwise_dists_out, uint32_t *parents_out);
 /* the intermediate vectors of population.rs:282-437 for parity checks; any may
  * be NULL. Valid after pansim_sample_indices. */
 int pansim_get_weights(pansim_ctx *ctx, double *weights, int32_t *num_genes, double *logfit);
@@ -190,6 +193,16 @@ int pansim_pair_counts_rows(pansim_ctx *ctx, uint32_t row_begin, uint32_t row_en
  * of column-sharded contexts) */
 int pansim_pair_counts_rows_device(pansim_ctx *ctx, uint32_t row_begin, uint32_t row_end, void *d_core_diff,
                                    void *d_inter, void *d_uni, size_t *n_pairs_out);
+/* The per-generation statistics of --print_dist (main.rs:502-519) computed on the device: the
+ * distance pass above followed by standard_deviation (population.rs:87-94) of both distance vectors.
+ * out[4] = { avg_core, std_core, avg_acc, std_acc }, the columns of _per_gen.tsv (main.rs:546). The
+ * four f64 sums are taken strictly left to right like `iter().sum::<f64>()`, so the values are the
+ * reference's bit for bit; 32 bytes leave the device instead of three count vectors. */
+int pansim_pair_stats(pansim_ctx *ctx, const uint32_t *range1, const uint32_t *range2, size_t n_pairs, double *out);
+/* n generations gen0..gen0+n-1, each followed by that pass and its statistics (the loop of
+ * main.rs:429-519 under --print_dist), without returning to the host: stats_out[n][4]. */
+int pansim_run_generations_stats(pansim_ctx *ctx, uint32_t gen0, uint32_t n, const uint32_t *range1,
+                                 const uint32_t *range2, size_t n_pairs, double *stats_out);
 /* the two f64 formulas (population.rs:822, :828-830), exported so every host
  * language forms the distances identically */
 double pansim_core_distance(uint32_t core_diff, uint64_t core_size);
@@ -197,6 +210,52 @@ double pansim_acc_distance(uint32_t inter, uint32_t uni, uint32_t core_genes);
 
 /* Population::gene_frequencies numerators (population.rs:840-856): counts[G] */
 int pansim_gene_counts(pansim_ctx *ctx, uint32_t *counts);
+
+/* ---- multi-GPU: column shards of one alignment --------------------------
+ * (the reference is one shared-memory process, population.rs has no analogue.)
+ * Every shard context holds all individuals for [site_begin, site_end) and a replica of the
+ * accessory matrix; parents, flips and HGT are recomputed identically everywhere from the same
+ * counters, so the generation step needs no exchange. The distance pass has one: the per-pair partial
+ * core counts are summed over the shards with NCCL inside the library.
+ *
+ * (a) one process per GPU (torchrun, MPI): rank 0 calls pansim_comm_unique_id, the host plumbing
+ *     broadcasts the 128 bytes, every rank calls pansim_comm_init_rank on its context. From then on
+ *     pansim_pair_counts / _device / _rows / _rows_device / pansim_pair_stats return WHOLE-alignment
+ *     core counts on every rank (ncclAllReduce on the context's stream before the read-back).
+ * (b) one process, several GPUs: pansim_group_* below (ncclCommInitAll). */
+#define PANSIM_COMM_ID_BYTES 128
+int pansim_comm_unique_id(void *id_out);
+int pansim_comm_init_rank(pansim_ctx *ctx, int n_ranks, int rank, const void *id);
+int pansim_comm_info(pansim_ctx *ctx, int *n_ranks, int *rank);
+
+/* (b) one process, several GPUs. The configuration describes the WHOLE alignment (site_begin =
+ *     site_end = 0, `device` ignored); devices == NULL means 0..n_devices-1. Calls mirror the
+ *     single-context ones and cite the same reference lines; each enqueues on every shard before it
+ *     synchronises, so a single host thread keeps all devices busy. */
+typedef struct pansim_group pansim_group;
+int  pansim_group_create(const pansim_config *cfg, int n_devices, const int *devices, pansim_group **out);
+void pansim_group_destroy(pansim_group *g);
+const char *pansim_group_last_error(const pansim_group *g);   /* g == NULL: last pansim_group_create failure */
+int  pansim_group_size(const pansim_group *g);
+pansim_ctx *pansim_group_ctx(pansim_group *g, int shard);     /* borrowed; shard i holds sites [begin_i, end_i) */
+int pansim_group_set_initial(pansim_group *g, const uint8_t *core_row_onehot, const uint8_t *acc_row);
+int pansim_group_set_selection(pansim_group *g, const double *s);
+int pansim_group_run_generations(pansim_group *g, uint32_t gen0, uint32_t n);            /* main.rs:435-464 x n */
+int pansim_group_pair_counts(pansim_group *g, const uint32_t *range1, const uint32_t *range2, size_t n_pairs,
+                             uint32_t *core_diff, uint32_t *inter, uint32_t *uni);      /* population.rs:787-837 */
+int pansim_group_run_generations_stats(pansim_group *g, uint32_t gen0, uint32_t n, const uint32_t *range1,
+                                       const uint32_t *range2, size_t n_pairs, double *stats_out);
+/* Exact all-pairs mode over the group (extension, BASELINE config 5): row blocks of about chunk_pairs
+ * pairs; per block the partial core counts are reduce-scattered over the shards while the next block
+ * is being computed. cb is called once per block, in (i, j) order; the vectors are valid during the
+ * call; a non-zero return stops the walk and is returned. */
+typedef int (*pansim_pairs_cb)(void *user, uint32_t row_begin, uint32_t row_end, size_t n_pairs,
+                               const uint32_t *core_diff, const uint32_t *inter, const uint32_t *uni);
+int pansim_group_all_pairs(pansim_group *g, size_t chunk_pairs, pansim_pairs_cb cb, void *user);
+int pansim_group_gene_counts(pansim_group *g, uint32_t *counts);                          /* population.rs:840-856 */
+int pansim_group_download_acc(pansim_group *g, uint8_t *acc_out);
+int pansim_group_download_core(pansim_group *g, uint8_t *core_onehot_out);               /* [N x core_size] */
+int pansim_group_export_core_csv(pansim_group *g, uint32_t row_begin, uint32_t row_end, char *out);
 
 /* ---- introspection / instrumentation ----------------------------------- */
 typedef struct {

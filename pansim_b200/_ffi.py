@@ -11,7 +11,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpansim_b200.so")
+LIB_PATH = os.environ.get("PANSIM_B200_LIB") or os.path.join(_HERE, "libpansim_b200.so")   # override: kernel-variant experiments
 
 EXPORTED = [
     "pansim_config_init", "pansim_create", "pansim_destroy", "pansim_last_error", "pansim_version",
@@ -24,7 +24,14 @@ EXPORTED = [
     "pansim_core_distance", "pansim_acc_distance", "pansim_gene_counts", "pansim_get_info",
     "pansim_get_timing", "pansim_set_timing", "pansim_enable_event_dump",
     "pansim_fetch_event_dump", "pansim_free_event_dump", "pansim_get_rates",
+    "pansim_select_parents", "pansim_pair_stats", "pansim_run_generations_stats",
+    "pansim_comm_unique_id", "pansim_comm_init_rank", "pansim_comm_info",
+    "pansim_group_create", "pansim_group_destroy", "pansim_group_last_error", "pansim_group_size", "pansim_group_ctx",
+    "pansim_group_set_initial", "pansim_group_set_selection", "pansim_group_run_generations", "pansim_group_pair_counts",
+    "pansim_group_run_generations_stats", "pansim_group_all_pairs", "pansim_group_gene_counts",
+    "pansim_group_download_acc", "pansim_group_download_core", "pansim_group_export_core_csv",
 ]
+COMM_ID_BYTES = 128
 
 
 class Config(C.Structure):
@@ -82,10 +89,14 @@ class EventDump(C.Structure):
     ]
 
 
+PAIRS_CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_size_t, C.POINTER(C.c_uint32),
+                       C.POINTER(C.c_uint32), C.POINTER(C.c_uint32))
+
+
 def build(force: bool = False) -> str:
     """Compile libpansim_b200.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
     src_dir = os.path.join(_HERE, "csrc")
-    srcs = [os.path.join(src_dir, f) for f in os.listdir(src_dir) if f.endswith((".cu", ".cuh"))]
+    srcs = [os.path.join(src_dir, f) for f in os.listdir(src_dir) if f.endswith((".cu", ".cuh", ".hpp", ".inl"))]
     srcs.append(os.path.join(_HERE, "..", "include", "pansim_b200.h"))
     stale = (not os.path.exists(LIB_PATH)) or any(
         os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs if os.path.exists(s))
@@ -153,5 +164,26 @@ def lib():
     sig("pansim_fetch_event_dump", cint, vp, C.POINTER(EventDump))
     sig("pansim_free_event_dump", None, C.POINTER(EventDump))
     sig("pansim_get_rates", cint, vp, vp)
+    sig("pansim_select_parents", cint, vp, u32, vp, vp)
+    sig("pansim_pair_stats", cint, vp, vp, vp, sz, vp)
+    sig("pansim_run_generations_stats", cint, vp, u32, u32, vp, vp, sz, vp)
+    sig("pansim_comm_unique_id", cint, vp)
+    sig("pansim_comm_init_rank", cint, vp, cint, cint, vp)
+    sig("pansim_comm_info", cint, vp, C.POINTER(cint), C.POINTER(cint))
+    sig("pansim_group_create", cint, C.POINTER(Config), cint, vp, C.POINTER(vp))
+    sig("pansim_group_destroy", None, vp)
+    sig("pansim_group_last_error", C.c_char_p, vp)
+    sig("pansim_group_size", cint, vp)
+    sig("pansim_group_ctx", vp, vp, cint)
+    sig("pansim_group_set_initial", cint, vp, vp, vp)
+    sig("pansim_group_set_selection", cint, vp, vp)
+    sig("pansim_group_run_generations", cint, vp, u32, u32)
+    sig("pansim_group_pair_counts", cint, vp, vp, vp, sz, vp, vp, vp)
+    sig("pansim_group_run_generations_stats", cint, vp, u32, u32, vp, vp, sz, vp)
+    sig("pansim_group_all_pairs", cint, vp, sz, PAIRS_CB, vp)
+    sig("pansim_group_gene_counts", cint, vp, vp)
+    sig("pansim_group_download_acc", cint, vp, vp)
+    sig("pansim_group_download_core", cint, vp, vp)
+    sig("pansim_group_export_core_csv", cint, vp, u32, u32, vp)
     _lib = L
     return L

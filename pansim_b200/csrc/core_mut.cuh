@@ -49,7 +49,13 @@
 
 namespace pansim {
 
-constexpr int CM_WARPS = 8;
+#ifndef PANSIM_CM_WARPS
+#define PANSIM_CM_WARPS 8
+#endif
+#ifndef PANSIM_CM_MAXREG
+#define PANSIM_CM_MAXREG 0          // > 0: cap registers per thread with __maxnreg__ instead of the launch bound
+#endif
+constexpr int CM_WARPS = PANSIM_CM_WARPS;
 #ifndef PANSIM_CM_STAGES
 #define PANSIM_CM_STAGES 3
 #endif
@@ -508,7 +514,11 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
 // CTAs are short-lived on purpose: SM slots turn over every few tens of microseconds, so the
 // (higher-priority) accessory/selection kernels of the next generation can slip in between.
 template <bool RNG, bool DUMP>
+#if PANSIM_CM_MAXREG
+__global__ void __maxnreg__(PANSIM_CM_MAXREG) core_mut_kernel(const CoreMutArgs a)
+#else
 __global__ void __launch_bounds__(CM_THREADS, CM_CTAS_PER_SM) core_mut_kernel(const CoreMutArgs a)
+#endif
 {
     extern __shared__ uint8_t smem_dyn[];
     const MutSmem m = mut_smem_carve(smem_dyn, a.mut_size, a.hr_nsub ? a.hr_size : 0u);

@@ -321,4 +321,101 @@ __global__ void __launch_bounds__(256) pair_acc_kernel(const uint32_t *acc, uint
     }
 }
 
+// --print_dist statistics (main.rs:502-519): standard_deviation (population.rs:87-94) of the two
+// distance vectors of one pass, on the device, so 32 bytes leave the GPU per generation instead of
+// the three count vectors. The reference sums with `iter().sum::<f64>()`, i.e. strictly left to
+// right, and the result is printed with 17 significant digits, so the summation ORDER is part of
+// the result: each of the four sums (two means, then two sums of squared deviations) is one chain
+// of dependent f64 additions made by a single thread in index order. Everything that is not the
+// chain -- the divisions of population.rs:822 / :828-830, x - mean, the square -- is done by a
+// producer warp one 1024-element chunk ahead, through shared memory. No fused multiply-add can
+// form: the products are rounded into shared memory before they are added (Rust has no contraction).
+// out[4] = { avg_core, std_core, avg_acc, std_acc } (the column order of _per_gen.tsv, main.rs:546).
+constexpr int STATS_CHUNK = 1024;
+constexpr int STATS_THREADS = 128;      // warp 0: core producer, 1: core chain, 2: accessory producer, 3: accessory chain
+
+struct PairStatsArgs {
+    const uint32_t *core_diff, *inter, *uni;
+    uint32_t n_pairs;
+    double core_size, core_genes;
+    double *out;
+};
+
+__global__ void __launch_bounds__(STATS_THREADS) pair_stats_kernel(const PairStatsArgs a)
+{
+    __shared__ double buf[2][2][STATS_CHUNK];      // [vector][stage][element]
+    __shared__ double mean_s[2];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t vec = warp >> 1;                // 0 = core distances, 1 = accessory distances
+    const bool producer = (warp & 1u) == 0u;
+    const uint32_t n = a.n_pairs;
+    const uint32_t n_chunks = (n + STATS_CHUNK - 1) / STATS_CHUNK;
+    const double dn = (double)n;
+
+    auto produce = [&](uint32_t c, int pass, double mean) {
+        double *dst = buf[vec][c & 1u];
+        const uint32_t k0 = c * STATS_CHUNK, k1 = min(n, k0 + STATS_CHUNK);
+        for (uint32_t k = k0 + lane; k < k1; k += 32) {
+            double d;
+            if (vec == 0) {
+                d = __ddiv_rn((double)a.core_diff[k], a.core_size);                                          // population.rs:822
+            } else {
+                const double num = __dadd_rn((double)a.inter[k], a.core_genes), den = __dadd_rn((double)a.uni[k], a.core_genes);
+                d = __dsub_rn(1.0, __ddiv_rn(num, den));                                                     // :828-830
+            }
+            if (pass == 1) {
+                const double diff = __dsub_rn(d, mean);                                                      // :90
+                d = __dmul_rn(diff, diff);
+            }
+            dst[k - k0] = d;
+        }
+    };
+
+    double sum = 0.0;
+    for (int pass = 0; pass < 2; pass++) {
+        const double mean = pass ? mean_s[vec] : 0.0;
+        if (producer && n_chunks) produce(0, pass, mean);
+        __syncthreads();
+        sum = 0.0;
+        for (uint32_t c = 0; c < n_chunks; c++) {
+            if (producer) {
+                if (c + 1 < n_chunks) produce(c + 1, pass, mean);
+            } else if (lane == 0) {
+                const double *src = buf[vec][c & 1u];
+                const uint32_t len = min((uint32_t)STATS_CHUNK, n - c * STATS_CHUNK);
+                // the chain: one dependent DADD per element (8.2 cycles each); the shared-memory loads of the
+                // next eight elements are issued before the current eight are added, so only the adds remain
+                uint32_t i = 0;
+                if (len >= 8) {
+                    double v[8], w[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) v[j] = src[j];
+                    for (i = 8; i + 8 <= len; i += 8) {
+#pragma unroll
+                        for (int j = 0; j < 8; j++) w[j] = src[i + j];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) sum = __dadd_rn(sum, v[j]);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) v[j] = w[j];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; j++) sum = __dadd_rn(sum, v[j]);
+                }
+                for (; i < len; i++) sum = __dadd_rn(sum, src[i]);
+            }
+            __syncthreads();
+        }
+        if (!producer && lane == 0) {
+            if (pass == 0) {
+                const double mean0 = __ddiv_rn(sum, dn);                                                     // :83-85
+                mean_s[vec] = mean0;
+                a.out[vec * 2] = mean0;
+            } else {
+                a.out[vec * 2 + 1] = __dsqrt_rn(__ddiv_rn(sum, dn));                                         // :92-93
+            }
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace pansim

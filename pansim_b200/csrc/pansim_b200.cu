@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "acc_step.cuh"
+#include "comm.hpp"
 #include "common.cuh"
 #include "core_hr.cuh"
 #include "core_mut.cuh"
@@ -197,6 +198,20 @@ struct pansim_ctx {
     // pair buffers
     uint32_t *d_r1 = nullptr, *d_r2 = nullptr, *d_cd = nullptr, *d_in = nullptr, *d_un = nullptr;
     size_t pair_cap = 0;
+    bool pairs_on_device = false;        // d_r1 / d_r2 hold plan_r1 / plan_r2
+    uint32_t *d_cnt2[3] = {nullptr, nullptr, nullptr};   // second set of count vectors (per-generation statistics batch)
+    size_t cnt2_cap = 0;
+    double *d_stats = nullptr, *h_stats = nullptr;       // per-generation statistics (4 doubles each), device / pinned
+    size_t stats_cap = 0;
+    cudaStream_t stream_stats2[2] = {nullptr, nullptr};   // statistics kernels of consecutive generations run side by side
+    cudaEvent_t ev_pairs[2] = {nullptr, nullptr}, ev_stats[2] = {nullptr, nullptr};
+    bool ev_stats_valid[2] = {false, false};
+
+    // column shards of one alignment: NCCL communicator over the shards (comm.hpp). With a communicator the
+    // pair-count entry points return whole-alignment core counts (summed over the shards on the device).
+    ncclComm_t comm = nullptr;
+    int comm_size = 1, comm_rank = 0;
+    bool comm_owned = false;             // created by pansim_comm_init_rank (a pansim_group owns its communicators itself)
 
     // replay staging
     void *d_replay = nullptr;
@@ -387,6 +402,23 @@ int check_device_flag(pansim_ctx *c, int code, const char *what)
     return flags_inspect(c, code, what);
 }
 
+#define NCK(ctx, call)                                                                            \
+    do {                                                                                          \
+        ncclResult_t _r = (call);                                                                 \
+        if (_r != ncclSuccess)                                                                    \
+            FAIL(ctx, PANSIM_ERR_CUDA, "%s failed: %s (%s:%d)", #call, nccl_api().GetErrorString(_r), __FILE__, __LINE__); \
+    } while (0)
+
+// sum of the per-pair partial core counts over the column shards, in place, on c->stream (C2 of SURVEY.md 2)
+int comm_allreduce_counts(pansim_ctx *c, uint32_t *d_counts, size_t n)
+{
+    if (!c->comm || c->comm_size < 2 || !d_counts || !n) return 0;
+    NCK(c, nccl_api().AllReduce(d_counts, d_counts, n, ncclUint32, ncclSum, c->comm, c->stream));
+    c->launches++;
+    timing_end(c);          // the collective belongs to the pass it completes (total_ms of pansim_get_timing)
+    return 0;
+}
+
 // ---- kernel group launchers (asynchronous on ctx->stream) -----------------
 
 // order `stream` after the fitness kernel that launch_competition started on the aux stream
@@ -481,8 +513,10 @@ int launch_select(pansim_ctx *c, uint32_t gen, bool use_avgdist)
         FineSpan fs(c, TG_D_SEL);
         if (c->N <= SEL_SMALL_MAX)
             launch_dependent(c, select_parents_small_kernel, dim3(1), dim3(SEL_THREADS), 0, c->stream, a);
+        else if (c->N <= 4096)
+            launch_dependent(c, select_parents_kernel<SEL_THREADS>, dim3(1), dim3(SEL_THREADS), 0, c->stream, a);
         else
-            launch_dependent(c, select_parents_kernel, dim3(1), dim3(SEL_THREADS), 0, c->stream, a);
+            launch_dependent(c, select_parents_kernel<1024>, dim3(1), dim3(1024), 0, c->stream, a);
     }
     LAUNCH_CHECK(c);
     return 0;
@@ -774,6 +808,10 @@ void pansim_destroy(pansim_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->cfg.device);
+    if (c->comm && c->comm_owned) {
+        if (c->stream) cudaStreamSynchronize(c->stream);
+        nccl_api().CommDestroy(c->comm);
+    }
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->stream_core) cudaStreamSynchronize(c->stream_core);
     if (c->stream_aux) cudaStreamSynchronize(c->stream_aux);
@@ -791,6 +829,14 @@ void pansim_destroy(pansim_ctx *c)
         if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
     }
     if (c->h_avg) cudaFreeHost(c->h_avg);
+    if (c->h_stats) cudaFreeHost(c->h_stats);
+    if (c->d_stats) cudaFree(c->d_stats);
+    for (auto q : c->d_cnt2) if (q) cudaFree(q);
+    for (int i = 0; i < 2; i++) {
+        if (c->ev_pairs[i]) cudaEventDestroy(c->ev_pairs[i]);
+        if (c->ev_stats[i]) cudaEventDestroy(c->ev_stats[i]);
+    }
+    for (auto st : c->stream_stats2) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
     if (c->h_err) cudaFreeHost(c->h_err);
     c->pool.destroy();
     for (int i = 0; i < 3; i++) {
@@ -1005,10 +1051,13 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
             c->core_items_per_warp = (uint32_t)std::max<uint64_t>(1, (items + ctas * CM_WARPS - 1) / (ctas * CM_WARPS));
         }
         if (const char *e = getenv("PANSIM_CORE_ITEMS_PER_WARP")) c->core_items_per_warp = (uint32_t)std::max(1, atoi(e));
-        // In the device-resident batch nobody waits on the selection chain, so the CTAs may live longer
-        // (measured at cfg2: 3 -> 8 items per warp, +1.6 % generations/s; 12 makes the chain the critical path; through the host-driven calls the
-        // same change costs 12 % because the chain kernels queue longer for SM slots).
-        c->core_items_batch = std::max(c->core_items_per_warp, 8u);
+        // Items per warp in the device-resident batch. A CTA of this kernel fills its SM slot completely
+        // (registers and shared memory), so a selection-chain kernel of the NEXT generation can only start
+        // where a core CTA has just retired: the shorter the CTAs live, the sooner the chain gets its slots,
+        // and the chain (select + accessory step, ~150 us serial under contention) is what the core step waits
+        // for once the kernel itself is fast enough. Measured at cfg2 (round 2, us per generation): 3 items 168.7,
+        // 4 items 164.2, 6 items 171.1, 8 items 179.7, 12 items 182.8.
+        c->core_items_batch = std::max(c->core_items_per_warp, 4u);
         if (const char *e = getenv("PANSIM_CORE_ITEMS_BATCH")) c->core_items_batch = (uint32_t)std::max(0, atoi(e));
         const uint64_t per_cta = (uint64_t)CM_WARPS * c->core_items_per_warp;
         c->core_grid = (uint32_t)std::max<uint64_t>(1, (items + per_cta - 1) / per_cta);
@@ -1244,8 +1293,9 @@ int pansim_average_distance(pansim_ctx *c, double *out)
         if (int rc = launch_competition(c)) return rc;
     }
     timing_end(c);
-    if (out) CU(c, cudaMemcpyAsync(out, c->d_avgdist, (size_t)c->N * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (out) CU(c, cudaMemcpyAsync(c->h_avg, c->d_avgdist, (size_t)c->N * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
+    if (out) memcpy(out, c->h_avg, (size_t)c->N * 8);
     return 0;
 }
 
@@ -1258,7 +1308,8 @@ int pansim_sample_indices(pansim_ctx *c, uint32_t gen, const double *avg, uint32
     if (int rc = next_parents_buffer(c)) return rc;
     bool use_avg = false;
     if (avg) {
-        CU(c, cudaMemcpyAsync(c->d_avgdist, avg, (size_t)c->N * 8, cudaMemcpyHostToDevice, c->stream));
+        memcpy(c->h_avg, avg, (size_t)c->N * 8);      // pinned staging: the copy is a plain DMA (the previous use of h_avg was synchronised)
+        CU(c, cudaMemcpyAsync(c->d_avgdist, c->h_avg, (size_t)c->N * 8, cudaMemcpyHostToDevice, c->stream));
         use_avg = true;
     } else if (c->cfg.competition_strength > 0.0) {
         if (!c->avgdist_valid) FAIL(c, PANSIM_ERR_STATE, "competition_strength > 0: call pansim_average_distance first or pass avg_pairwise_dists");
@@ -1273,6 +1324,39 @@ int pansim_sample_indices(pansim_ctx *c, uint32_t gen, const double *avg, uint32
     // one read-back, one synchronisation: the parents and the kernel's status word behind them
     CU(c, cudaMemcpyAsync(c->h_parents, c->d_parents, ((size_t)c->N + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
+    if (parents_out) memcpy(parents_out, c->h_parents, (size_t)c->N * 4);
+    if (c->h_parents[c->N]) {
+        cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream);
+        FAIL(c, PANSIM_ERR_WEIGHTS, "WeightedIndex::new would fail: a weight is negative/NaN or the total is not positive (population.rs:440)");
+    }
+    return 0;
+}
+
+// main.rs:435-443 as ONE call: average_distance (if competition_strength > 0) + sample_indices, both
+// vectors read back behind a single synchronisation.
+int pansim_select_parents(pansim_ctx *c, uint32_t gen, double *avg_out, uint32_t *parents_out)
+{
+    if (!c) return PANSIM_ERR_INVALID;
+    if (int rc = require_state(c)) return rc;
+    CU(c, cudaSetDevice(c->cfg.device));
+    c->pdl_now = true;
+    if (int rc = next_parents_buffer(c)) return rc;
+    timing_begin(c);
+    const bool use_avg = c->cfg.competition_strength > 0.0;          // main.rs:438-440
+    {
+        ScopedSpan s(c, TG_SELECT);
+        if (use_avg)
+            if (int rc = launch_competition(c)) return rc;
+        if (int rc = launch_select(c, gen, use_avg)) return rc;
+    }
+    timing_end(c);
+    if (avg_out && use_avg) CU(c, cudaMemcpyAsync(c->h_avg, c->d_avgdist, (size_t)c->N * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(c->h_parents, c->d_parents, ((size_t)c->N + 1) * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (avg_out) {
+        if (use_avg) memcpy(avg_out, c->h_avg, (size_t)c->N * 8);
+        else for (uint32_t i = 0; i < c->N; i++) avg_out[i] = 1.0;    // main.rs:435
+    }
     if (parents_out) memcpy(parents_out, c->h_parents, (size_t)c->N * 4);
     if (c->h_parents[c->N]) {
         cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream);
@@ -1344,9 +1428,11 @@ int pansim_step_with_parents(pansim_ctx *c, uint32_t gen, const uint32_t *parent
 
 int pansim_step(pansim_ctx *c, uint32_t gen) { return pansim_run_generations(c, gen, 1); }
 
-int pansim_run_generations(pansim_ctx *c, uint32_t gen0, uint32_t n)
+#define PANSIM_WEIGHTS_MSG "WeightedIndex::new would fail: a weight is negative/NaN or the total is not positive (population.rs:440)"
+
+// enqueue n generations (asynchronous); the caller synchronises and inspects the device flags
+static int run_generations_enqueue(pansim_ctx *c, uint32_t gen0, uint32_t n)
 {
-    if (!c) return PANSIM_ERR_INVALID;
     if (int rc = require_state(c)) return rc;
     CU(c, cudaSetDevice(c->cfg.device));
     if (c->dump_enabled) CU(c, cudaMemsetAsync(c->d_dump_counters, 0, 2 * sizeof(uint32_t), c->stream));
@@ -1356,7 +1442,14 @@ int pansim_run_generations(pansim_ctx *c, uint32_t gen0, uint32_t n)
         if (int rc = step_device(c, gen0 + g)) return rc;
     if (int rc = join_core_stream(c)) return rc;
     timing_end(c);
-    return check_device_flag(c, PANSIM_ERR_WEIGHTS, "WeightedIndex::new would fail: a weight is negative/NaN or the total is not positive (population.rs:440)");
+    return 0;
+}
+
+int pansim_run_generations(pansim_ctx *c, uint32_t gen0, uint32_t n)
+{
+    if (!c) return PANSIM_ERR_INVALID;
+    if (int rc = run_generations_enqueue(c, gen0, n)) return rc;
+    return check_device_flag(c, PANSIM_ERR_WEIGHTS, PANSIM_WEIGHTS_MSG);
 }
 
 int pansim_next_generation(pansim_ctx *c, const uint32_t *parents)
@@ -1482,6 +1575,7 @@ static int ensure_pairs(pansim_ctx *c, size_t n)
         *p = nullptr;
     }
     c->pair_cap = 0;
+    c->pairs_on_device = false;
     for (uint32_t **p : {&c->d_r1, &c->d_r2, &c->d_cd, &c->d_in, &c->d_un})
         if (cudaMalloc(p, n * 4) != cudaSuccess) FAIL(c, PANSIM_ERR_NOMEM, "cudaMalloc for %zu pairs failed", n);
     c->pair_cap = n;
@@ -1641,17 +1735,34 @@ static int launch_pair_core(pansim_ctx *c, uint32_t *d_cd, size_t P, uint32_t ro
     return 0;
 }
 
-static int pair_counts_impl(pansim_ctx *c, const uint32_t *r1, const uint32_t *r2, size_t P, uint32_t *d_cd,
-                            uint32_t *d_in, uint32_t *d_un)
+// Validate the pair list, build (or reuse) its plan and put range1/range2 on the device. A list that
+// equals the cached one (the pairs are fixed for a whole run, main.rs:413-427) has been validated and
+// uploaded before: two memcmp and nothing else.
+static int pair_prepare(pansim_ctx *c, const uint32_t *r1, const uint32_t *r2, size_t P)
 {
     if (P > 0x7FFFFFFFull) FAIL(c, PANSIM_ERR_INVALID, "more than 2^31 pairs per call");
+    if (c->pairs_on_device && c->plan_r1.size() == P && memcmp(c->plan_r1.data(), r1, P * 4) == 0 &&
+        memcmp(c->plan_r2.data(), r2, P * 4) == 0)
+        return 0;
     for (size_t k = 0; k < P; k++)
         if (r1[k] >= c->N || r2[k] >= c->N) FAIL(c, PANSIM_ERR_INVALID, "pair %zu out of range", k);
-    if (d_cd && c->Ll)
+    c->pairs_on_device = false;
+    if (c->Ll) {
         if (int rc = ensure_pair_plan(c, r1, r2, P)) return rc;
-    CU(c, cudaMemcpyAsync(c->d_r1, r1, P * 4, cudaMemcpyHostToDevice, c->stream));
-    CU(c, cudaMemcpyAsync(c->d_r2, r2, P * 4, cudaMemcpyHostToDevice, c->stream));
-    timing_begin(c);
+    } else {
+        c->plan_r1.assign(r1, r1 + P);
+        c->plan_r2.assign(r2, r2 + P);
+    }
+    CU(c, cudaMemcpyAsync(c->d_r1, c->plan_r1.data(), P * 4, cudaMemcpyHostToDevice, c->stream));   // from the context's copy:
+    CU(c, cudaMemcpyAsync(c->d_r2, c->plan_r2.data(), P * 4, cudaMemcpyHostToDevice, c->stream));   // the caller's may go away
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->pairs_on_device = true;
+    return 0;
+}
+
+// the kernels of one distance pass over the prepared pairs (asynchronous on c->stream)
+static int pair_launch(pansim_ctx *c, size_t P, uint32_t *d_cd, uint32_t *d_in, uint32_t *d_un)
+{
     if (d_cd && c->Ll)
         if (int rc = core_materialize(c, c->stream)) return rc;     // recombination events still pending on the rows
     if (d_cd) {
@@ -1668,6 +1779,15 @@ static int pair_counts_impl(pansim_ctx *c, const uint32_t *r1, const uint32_t *r
         pair_acc_kernel<<<grid ? grid : 1, 256, 0, c->stream>>>(c->acc[c->acc_cur], c->acc_stride_words, c->acc_words, c->d_r1, c->d_r2, (uint32_t)P, d_in, d_un);
         LAUNCH_CHECK(c);
     }
+    return 0;
+}
+
+static int pair_counts_impl(pansim_ctx *c, const uint32_t *r1, const uint32_t *r2, size_t P, uint32_t *d_cd,
+                            uint32_t *d_in, uint32_t *d_un)
+{
+    if (int rc = pair_prepare(c, r1, r2, P)) return rc;
+    timing_begin(c);
+    if (int rc = pair_launch(c, P, d_cd, d_in, d_un)) return rc;
     timing_end(c);
     return 0;
 }
@@ -1681,6 +1801,8 @@ int pansim_pair_counts(pansim_ctx *c, const uint32_t *r1, const uint32_t *r2, si
     CU(c, cudaSetDevice(c->cfg.device));
     if (int rc = ensure_pairs(c, P)) return rc;
     if (int rc = pair_counts_impl(c, r1, r2, P, core_diff ? c->d_cd : nullptr, (inter || uni) ? c->d_in : nullptr, (inter || uni) ? c->d_un : nullptr)) return rc;
+    if (core_diff)
+        if (int rc = comm_allreduce_counts(c, c->d_cd, P)) return rc;
     if (core_diff) CU(c, cudaMemcpyAsync(core_diff, c->d_cd, P * 4, cudaMemcpyDeviceToHost, c->stream));
     if (inter) CU(c, cudaMemcpyAsync(inter, c->d_in, P * 4, cudaMemcpyDeviceToHost, c->stream));
     if (uni) CU(c, cudaMemcpyAsync(uni, c->d_un, P * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -1698,9 +1820,122 @@ int pansim_pair_counts_device(pansim_ctx *c, const uint32_t *r1, const uint32_t 
     CU(c, cudaSetDevice(c->cfg.device));
     if (int rc = ensure_pairs(c, P)) return rc;
     if (int rc = pair_counts_impl(c, r1, r2, P, (uint32_t *)d_cd, (uint32_t *)d_in, (uint32_t *)d_un)) return rc;
+    if (int rc = comm_allreduce_counts(c, (uint32_t *)d_cd, P)) return rc;
     if (int rc = flags_enqueue_readback(c)) return rc;
     CU(c, cudaStreamSynchronize(c->stream));
     return flags_inspect(c, PANSIM_ERR_WEIGHTS, "WeightedIndex::new would fail: a weight is negative/NaN or the total is not positive (population.rs:440)");
+}
+
+// ---- --print_dist statistics on the device (main.rs:502-519, population.rs:87-94) -------------
+static int ensure_stats(pansim_ctx *c, size_t n_gen, size_t P, bool second_counts)
+{
+    if (!c->stream_stats2[0]) {
+        int lo = 0, hi = 0;
+        CU(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        for (int i = 0; i < 2; i++) {
+            CU(c, cudaStreamCreateWithPriority(&c->stream_stats2[i], cudaStreamNonBlocking, hi));
+            CU(c, cudaEventCreateWithFlags(&c->ev_pairs[i], cudaEventDisableTiming));
+            CU(c, cudaEventCreateWithFlags(&c->ev_stats[i], cudaEventDisableTiming));
+        }
+    }
+    if (n_gen > c->stats_cap) {
+        if (c->d_stats) cudaFree(c->d_stats);
+        if (c->h_stats) cudaFreeHost(c->h_stats);
+        c->d_stats = nullptr; c->h_stats = nullptr; c->stats_cap = 0;
+        CU(c, cudaMalloc(&c->d_stats, n_gen * 4 * sizeof(double)));
+        CU(c, cudaMallocHost(&c->h_stats, n_gen * 4 * sizeof(double)));
+        c->stats_cap = n_gen;
+    }
+    if (second_counts && P > c->cnt2_cap) {
+        for (auto &q : c->d_cnt2) { if (q) cudaFree(q); q = nullptr; }
+        c->cnt2_cap = 0;
+        for (auto &q : c->d_cnt2)
+            if (cudaMalloc(&q, P * 4) != cudaSuccess) FAIL(c, PANSIM_ERR_NOMEM, "cudaMalloc for %zu pairs failed", P);
+        c->cnt2_cap = P;
+    }
+    return 0;
+}
+
+// statistics kernel of one pass on the statistics stream, behind the pass on c->stream
+static int launch_pair_stats(pansim_ctx *c, int slot, size_t P, const uint32_t *d_cd, const uint32_t *d_in, const uint32_t *d_un,
+                             double *d_out)
+{
+    CU(c, cudaEventRecord(c->ev_pairs[slot], c->stream));
+    cudaStream_t st = c->stream_stats2[slot];
+    CU(c, cudaStreamWaitEvent(st, c->ev_pairs[slot], 0));
+    PairStatsArgs a;
+    a.core_diff = d_cd; a.inter = d_in; a.uni = d_un;
+    a.n_pairs = (uint32_t)P;
+    a.core_size = (double)c->L;
+    a.core_genes = (double)c->cfg.core_genes;
+    a.out = d_out;
+    pair_stats_kernel<<<1, STATS_THREADS, 0, st>>>(a);
+    LAUNCH_CHECK(c);
+    CU(c, cudaEventRecord(c->ev_stats[slot], st));
+    c->ev_stats_valid[slot] = true;
+    return 0;
+}
+
+static int require_whole_alignment(pansim_ctx *c, const char *what)
+{
+    if (c->Ll != c->L && !c->comm) FAIL(c, PANSIM_ERR_STATE, "%s on a column shard needs a communicator (pansim_comm_init_rank): core counts are partial", what);
+    return 0;
+}
+
+int pansim_pair_stats(pansim_ctx *c, const uint32_t *r1, const uint32_t *r2, size_t P, double *out)
+{
+    if (!c || !out || !P || !r1 || !r2) return PANSIM_ERR_INVALID;
+    if (int rc = require_state(c)) return rc;
+    if (int rc = require_whole_alignment(c, "pansim_pair_stats")) return rc;
+    CU(c, cudaSetDevice(c->cfg.device));
+    if (int rc = ensure_pairs(c, P)) return rc;
+    if (int rc = ensure_stats(c, 1, P, false)) return rc;
+    if (int rc = pair_counts_impl(c, r1, r2, P, c->d_cd, c->d_in, c->d_un)) return rc;
+    if (int rc = comm_allreduce_counts(c, c->d_cd, P)) return rc;
+    if (int rc = launch_pair_stats(c, 0, P, c->d_cd, c->d_in, c->d_un, c->d_stats)) return rc;
+    CU(c, cudaMemcpyAsync(c->h_stats, c->d_stats, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream_stats2[0]));
+    if (int rc = flags_enqueue_readback(c)) return rc;
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaStreamSynchronize(c->stream_stats2[0]));
+    memcpy(out, c->h_stats, 4 * sizeof(double));
+    return flags_inspect(c, PANSIM_ERR_WEIGHTS, "WeightedIndex::new would fail: a weight is negative/NaN or the total is not positive (population.rs:440)");
+}
+
+// n generations, each followed by the distance pass and its statistics, without returning to the
+// host: the loop main.rs:429-519 runs with --print_dist. 32 bytes per generation leave the device.
+int pansim_run_generations_stats(pansim_ctx *c, uint32_t gen0, uint32_t n, const uint32_t *r1, const uint32_t *r2, size_t P,
+                                 double *stats_out)
+{
+    if (!c || !stats_out || !P || !r1 || !r2) return PANSIM_ERR_INVALID;
+    if (int rc = require_state(c)) return rc;
+    if (int rc = require_whole_alignment(c, "pansim_run_generations_stats")) return rc;
+    if (n == 0) return 0;
+    CU(c, cudaSetDevice(c->cfg.device));
+    if (int rc = ensure_pairs(c, P)) return rc;
+    if (int rc = ensure_stats(c, n, P, true)) return rc;
+    if (int rc = pair_prepare(c, r1, r2, P)) return rc;
+    if (c->dump_enabled) CU(c, cudaMemsetAsync(c->d_dump_counters, 0, 2 * sizeof(uint32_t), c->stream));
+    c->pdl_now = false;
+    timing_begin(c);
+    for (uint32_t g = 0; g < n; g++) {
+        if (int rc = step_device(c, gen0 + g)) return rc;
+        const int slot = (int)(g & 1u);
+        uint32_t *cd = slot ? c->d_cnt2[0] : c->d_cd, *in = slot ? c->d_cnt2[1] : c->d_in, *un = slot ? c->d_cnt2[2] : c->d_un;
+        // the statistics kernel of two generations ago still reads this set of count vectors
+        if (c->ev_stats_valid[slot]) CU(c, cudaStreamWaitEvent(c->stream, c->ev_stats[slot], 0));
+        if (int rc = pair_launch(c, P, cd, in, un)) return rc;
+        if (int rc = comm_allreduce_counts(c, cd, P)) return rc;
+        if (int rc = launch_pair_stats(c, slot, P, cd, in, un, c->d_stats + (size_t)g * 4)) return rc;
+    }
+    if (int rc = join_core_stream(c)) return rc;
+    // the batch ends when the last statistics are in: c->stream joins both statistics streams
+    for (int i = 0; i < 2; i++)
+        if (c->ev_stats_valid[i]) CU(c, cudaStreamWaitEvent(c->stream, c->ev_stats[i], 0));
+    timing_end(c);
+    CU(c, cudaMemcpyAsync(c->h_stats, c->d_stats, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (int rc = check_device_flag(c, PANSIM_ERR_WEIGHTS, "WeightedIndex::new would fail: a weight is negative/NaN or the total is not positive (population.rs:440)")) return rc;
+    memcpy(stats_out, c->h_stats, (size_t)n * 4 * sizeof(double));
+    return 0;
 }
 
 // Exact all-pairs extension: every pair (i, j), i in [row_begin, row_end), i < j < N, in (i, j)
@@ -1761,6 +1996,7 @@ static int pair_counts_rows_impl(pansim_ctx *c, uint32_t row_begin, uint32_t row
     CU(c, cudaMemcpyAsync(d_goff, goff.data(), goff.size() * 4, cudaMemcpyHostToDevice, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));                 // the host vectors go out of scope
     c->plan_r1.clear(); c->plan_r2.clear();                  // the cached sampled-pair plan is gone
+    c->pairs_on_device = false;
     c->plan_batches = 0;
     timing_begin(c);
     if (c->Ll)
@@ -1807,6 +2043,8 @@ int pansim_pair_counts_rows(pansim_ctx *c, uint32_t row_begin, uint32_t row_end,
                                        (inter || uni) ? c->d_un : nullptr, &P)) return rc;
     if (n_pairs_out) *n_pairs_out = P;
     if (P == 0) return 0;
+    if (core_diff)
+        if (int rc = comm_allreduce_counts(c, c->d_cd, P)) return rc;
     if (core_diff) CU(c, cudaMemcpyAsync(core_diff, c->d_cd, P * 4, cudaMemcpyDeviceToHost, c->stream));
     if (inter) CU(c, cudaMemcpyAsync(inter, c->d_in, P * 4, cudaMemcpyDeviceToHost, c->stream));
     if (uni) CU(c, cudaMemcpyAsync(uni, c->d_un, P * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -1823,6 +2061,7 @@ int pansim_pair_counts_rows_device(pansim_ctx *c, uint32_t row_begin, uint32_t r
     CU(c, cudaSetDevice(c->cfg.device));
     size_t P = 0;
     if (int rc = pair_counts_rows_impl(c, row_begin, row_end, (uint32_t *)d_cd, (uint32_t *)d_in, (uint32_t *)d_un, &P)) return rc;
+    if (int rc = comm_allreduce_counts(c, (uint32_t *)d_cd, P)) return rc;
     if (n_pairs_out) *n_pairs_out = P;
     if (int rc = flags_enqueue_readback(c)) return rc;
     CU(c, cudaStreamSynchronize(c->stream));
@@ -1839,6 +2078,42 @@ int pansim_gene_counts(pansim_ctx *c, uint32_t *counts)
     LAUNCH_CHECK(c);
     CU(c, cudaMemcpyAsync(counts, c->d_gain_thr, (size_t)c->G * 4, cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- communicator over column shards (one process per GPU) -------------------
+int pansim_comm_unique_id(void *id_out)
+{
+    if (!id_out) return PANSIM_ERR_INVALID;
+    NcclApi &api = nccl_api();
+    if (!api.ok()) { g_create_error = api.error; return PANSIM_ERR_CUDA; }
+    ncclUniqueId id;
+    const ncclResult_t r = api.GetUniqueId(&id);
+    if (r != ncclSuccess) { g_create_error = std::string("ncclGetUniqueId failed: ") + api.GetErrorString(r); return PANSIM_ERR_CUDA; }
+    static_assert(sizeof(id) == PANSIM_COMM_ID_BYTES, "ncclUniqueId size");
+    memcpy(id_out, &id, sizeof id);
+    return 0;
+}
+
+int pansim_comm_init_rank(pansim_ctx *c, int n_ranks, int rank, const void *id)
+{
+    if (!c || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return PANSIM_ERR_INVALID;
+    if (c->comm) FAIL(c, PANSIM_ERR_STATE, "context already has a communicator");
+    NcclApi &api = nccl_api();
+    if (!api.ok()) FAIL(c, PANSIM_ERR_CUDA, "%s", api.error.c_str());
+    CU(c, cudaSetDevice(c->cfg.device));
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof uid);
+    NCK(c, api.CommInitRank(&c->comm, n_ranks, uid, rank));
+    c->comm_size = n_ranks; c->comm_rank = rank; c->comm_owned = true;
+    return 0;
+}
+
+int pansim_comm_info(pansim_ctx *c, int *n_ranks, int *rank)
+{
+    if (!c) return PANSIM_ERR_INVALID;
+    if (n_ranks) *n_ranks = c->comm ? c->comm_size : 1;
+    if (rank) *rank = c->comm ? c->comm_rank : 0;
     return 0;
 }
 
@@ -1918,5 +2193,7 @@ void pansim_free_event_dump(pansim_event_dump *d)
     free(d->acc_flip_mask); free(d->acc_gain_mask);
     memset(d, 0, sizeof *d);
 }
+
+#include "group_api.inl"
 
 }  // extern "C"

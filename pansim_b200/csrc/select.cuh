@@ -471,7 +471,7 @@ constexpr int SEL_WARPS = SEL_THREADS / 32;
 
 // block-wide reduction of three values at once (fixed order: shuffle tree, then the warp results
 // in warp order), result in every thread
-template <bool IS_MAX>
+template <bool IS_MAX, int WARPS = SEL_WARPS>
 __device__ __forceinline__ void block_reduce3(double &x, double &y, double &z, double (*scratch)[3])
 {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -488,7 +488,7 @@ __device__ __forceinline__ void block_reduce3(double &x, double &y, double &z, d
     __syncthreads();
     x = scratch[0][0]; y = scratch[0][1]; z = scratch[0][2];
 #pragma unroll
-    for (int q = 1; q < SEL_WARPS; q++) {
+    for (int q = 1; q < WARPS; q++) {
         x = IS_MAX ? fmax(x, scratch[q][0]) : x + scratch[q][0];
         y = IS_MAX ? fmax(y, scratch[q][1]) : y + scratch[q][1];
         z = IS_MAX ? fmax(z, scratch[q][2]) : z + scratch[q][2];
@@ -638,10 +638,15 @@ __global__ void __launch_bounds__(SEL_THREADS) select_parents_small_kernel(const
 // The three softmaxes of population.rs:325-382 (fitness a, genome size b, competition c) are
 // independent of each other, so each of their passes is made once for all three:
 //   m = max v; s = sum exp(v - m); lse = m + ln s; e_i = exp(v_i - lse); out_i = e_i / sum e
-__global__ void __launch_bounds__(SEL_THREADS) select_parents_kernel(const SelectArgs a)
+// THREADS = 1024 for large populations: four times the lanes for the transcendental passes and the
+// binary searches, and a CTA that owns its SM (nothing else fits beside 1024 threads), so the kernel
+// is not slowed by the core step's CTAs once it has got its slot.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) select_parents_kernel(const SelectArgs a)
 {
-    __shared__ double scratch[SEL_WARPS][3];
-    __shared__ double warp_excl[SEL_WARPS + 1];
+    constexpr int WARPS = THREADS / 32;
+    __shared__ double scratch[WARPS][3];
+    __shared__ double warp_excl[WARPS + 1];
     __shared__ int bad;
     const uint32_t n = a.n_rows, tid = threadIdx.x;
     const bool use_a = a.n_genes > 0, use_b = !a.no_control_genome_size;
@@ -651,51 +656,51 @@ __global__ void __launch_bounds__(SEL_THREADS) select_parents_kernel(const Selec
 
     // pass 0: the three arguments and their maxima
     double ma = -INFINITY, mb = -INFINITY, mc = -INFINITY;
-    for (uint32_t i = tid; i < n; i += SEL_THREADS) {
+    for (uint32_t i = tid; i < n; i += THREADS) {
         const double xa = use_a ? a.logfit[i] : 0.0;
         const double xb = use_b ? (double)(a.num_genes[i] - a.avg_gene_num) * a.log_penalty : 0.0;     // :350,355
         const double xc = a.competition_strength * log(a.avgdist ? a.avgdist[i] : 1.0);                // :375
         vb[i] = xb; vc[i] = xc;
         ma = fmax(ma, xa); mb = fmax(mb, xb); mc = fmax(mc, xc);
     }
-    block_reduce3<true>(ma, mb, mc, scratch);
+    block_reduce3<true, WARPS>(ma, mb, mc, scratch);
     // pass 1: log-sum-exp
     double sa = 0.0, sb = 0.0, sc = 0.0;
-    for (uint32_t i = tid; i < n; i += SEL_THREADS) {
+    for (uint32_t i = tid; i < n; i += THREADS) {
         if (use_a) sa += exp(a.logfit[i] - ma);
         if (use_b) sb += exp(vb[i] - mb);
         sc += exp(vc[i] - mc);
     }
-    block_reduce3<false>(sa, sb, sc, scratch);
+    block_reduce3<false, WARPS>(sa, sb, sc, scratch);
     const double la = (ma == -INFINITY) ? -INFINITY : ma + log(sa);
     const double lb = (mb == -INFINITY) ? -INFINITY : mb + log(sb);
     const double lc = (mc == -INFINITY) ? -INFINITY : mc + log(sc);
     // pass 2: exp(v - lse) and their totals
     double ta = 0.0, tb = 0.0, tc = 0.0;
-    for (uint32_t i = tid; i < n; i += SEL_THREADS) {
+    for (uint32_t i = tid; i < n; i += THREADS) {
         const double ea = use_a ? exp(a.logfit[i] - la) : 1.0;
         const double eb = use_b ? exp(vb[i] - lb) : 1.0;
         const double ec = exp(vc[i] - lc);
         va[i] = ea; vb[i] = eb; vc[i] = ec;
         ta += ea; tb += eb; tc += ec;
     }
-    block_reduce3<false>(ta, tb, tc, scratch);
+    block_reduce3<false, WARPS>(ta, tb, tc, scratch);
     // pass 3: weights (population.rs:365-393) and their maximum
     double mx = -INFINITY, dummy0 = -INFINITY, dummy1 = -INFINITY;
-    for (uint32_t i = tid; i < n; i += SEL_THREADS) {
+    for (uint32_t i = tid; i < n; i += THREADS) {
         const double wa = use_a ? va[i] / ta : 1.0;                 // a_i = 1 without an accessory genome (:293-296)
         const double w0 = use_b ? (vb[i] / tb) * wa : wa;           // :368 / :371
         const double w = w0 * (vc[i] / tc);                         // :391
         a.weights[i] = w;
         mx = fmax(mx, w);
     }
-    block_reduce3<true>(mx, dummy0, dummy1, scratch);
+    block_reduce3<true, WARPS>(mx, dummy0, dummy1, scratch);
     if (mx == 0.0)                                                                       // :435-437
-        for (uint32_t i = tid; i < n; i += SEL_THREADS) a.weights[i] = 1.0;
+        for (uint32_t i = tid; i < n; i += THREADS) a.weights[i] = 1.0;
     __syncthreads();
 
     // WeightedIndex::new: cumulative sums; contiguous chunk per thread, then a scan of the chunk totals
-    const uint32_t per = (n + SEL_THREADS - 1) / SEL_THREADS;
+    const uint32_t per = (n + THREADS - 1) / THREADS;
     const uint32_t lo = min(n, tid * per), hi = min(n, lo + per);
     double s = 0.0;
     bool mybad = false;
@@ -716,12 +721,12 @@ __global__ void __launch_bounds__(SEL_THREADS) select_parents_kernel(const Selec
     __syncthreads();
     if (tid == 0) {
         double run = 0.0;
-        for (int q = 0; q < SEL_WARPS; q++) { warp_excl[q] = run; run += scratch[q][0]; }
-        warp_excl[SEL_WARPS] = run;
+        for (int q = 0; q < WARPS; q++) { warp_excl[q] = run; run += scratch[q][0]; }
+        warp_excl[WARPS] = run;
         if (!(run > 0.0) || isinf(run)) bad = 1;
     }
     __syncthreads();
-    const double total = warp_excl[SEL_WARPS];
+    const double total = warp_excl[WARPS];
     double run = warp_excl[warp] + (v - s);
     for (uint32_t i = lo; i < hi; i++) {
         run += a.weights[i];
@@ -731,11 +736,11 @@ __global__ void __launch_bounds__(SEL_THREADS) select_parents_kernel(const Selec
     if (tid == 0) a.parents[n] = bad ? 1u : 0u;       // status word behind the vector: one read-back serves both
     if (bad) {
         if (tid == 0) *a.err_flag = 1;
-        for (uint32_t i = tid; i < n; i += SEL_THREADS) a.parents[i] = i;
+        for (uint32_t i = tid; i < n; i += THREADS) a.parents[i] = i;
         return;
     }
     // N draws: u ~ U[0,total), index = #cumulative[0..n-1) <= u
-    for (uint32_t i = tid; i < n; i += SEL_THREADS) {
+    for (uint32_t i = tid; i < n; i += THREADS) {
         const uint4 r = philox4x32_10(make_ctr(i, 0u, a.gen, STREAM_PARENTS), a.key);
         const uint64_t bits = (((uint64_t)r.x << 32) | r.y) >> 11;
         const double u = (double)bits * 0x1.0p-53 * total;

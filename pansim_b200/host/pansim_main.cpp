@@ -40,7 +40,7 @@ struct Flags {
 const char *VALUE_FLAGS[] = {"pop_size", "core_size", "pan_genes", "core_genes", "avg_gene_freq", "n_gen",
                              "max_distances", "core_mu", "HR_rate", "HGT_rate", "rate_genes1", "rate_genes2",
                              "prop_genes2", "prop_positive", "pos_lambda", "neg_lambda", "seed", "outpref",
-                             "threads", "genome_size_penalty", "competition_strength", "device"};
+                             "threads", "genome_size_penalty", "competition_strength", "device", "gpus"};
 const char *SWITCH_FLAGS[] = {"print_dist", "print_matrices", "print_selection", "verbose", "no_control_genome_size",
                               "all_pairs"};   // all_pairs: extension (every pair i < j in <outpref>.tsv)
 
@@ -51,7 +51,7 @@ bool parse(int argc, char **argv, Flags &f)
              {"HR_rate", "0.05"}, {"HGT_rate", "0.05"}, {"rate_genes1", "1.0"}, {"rate_genes2", "1000.0"},
              {"prop_genes2", "0.1"}, {"prop_positive", "-0.1"}, {"pos_lambda", "10.0"}, {"neg_lambda", "10.0"},
              {"seed", "0"}, {"outpref", "distances"}, {"threads", "1"}, {"genome_size_penalty", "0.99"},
-             {"competition_strength", "0.0"}, {"device", "0"}};
+             {"competition_strength", "0.0"}, {"device", "0"}, {"gpus", "1"}};
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         if (a == "--help" || a == "-h") {
@@ -86,19 +86,19 @@ size_t as_rounded(const Flags &f, const char *n) { return (size_t)std::llround(a
 
 void pansim::Populations::write(const std::string &outpref)
 {
-    const size_t N = cfg_.pop_size, L = cfg_.site_end ? cfg_.site_end - cfg_.site_begin : cfg_.core_size, G = cfg_.pan_size;
+    const size_t N = cfg_.pop_size, L = cfg_.core_size, G = cfg_.pan_size;
     {
         std::ofstream f(outpref + "_core_genome.csv", std::ios::binary);
         const uint32_t step = (uint32_t)std::max<size_t>(1, (64u << 20) / std::max<size_t>(1, 2 * L));
         std::vector<char> buf((size_t)step * 2 * L);
         for (uint32_t r0 = 0; r0 < N; r0 += step) {
             const uint32_t r1 = (uint32_t)std::min<size_t>(N, r0 + step);
-            check(pansim_export_core_csv(ctx_, r0, r1, buf.data()));
+            gcheck(pansim_group_export_core_csv(grp_, r0, r1, buf.data()));
             f.write(buf.data(), (std::streamsize)((size_t)(r1 - r0) * 2 * L));
         }
     }
     std::vector<uint8_t> acc(N * G);
-    check(pansim_download_acc(ctx_, acc.data()));
+    gcheck(pansim_group_download_acc(grp_, acc.data()));
     std::ofstream f(outpref + "_pangenome.csv");
     for (size_t r = 0; r < N; r++) {
         std::string line;
@@ -125,6 +125,7 @@ int main(int argc, char **argv)
     const uint64_t seed = std::strtoull(fl.val["seed"].c_str(), nullptr, 10);
     const bool verbose = fl.sw["verbose"], print_dist = fl.sw["print_dist"], print_matrices = fl.sw["print_matrices"];
     const bool all_pairs = fl.sw["all_pairs"];
+    const int n_gpus = std::max(1, std::atoi(fl.val["gpus"].c_str()));       // extension: column shards over N devices of the box
     const bool print_selection = fl.sw["print_selection"], no_control = fl.sw["no_control_genome_size"];
     const double genome_size_penalty = as_f64(fl, "genome_size_penalty"), competition_strength = as_f64(fl, "competition_strength");
 
@@ -208,40 +209,44 @@ int main(int argc, char **argv)
     }
 
     try {
-        pansim::Populations pops(cfg);
+        pansim::Populations pops(cfg, n_gpus);
         pops.set_initial(core_row, acc_row);
         pops.set_selection(selection);
         std::vector<double> avg_core(n_gen, 0.0), avg_acc(n_gen, 0.0), std_core(n_gen, 0.0), std_acc(n_gen, 0.0);
         std::vector<double> core_d, acc_d;
-        // nothing is read back between generations unless --print_dist / --verbose ask for it: the run is
-        // then one device-resident batch (same states)
-        const bool batched = !print_dist && !verbose && n_gen > 1;
-        if (batched) pops.run_generations(0, (uint32_t)(n_gen - 1));
-        for (int j = batched ? n_gen - 1 : 0; j < n_gen; j++) {
-            pops.step((uint32_t)j);                                         // main.rs:435-464
-            if (j == n_gen - 1) {                                           // main.rs:467-499
-                std::ofstream f(outpref + ".tsv");
-                if (all_pairs) {
-                    // row blocks of about 4 million pairs, (i, j) order
-                    const uint32_t N = cfg.pop_size;
-                    uint32_t i0 = 0;
-                    while (N > 1 && i0 < N - 1) {
-                        uint32_t i1 = i0;
-                        size_t n = 0;
-                        while (i1 < N - 1 && (n == 0 || n + (N - 1 - i1) <= 4000000)) { n += N - 1 - i1; i1++; }
-                        std::vector<double> c_, a_;
-                        pops.pairwise_distances_rows(i0, i1, c_, a_);
-                        for (size_t k = 0; k < c_.size(); k++) f << fmt(c_[k]) << "\t" << fmt(a_[k]) << "\n";
-                        i0 = i1;
-                    }
-                }
+        auto last_generation_outputs = [&]() {                              // main.rs:467-499
+            std::ofstream f(outpref + ".tsv");
+            if (all_pairs) {
+                // every pair i < j in (i, j) order, row blocks of about 4 million pairs
+                std::string line;
+                pops.all_pairs(4000000, [&](double c_, double a_) { f << fmt(c_) << "\t" << fmt(a_) << "\n"; });
+            } else {
                 pops.pairwise_distances(range1, range2, core_d, acc_d);
-                for (size_t k = 0; k < max_distances && !all_pairs; k++) f << fmt(core_d[k]) << "\t" << fmt(acc_d[k]) << "\n";
-                std::ofstream g(outpref + "_freqs.txt");
-                for (double x : pops.gene_frequencies()) g << fmt(x) << "\n";
+                for (size_t k = 0; k < max_distances; k++) f << fmt(core_d[k]) << "\t" << fmt(acc_d[k]) << "\n";
             }
+            std::ofstream g(outpref + "_freqs.txt");
+            for (double x : pops.gene_frequencies()) g << fmt(x) << "\n";
+        };
+        // Nothing has to come back between generations unless --verbose asks for it: the run is one
+        // device-resident batch (same states). With --print_dist the batch also makes the distance pass and
+        // its mean / standard deviation on the device every generation (pansim_run_generations_stats).
+        const bool device_loop = !verbose;
+        int first_host_gen = 0;
+        if (device_loop) {
+            if (print_dist) {
+                const std::vector<double> st = pops.run_generations_stats(0, (uint32_t)n_gen, range1, range2);
+                for (int j = 0; j < n_gen; j++) { avg_core[j] = st[4 * j]; std_core[j] = st[4 * j + 1]; avg_acc[j] = st[4 * j + 2]; std_acc[j] = st[4 * j + 3]; }
+            } else {
+                pops.run_generations(0, (uint32_t)n_gen);
+            }
+            first_host_gen = n_gen;
+            last_generation_outputs();
+        }
+        for (int j = first_host_gen; j < n_gen; j++) {
+            pops.step((uint32_t)j);                                         // main.rs:435-464
+            if (j == n_gen - 1) last_generation_outputs();
             if (print_dist) {                                               // main.rs:502-519
-                if (j != n_gen - 1) pops.pairwise_distances(range1, range2, core_d, acc_d);
+                if (j != n_gen - 1 || all_pairs) pops.pairwise_distances(range1, range2, core_d, acc_d);
                 auto sc = pansim::standard_deviation(core_d), sa = pansim::standard_deviation(acc_d);
                 std_core[j] = sc.first; avg_core[j] = sc.second; std_acc[j] = sa.first; avg_acc[j] = sa.second;
             }

@@ -3,7 +3,8 @@
 //
 // The reference keeps two Population objects (core_genome, pan_genome) that are
 // always advanced together with the same parent vector (main.rs:442-464); here one
-// `Populations` object owns one pansim_ctx = both of them. Method names, argument
+// `Populations` object owns both of them, on one GPU or column-sharded over several
+// (pansim_group: one process, NCCL inside the library, `pansim --gpus N`). Method names, argument
 // meaning and error behaviour follow population.rs; errors surface as
 // pansim::Error (the reference panics via unwrap()).
 #pragma once
@@ -41,25 +42,30 @@ inline char int_to_base(uint8_t n)
 
 class Populations {
 public:
-    explicit Populations(const pansim_config &cfg) : cfg_(cfg)
+    explicit Populations(const pansim_config &cfg, int n_gpus = 1) : cfg_(cfg)
     {
-        const int rc = pansim_create(&cfg_, &ctx_);
-        if (rc != PANSIM_OK) throw Error(rc, pansim_last_error(nullptr));
+        std::vector<int> devs;
+        for (int i = 0; i < n_gpus; i++) devs.push_back(cfg.device + i);
+        const int rc = pansim_group_create(&cfg_, n_gpus, devs.data(), &grp_);
+        if (rc != PANSIM_OK) throw Error(rc, pansim_group_last_error(nullptr));
+        ctx_ = pansim_group_ctx(grp_, 0);
     }
-    ~Populations() { pansim_destroy(ctx_); }
+    ~Populations() { pansim_group_destroy(grp_); }
+    int n_gpus() const { return pansim_group_size(grp_); }
     Populations(const Populations &) = delete;
     Populations &operator=(const Populations &) = delete;
 
     // Population::new x2 (population.rs:181-242): every row starts as the given row
     void set_initial(const std::vector<uint8_t> &core_row_onehot, const std::vector<uint8_t> &acc_row)
     {
-        check(pansim_set_initial(ctx_, core_row_onehot.data(), acc_row.data()));
+        gcheck(pansim_group_set_initial(grp_, core_row_onehot.data(), acc_row.data()));
     }
-    void set_selection(const std::vector<double> &s) { check(pansim_set_selection(ctx_, s.data())); }
+    void set_selection(const std::vector<double> &s) { gcheck(pansim_group_set_selection(grp_, s.data())); }
 
     // population.rs:753-784 (accessory population)
     std::vector<double> average_distance()
     {
+        single("average_distance");
         std::vector<double> out(cfg_.pop_size);
         check(pansim_average_distance(ctx_, out.data()));
         return out;
@@ -67,19 +73,21 @@ public:
     // population.rs:270-448
     std::vector<uint32_t> sample_indices(uint32_t gen, const std::vector<double> &avg_pairwise_dists)
     {
+        single("sample_indices");
         std::vector<uint32_t> out(cfg_.pop_size);
         check(pansim_sample_indices(ctx_, gen, avg_pairwise_dists.empty() ? nullptr : avg_pairwise_dists.data(), out.data()));
         return out;
     }
     // population.rs:450-465 for both populations
-    void next_generation(const std::vector<uint32_t> &parents) { check(pansim_next_generation(ctx_, parents.data())); }
+    void next_generation(const std::vector<uint32_t> &parents) { single("next_generation"); check(pansim_next_generation(ctx_, parents.data())); }
     // main.rs:445-464 in one fused pass (next_generation + mutate_alleles + recombine, both populations)
     void step_with_parents(uint32_t gen, const std::vector<uint32_t> &parents)
     {
+        single("step_with_parents");
         check(pansim_step_with_parents(ctx_, gen, parents.data()));
     }
     // main.rs:435-464 entirely on the device
-    void step(uint32_t gen) { check(pansim_step(ctx_, gen)); }
+    void step(uint32_t gen) { gcheck(pansim_group_run_generations(grp_, gen, 1)); }
 
     // population.rs:787-837 for both populations: f64 distances formed on the host from
     // the integer counts with the reference's own expressions (:822, :828-830)
@@ -88,7 +96,7 @@ public:
     {
         const size_t P = range1.size();
         std::vector<uint32_t> cd(P), in(P), un(P);
-        check(pansim_pair_counts(ctx_, range1.data(), range2.data(), P, cd.data(), in.data(), un.data()));
+        gcheck(pansim_group_pair_counts(grp_, range1.data(), range2.data(), P, cd.data(), in.data(), un.data()));
         core_out.resize(P);
         acc_out.resize(P);
         for (size_t k = 0; k < P; k++) {
@@ -96,30 +104,36 @@ public:
             acc_out[k] = pansim_acc_distance(in[k], un[k], cfg_.core_genes);
         }
     }
-    // (extension) exact all-pairs mode: distances of every pair (i, j), row_begin <= i < row_end, i < j < N,
-    // ordered by i then j; at most 2^31 - 1 pairs per call
-    void pairwise_distances_rows(uint32_t row_begin, uint32_t row_end, std::vector<double> &core_out,
-                                 std::vector<double> &acc_out)
+    // (extension, BASELINE config 5) exact all-pairs mode: `sink(core_distance, acc_distance)` is called for
+    // every pair i < j in (i, j) order. Row blocks of about chunk_pairs pairs; over several GPUs the partial
+    // core counts of a block are reduce-scattered while the next block is computed (pansim_group_all_pairs).
+    template <typename Sink>
+    void all_pairs(size_t chunk_pairs, Sink &&sink)
     {
-        size_t P = 0;
-        for (uint32_t i = row_begin; i < row_end && i < cfg_.pop_size; i++) P += cfg_.pop_size - 1 - i;
-        std::vector<uint32_t> cd(P ? P : 1), in(P ? P : 1), un(P ? P : 1);
-        size_t n = 0;
-        check(pansim_pair_counts_rows(ctx_, row_begin, row_end, cd.data(), in.data(), un.data(), &n));
-        core_out.resize(n);
-        acc_out.resize(n);
-        for (size_t k = 0; k < n; k++) {
-            core_out[k] = pansim_core_distance(cd[k], cfg_.core_size);
-            acc_out[k] = pansim_acc_distance(in[k], un[k], cfg_.core_genes);
-        }
+        struct Ctx { Populations *self; Sink *sink; } u{this, &sink};
+        auto cb = [](void *user, uint32_t, uint32_t, size_t n, const uint32_t *cd, const uint32_t *in, const uint32_t *un) -> int {
+            Ctx *x = static_cast<Ctx *>(user);
+            const pansim_config &cf = x->self->cfg_;
+            for (size_t k = 0; k < n; k++) (*x->sink)(pansim_core_distance(cd[k], cf.core_size), pansim_acc_distance(in[k], un[k], cf.core_genes));
+            return 0;
+        };
+        gcheck(pansim_group_all_pairs(grp_, chunk_pairs, cb, &u));
+    }
+    // main.rs:429-519 under --print_dist as one device-resident batch: per generation (avg_core, std_core, avg_acc, std_acc)
+    std::vector<double> run_generations_stats(uint32_t gen0, uint32_t n, const std::vector<uint32_t> &range1,
+                                              const std::vector<uint32_t> &range2)
+    {
+        std::vector<double> out((size_t)n * 4);
+        gcheck(pansim_group_run_generations_stats(grp_, gen0, n, range1.data(), range2.data(), range1.size(), out.data()));
+        return out;
     }
     // main.rs:435-464 for generations gen0 .. gen0+n-1 as one device-resident batch
-    void run_generations(uint32_t gen0, uint32_t n) { check(pansim_run_generations(ctx_, gen0, n)); }
+    void run_generations(uint32_t gen0, uint32_t n) { gcheck(pansim_group_run_generations(grp_, gen0, n)); }
     // population.rs:840-863: accessory gene frequencies, then core_genes x 1.0
     std::vector<double> gene_frequencies()
     {
         std::vector<uint32_t> counts(cfg_.pan_size);
-        check(pansim_gene_counts(ctx_, counts.data()));
+        gcheck(pansim_group_gene_counts(grp_, counts.data()));
         std::vector<double> f;
         f.reserve(cfg_.pan_size + cfg_.core_genes);
         for (uint32_t c : counts) f.push_back((double)c / (double)cfg_.pop_size);
@@ -130,7 +144,7 @@ public:
     double calc_gene_freq()
     {
         std::vector<uint8_t> acc((size_t)cfg_.pop_size * cfg_.pan_size);
-        check(pansim_download_acc(ctx_, acc.data()));
+        gcheck(pansim_group_download_acc(grp_, acc.data()));
         double sum = 0.0;
         for (uint32_t r = 0; r < cfg_.pop_size; r++) {
             size_t s = 0;
@@ -142,7 +156,8 @@ public:
     // population.rs:865-897 `write` for both populations
     void write(const std::string &outpref);
 
-    pansim_ctx *raw() { return ctx_; }
+    pansim_ctx *raw() { return ctx_; }          // shard 0 (the whole run when n_gpus() == 1)
+    pansim_group *group() { return grp_; }
     const pansim_config &config() const { return cfg_; }
 
 private:
@@ -150,7 +165,17 @@ private:
     {
         if (rc != PANSIM_OK) throw Error(rc, pansim_last_error(ctx_));
     }
+    void gcheck(int rc)
+    {
+        if (rc != PANSIM_OK) throw Error(rc, pansim_group_last_error(grp_));
+    }
+    // host-driven operators work on one context; a sharded run uses the device-resident calls
+    void single(const char *what)
+    {
+        if (n_gpus() != 1) throw Error(PANSIM_ERR_STATE, std::string(what) + " is a single-GPU call; use step() / run_generations() with --gpus > 1");
+    }
     pansim_config cfg_;
+    pansim_group *grp_ = nullptr;
     pansim_ctx *ctx_ = nullptr;
 };
 

@@ -180,6 +180,13 @@ class Pansim:
         self._check(self._lib.pansim_sample_indices(self._h, gen, _ptr(avg), _ptr(out)))
         return out
 
+    def select_parents(self, gen: int):
+        """main.rs:435-443 in one call (one synchronisation): (avg_pairwise_dists, parents)."""
+        avg = np.empty(self.N, np.float64)
+        out = np.empty(self.N, np.uint32)
+        self._check(self._lib.pansim_select_parents(self._h, gen, _ptr(avg), _ptr(out)))
+        return avg, out
+
     def weights(self):
         w = np.empty(self.N, np.float64)
         ng = np.empty(self.N, np.int32)
@@ -276,6 +283,40 @@ class Pansim:
         """population.rs:787-837 for both populations -> (core_distances, acc_distances)."""
         cd, it, un = self.pair_counts(range1, range2)
         return self.distances_from_counts(cd, it, un)
+
+    def pair_stats(self, range1, range2) -> tuple[float, float, float, float]:
+        """main.rs:502-519 on the device: (avg_core, std_core, avg_acc, std_acc) of one distance pass,
+        sums in the reference's left-to-right order (population.rs:87-94)."""
+        r1 = np.ascontiguousarray(range1, np.uint32)
+        r2 = np.ascontiguousarray(range2, np.uint32)
+        out = np.empty(4, np.float64)
+        self._check(self._lib.pansim_pair_stats(self._h, _ptr(r1), _ptr(r2), len(r1), _ptr(out)))
+        return tuple(float(x) for x in out)
+
+    def run_generations_stats(self, gen0: int, n: int, range1, range2) -> np.ndarray:
+        """n generations, each followed by the distance pass and its statistics, in one device-resident
+        batch (the --print_dist loop, main.rs:429-519): array [n, 4] of (avg_core, std_core, avg_acc, std_acc)."""
+        r1 = np.ascontiguousarray(range1, np.uint32)
+        r2 = np.ascontiguousarray(range2, np.uint32)
+        out = np.empty((n, 4), np.float64)
+        self._check(self._lib.pansim_run_generations_stats(self._h, gen0, n, _ptr(r1), _ptr(r2), len(r1), _ptr(out)))
+        return out
+
+    # -- multi-GPU: communicator over column shards (one process per GPU) --
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * _ffi.COMM_ID_BYTES)()
+        rc = _ffi.lib().pansim_comm_unique_id(C.byref(buf))
+        if rc != OK:
+            raise PansimError(rc, _ffi.lib().pansim_last_error(None).decode())
+        return bytes(buf)
+
+    def comm_init_rank(self, n_ranks: int, rank: int, unique_id: bytes):
+        """ncclCommInitRank inside the library: from now on the pair-count calls return
+        whole-alignment core counts (summed over the column shards on the device)."""
+        assert len(unique_id) == _ffi.COMM_ID_BYTES
+        buf = (C.c_uint8 * _ffi.COMM_ID_BYTES).from_buffer_copy(unique_id)
+        self._check(self._lib.pansim_comm_init_rank(self._h, n_ranks, rank, C.byref(buf)))
 
     def pairs_in_rows(self, row_begin: int, row_end: int) -> int:
         """Number of pairs (i, j) with row_begin <= i < row_end, i < j < N."""

@@ -1,5 +1,5 @@
 """Multi-GPU host plumbing: column shards of the core alignment + the one
-collective the path needs (sum of per-pair partial core counts).
+collective the path needs (sum of per-pair partial core counts, made by the library over NCCL).
 
 One process per GPU (torchrun); every rank holds all individuals for its
 [site_begin, site_end) slice and a replica of the (small) accessory matrix.
@@ -45,10 +45,29 @@ def allreduce_pair_counts(partial_core_diff, group=None):
     return partial_core_diff
 
 
-class ShardedPansim:
-    """This rank's shard of a column-sharded run (wraps `Pansim`)."""
+def broadcast_unique_id(rank: int, group=None) -> bytes:
+    """Host plumbing for pansim_comm_init_rank: rank 0 creates the NCCL unique id (128 bytes), the
+    process group carries it to the other ranks (any backend; gloo on CPU works)."""
+    import torch
+    import torch.distributed as dist
+    from .population import Pansim
+    t = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        t = torch.frombuffer(bytearray(Pansim.comm_unique_id()), dtype=torch.uint8).clone()
+    dev = None
+    if dist.get_backend(group) == "nccl":
+        dev = torch.device("cuda", torch.cuda.current_device())
+        t = t.to(dev)
+    dist.broadcast(t, src=0, group=group)
+    return bytes(t.cpu().numpy().tobytes())
 
-    def __init__(self, params, rank: int, world: int, device: int = 0):
+
+class ShardedPansim:
+    """This rank's shard of a column-sharded run (wraps `Pansim`). The one collective of the path --
+    the sum of the per-pair partial core counts -- runs inside the library (NCCL communicator created
+    with pansim_comm_init_rank); torch.distributed only carries the 128-byte unique id."""
+
+    def __init__(self, params, rank: int, world: int, device: int = 0, group=None):
         from .population import Pansim
         self.rank, self.world = rank, world
         self.shards = column_shards(params.core_size, world)
@@ -56,38 +75,12 @@ class ShardedPansim:
         if world == 1:
             b, e = 0, 0
         self.sim = Pansim.from_params(params, device=device, site_begin=b, site_end=e)
+        if world > 1:
+            self.sim.comm_init_rank(world, rank, broadcast_unique_id(rank, group))
 
     def __getattr__(self, name):
         return getattr(self.sim, name)
 
-    def pair_counts(self, range1, range2):
-        """Whole-alignment counts on every rank: device partials + NCCL all-reduce."""
-        if self.world == 1:
-            return self.sim.pair_counts(range1, range2)
-        import torch
-        P = len(range1)
-        d_cd = torch.zeros(P, dtype=torch.int32, device="cuda")
-        d_in = torch.zeros(P, dtype=torch.int32, device="cuda")
-        d_un = torch.zeros(P, dtype=torch.int32, device="cuda")
-        self.sim.pair_counts_device(range1, range2, d_cd.data_ptr(), d_in.data_ptr(), d_un.data_ptr())
-        allreduce_pair_counts(d_cd)
-        return (d_cd.cpu().numpy().astype(np.uint32), d_in.cpu().numpy().astype(np.uint32),
-                d_un.cpu().numpy().astype(np.uint32))
-
-    def pair_counts_rows(self, row_begin: int, row_end: int):
-        """Exact all-pairs block (Pansim.pair_counts_rows): device partials + NCCL all-reduce."""
-        if self.world == 1:
-            return self.sim.pair_counts_rows(row_begin, row_end)
-        import torch
-        P = self.sim.pairs_in_rows(row_begin, row_end)
-        d_cd = torch.zeros(P, dtype=torch.int32, device="cuda")
-        d_in = torch.zeros(P, dtype=torch.int32, device="cuda")
-        d_un = torch.zeros(P, dtype=torch.int32, device="cuda")
-        self.sim.pair_counts_rows_device(row_begin, row_end, d_cd.data_ptr(), d_in.data_ptr(), d_un.data_ptr())
-        allreduce_pair_counts(d_cd)
-        return (d_cd.cpu().numpy().astype(np.uint32), d_in.cpu().numpy().astype(np.uint32),
-                d_un.cpu().numpy().astype(np.uint32))
-
     def pairwise_distances(self, range1, range2):
-        cd, it, un = self.pair_counts(range1, range2)
+        cd, it, un = self.sim.pair_counts(range1, range2)        # whole-alignment counts on every rank
         return self.sim.distances_from_counts(cd, it, un)

@@ -91,28 +91,39 @@ def run(p: Params, outpref: str | None = None, device: int = 0, out=None, all_pa
     with Pansim.from_params(p, device=device) as sim:
         sim.set_initial(core_row, acc_row)
         sim.set_selection(sel)
-        # nothing is read back between generations unless --print_dist / --verbose ask for it: the whole
-        # run is then one device-resident batch (same states, tests/test_gpu_parity.py)
-        batched = not p.print_dist and not p.verbose and p.n_gen > 1
-        if batched:
-            sim.run_generations(0, p.n_gen - 1)
-        for j in range(p.n_gen - 1 if batched else 0, p.n_gen):                  # main.rs:429
+        def last_generation_outputs():                                           # main.rs:467-499
+            if not all_pairs:
+                res.core_distances, res.acc_distances = sim.pairwise_distances(r1, r2)
+            res.gene_freqs = sim.gene_frequencies()
+            if outpref:
+                with open(outpref + ".tsv", "w") as f:
+                    if all_pairs:
+                        for _, _, cd_, it_, un_ in sim.iter_all_pairs(with_indices=False):
+                            c_, a_ = sim.distances_from_counts(cd_, it_, un_)
+                            f.write("".join(f"{fmt_f64(float(c))}\t{fmt_f64(float(a))}\n" for c, a in zip(c_, a_)))
+                    else:
+                        f.write("".join(f"{fmt_f64(float(c))}\t{fmt_f64(float(a))}\n"
+                                        for c, a in zip(res.core_distances, res.acc_distances)))
+                with open(outpref + "_freqs.txt", "w") as f:
+                    f.write("".join(fmt_f64(float(x)) + "\n" for x in res.gene_freqs))
+
+        # Nothing has to come back between generations unless --verbose asks for it: the whole run is one
+        # device-resident batch (same states, tests/test_gpu_parity.py). With --print_dist the batch also
+        # makes the distance pass and its mean / standard deviation every generation on the device
+        # (pansim_run_generations_stats: sums in the reference's left-to-right order, population.rs:87-94).
+        device_loop = not p.verbose and not (p.print_dist and all_pairs)
+        first_host_gen = 0
+        if device_loop:
+            if p.print_dist:
+                res.per_gen = [tuple(float(x) for x in row) for row in sim.run_generations_stats(0, p.n_gen, r1, r2)]
+            else:
+                sim.run_generations(0, p.n_gen)
+            first_host_gen = p.n_gen
+            last_generation_outputs()
+        for j in range(first_host_gen, p.n_gen):                                 # main.rs:429
             sim.step(j)                                                          # main.rs:435-464
-            if j == p.n_gen - 1:                                                 # main.rs:467-499
-                if not all_pairs:
-                    res.core_distances, res.acc_distances = sim.pairwise_distances(r1, r2)
-                res.gene_freqs = sim.gene_frequencies()
-                if outpref:
-                    with open(outpref + ".tsv", "w") as f:
-                        if all_pairs:
-                            for _, _, cd_, it_, un_ in sim.iter_all_pairs(with_indices=False):
-                                c_, a_ = sim.distances_from_counts(cd_, it_, un_)
-                                f.write("".join(f"{fmt_f64(float(c))}\t{fmt_f64(float(a))}\n" for c, a in zip(c_, a_)))
-                        else:
-                            f.write("".join(f"{fmt_f64(float(c))}\t{fmt_f64(float(a))}\n"
-                                            for c, a in zip(res.core_distances, res.acc_distances)))
-                    with open(outpref + "_freqs.txt", "w") as f:
-                        f.write("".join(fmt_f64(float(x)) + "\n" for x in res.gene_freqs))
+            if j == p.n_gen - 1:
+                last_generation_outputs()
             if p.print_dist:                                                     # main.rs:502-519
                 # the reference recomputes both passes here even on the last generation;
                 # the result is identical, so the last one is reused

@@ -34,13 +34,14 @@ def main():
         s.set_initial(core_row, acc_row)
         s.set_selection(sel)
         s.run_generations(0, p.n_gen)
-    cd, it, un = sh.pair_counts(r1, r2)                  # NCCL all-reduce of the partial core counts
+    cd, it, un = sh.pair_counts(r1, r2)                  # ncclAllReduce of the partial core counts inside the library
     wcd, wit, wun = whole.pair_counts(r1, r2)
     b, e = sh.shards[rank]
     ok = (cd == wcd).all() and (it == wit).all() and (un == wun).all()
     ok = ok and (sh.download_acc() == whole.download_acc()).all() and (sh.parents() == whole.parents()).all()
     ok = ok and (sh.download_core() == whole.download_core()[:, b:e]).all()
     acd, ait, aun = sh.pair_counts_rows(10, 40)          # exact all-pairs block, all-reduced as well
+    ok = ok and sh.pair_stats(r1, r2) == whole.pair_stats(r1, r2)
     wacd, wait_, waun = whole.pair_counts_rows(10, 40)
     ok = ok and (acd == wacd).all() and (ait == wait_).all() and (aun == waun).all()
     t = torch.tensor([1 if ok else 0], device="cuda")

@@ -156,3 +156,22 @@ def test_all_pairs_extension_and_batched_run(tmp_path):
             acc_d = 1.0 - ((inter + 10.0) / (uni + 10.0))
             assert rows[k][0] == pb.fmt_f64(float(core_d)) and rows[k][1] == pb.fmt_f64(float(acc_d))
             k += 1
+
+
+def test_per_gen_tsv_from_the_device_loop_is_byte_identical(tmp_path):
+    """--print_dist: the device-resident loop (distance pass + mean / std on the GPU every generation,
+    pansim_run_generations_stats) writes the same _per_gen.tsv, byte for byte, as the host loop that
+    reads the distances back and sums them on the host (taken with --verbose, which forces it)."""
+    kw = dict(pop_size=40, core_size=9000, pan_genes=300, core_genes=50, n_gen=6, max_distances=1500, seed=13,
+              print_dist=True, prop_positive=0.1, competition_strength=0.3, HR_rate=0.5)
+    pa, pb_ = str(tmp_path / "dev"), str(tmp_path / "host")
+
+    class Null:
+        def write(self, s):
+            pass
+
+    a = simulate.run(pb.Params(**kw), outpref=pa)
+    b = simulate.run(pb.Params(verbose=True, **kw), outpref=pb_, out=Null())
+    assert open(pa + "_per_gen.tsv", "rb").read() == open(pb_ + "_per_gen.tsv", "rb").read()
+    assert open(pa + ".tsv", "rb").read() == open(pb_ + ".tsv", "rb").read()
+    assert a.per_gen == b.per_gen and len(a.per_gen) == 6

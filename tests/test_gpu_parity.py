@@ -857,3 +857,98 @@ def test_step_with_parents_consumes_the_vector_before_returning():
         sim.step_with_parents(0, buf)
         buf[:] = 0                                        # scribble over it immediately
         assert (sim.download_core() == core[par]).all()
+
+
+# ------------------------------------------------ per-generation statistics on the device (8f-4)
+@pytest.mark.parametrize("N,L,G,P", [(9, 100, 31, 7), (40, 20011, 333, 1024), (64, 8192 * 3, 500, 5000), (17, 501, 64, 1025)])
+def test_pair_stats_equal_reference_order_sums(N, L, G, P):
+    """pansim_pair_stats = pairwise_distances x2 + standard_deviation x2 (main.rs:502-519,
+    population.rs:87-94). The oracle sums left to right like `iter().sum::<f64>()`; the device chain
+    does the same, so all four doubles are bit-identical (also with P not a multiple of the chunk)."""
+    rng = np.random.default_rng(N + P)
+    core, acc = random_state(rng, N, L, G)
+    r1, r2 = sample_pairs(rng, N, P)
+    p = pb.Params(pop_size=N, core_size=L, pan_genes=G + 5, core_genes=5)
+    with make(p) as sim:
+        sim.upload(core, acc)
+        avg_core, std_core, avg_acc, std_acc = sim.pair_stats(r1, r2)
+        core_d, acc_d = sim.pairwise_distances(r1, r2)
+    o_std_c, o_avg_c = ob.standard_deviation(core_d)
+    o_std_a, o_avg_a = ob.standard_deviation(acc_d)
+    assert (avg_core, std_core, avg_acc, std_acc) == (o_avg_c, o_std_c, o_avg_a, o_std_a)
+    assert (std_core, avg_core) == pb.standard_deviation(core_d)
+
+
+def test_run_generations_stats_equals_host_loop():
+    """The --print_dist loop as one device-resident batch: states, parents and the per-generation
+    statistics equal those of the host-driven loop (step, distance pass, host-side sums)."""
+    p = small_params(pop_size=60, core_size=8192 * 5 + 77, n_gen=5, HR_rate=0.5, prop_positive=0.1, competition_strength=0.3)
+    d = pb.derive(p)
+    rng = np.random.default_rng(71)
+    core, acc = random_state(rng, p.pop_size, p.core_size, d.pan_size)
+    sel = rng.normal(0, 0.05, d.pan_size)
+    r1, r2 = sample_pairs(rng, p.pop_size, 700)
+    with make(p) as a, make(p) as b:
+        for s in (a, b):
+            s.upload(core, acc)
+            s.set_selection(sel)
+        stats = a.run_generations_stats(0, 5, r1, r2)
+        want = []
+        for g in range(5):
+            b.step(g)
+            core_d, acc_d = b.pairwise_distances(r1, r2)
+            sc, ac = ob.standard_deviation(core_d)
+            sa, aa = ob.standard_deviation(acc_d)
+            want.append((ac, sc, aa, sa))
+        assert stats.tolist() == [list(w) for w in want]
+        assert (a.download_core() == b.download_core()).all() and (a.download_acc() == b.download_acc()).all()
+        assert (a.parents() == b.parents()).all()
+
+
+def test_select_parents_is_average_distance_plus_sample_indices():
+    p = small_params(pop_size=200, prop_positive=0.1, competition_strength=0.5)
+    d = pb.derive(p)
+    rng = np.random.default_rng(72)
+    core, acc = random_state(rng, p.pop_size, p.core_size, d.pan_size)
+    sel = rng.normal(0, 0.05, d.pan_size)
+    with make(p) as a, make(p) as b:
+        for s in (a, b):
+            s.upload(core, acc)
+            s.set_selection(sel)
+        for g in range(3):
+            avg, par = a.select_parents(g)
+            avg2 = b.average_distance()
+            par2 = b.sample_indices(g, avg2)
+            assert (avg == avg2).all() and (par == par2).all()
+            a.step_with_parents(g, par)
+            b.step_with_parents(g, par2)
+        assert (a.download_core() == b.download_core()).all()
+    with make(dataclasses.replace(p, competition_strength=0.0)) as c:
+        c.upload(core, acc)
+        avg, par = c.select_parents(0)
+        assert (avg == 1.0).all() and par.max() < p.pop_size          # main.rs:435
+
+
+@pytest.mark.parametrize("N", [1500, 5000])
+def test_selection_weights_for_large_populations(N):
+    """N > 1024 uses the global-memory selection kernel (256 threads up to 4096 individuals, 1024
+    beyond): weights within 1e-12 of the oracle's three-softmax product (population.rs:325-393),
+    the cumulative table consistent with them, the draws a pure function of (seed, gen)."""
+    rng = np.random.default_rng(N)
+    G = 96
+    core, acc = random_state(rng, N, 64, G, 0.4)
+    sel = rng.normal(0, 0.08, G)
+    p = pb.Params(pop_size=N, core_size=64, pan_genes=G, core_genes=0, competition_strength=0.7)
+    avg = rng.uniform(0.05, 0.9, N)
+    with make(p) as sim:
+        sim.upload(core, acc)
+        sim.set_selection(sel)
+        par = sim.sample_indices(3, avg)
+        w, ng, lf = sim.weights()
+        par2 = sim.sample_indices(3, avg)
+    ow, ong, olf = ob.Population(acc, False, 0).selection_weights(pb.derive(p).avg_gene_num, avg, sel, competition_strength=0.7)
+    assert (ng == ong).all() and (lf == olf).all()
+    np.testing.assert_allclose(w, ow, rtol=1e-12)
+    assert (par == par2).all() and par.max() < N
+    # the favoured individuals are drawn more often: mean weight of the drawn parents exceeds the plain mean
+    assert w[par].mean() > w.mean()
