@@ -8,6 +8,8 @@
 // Two words share one POPC by parking the second mask in the odd bits.
 // Row padding is zero in every row, so it never contributes.
 #pragma once
+#include <cuda.h>          // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no libcuda link)
+
 #include "common.cuh"
 
 namespace pansim {
@@ -171,124 +173,251 @@ __global__ void rows_groups_kernel(const uint32_t *off, const uint32_t *goff, ui
     groups[g] = PairGroup{i, off[r] + (j - (i + 1u)), min((uint32_t)PAIR_GROUP, jb1 - j)};
 }
 
-// v2: shared-memory row tiles. The host plan (cached) buckets the pairs by the pair of
-// 32-row blocks their endpoints fall in. A CTA takes one batch (<= 256 pairs of one
-// block pair), stages the <= 64 rows it needs, 512 B per row per stage, with cp.async
-// (LDGSTS, 16 B per thread, 3-stage ring; 64 separate 512 B TMA bulk copies per stage were
-// measured slower), and walks the whole column range. Each warp owns up to 16 consecutive pairs of the batch (sorted by
-// first endpoint so the first row is re-read only when it changes) and keeps their counts
-// in registers until the end: every staged byte is reused by all pairs of the batch that
-// touch its row, which cuts the L2 traffic of the streaming kernels ~3-6x.
-constexpr int TILE_ROWS = 64;          // 2 blocks of 32 rows
-constexpr int TILE_BYTES = 512;        // per row per stage
-constexpr int TILE_STAGES = 3;
-constexpr int TILE_WARPS = 16;
-constexpr int TILE_THREADS = TILE_WARPS * 32;
-constexpr int TILE_PPW = 16;           // pairs per warp
-constexpr int TILE_BATCH = TILE_WARPS * TILE_PPW;   // 256
-
 struct TileBatch {
-    uint32_t block_a, block_b;         // 32-row blocks (block_a <= block_b)
+    uint32_t block_a, block_b;         // 64-row blocks (block_a <= block_b)
     uint32_t first, count;             // range in the tile pair arrays
-    uint32_t col_begin, col_end;       // column range in units of TILE_BYTES
+    uint32_t col_begin, col_end;       // column range in units of 512-byte chunks
 };
 
-static inline size_t tile_smem_bytes()
+// ===========================================================================
+// K7 on bit planes (round 2).
+//
+// The XOR-popcount on 2-bit cells costs three logic operations per 32-bit word before the POPC
+// ((a ^ b), >> 1, (x | s) & 0x5555...), all on the ALU pipe the POPC shares (64 lanes/clk/SM, POPC a
+// quarter of that): 12 ALU slots per 32 sites, which is what bounded the row-stationary kernel at
+// 4.3e7 pairs/s. A site differs iff its low bits differ OR its high bits differ, so with the low bits
+// and the high bits of 32 sites in two separate words the mask is two operations:
+//     m = (aL ^ bL) | (aH ^ bH)            (LOP3, LOP3)           -> 7 slots per 32 sites with the POPC
+// The packed state stays 2 bits per site (the generation step writes cells); a pre-pass over the rows
+// makes the plane form once per distance pass (4 logic ops per 32 sites, HBM-bound, ~0.1 ms at cfg1).
+// Any bijection of the sites works as long as both planes use the same one: for the two words (w0, w1)
+// of 32 sites
+//     L = (w0 & 0x5555..) | ((w1 & 0x5555..) << 1)      H = ((w0 >> 1) & 0x5555..) | (w1 & 0xAAAA..)
+// (site k of w0 -> bit 2k of L and H, site k of w1 -> bit 2k+1), so a 16-byte piece (64 sites) becomes
+// the 16-byte piece {L01, H01, L23, H23} at the same offset: same geometry, padding stays zero.
+// ===========================================================================
+__global__ void __launch_bounds__(256) core_planes_kernel(const uint4 *__restrict__ state, uint4 *__restrict__ planes, uint64_t n_vec4)
 {
-    return (size_t)TILE_STAGES * TILE_ROWS * TILE_BYTES + TILE_BATCH * sizeof(uint32_t);
+    for (uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_vec4; v += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 w = ld_stream(state + v);
+        uint4 o;
+        o.x = (w.x & 0x55555555u) | ((w.y & 0x55555555u) << 1);
+        o.y = ((w.x >> 1) & 0x55555555u) | (w.y & 0xAAAAAAAAu);
+        o.z = (w.z & 0x55555555u) | ((w.w & 0x55555555u) << 1);
+        o.w = ((w.z >> 1) & 0x55555555u) | (w.w & 0xAAAAAAAAu);
+        planes[v] = o;
+    }
 }
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+// differing sites of two 16-byte plane pieces (64 sites)
+__device__ __forceinline__ uint32_t diff_planes(const uint4 a, const uint4 b)
 {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+    const uint32_t m0 = (a.x ^ b.x) | (a.y ^ b.y);
+    const uint32_t m1 = (a.z ^ b.z) | (a.w ^ b.w);
+    return __popc(m0) + __popc(m1);
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(TILE_THREADS, 2) pair_core_tile_kernel(
-    const uint8_t *state, uint64_t row_stride, uint32_t n_rows, const TileBatch *batches,
+// row-stationary groups (see pair_core_grouped_kernel) on the plane form: the sparse remainder of a
+// sampled pair list and the exact all-pairs row blocks
+__global__ void __launch_bounds__(PAIR_THREADS) pair_planes_grouped_kernel(
+    const uint8_t *planes, uint64_t row_stride, uint32_t chunk_vec4, uint32_t row_vec4, const PairGroup *groups,
+    uint32_t n_groups, const uint32_t *partner, const uint32_t *orig_index, uint32_t *core_diff)
+{
+    __shared__ uint32_t wsum[PAIR_THREADS / 32][PAIR_GROUP];
+    const uint32_t chunk = blockIdx.y;
+    const uint32_t v_lo = chunk * chunk_vec4;
+    const uint32_t v_hi = min(row_vec4, v_lo + chunk_vec4);
+    for (uint32_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const PairGroup grp = groups[g];
+        const uint4 *ra = reinterpret_cast<const uint4 *>(planes + (uint64_t)grp.row_i * row_stride);
+        const uint4 *rb[PAIR_GROUP];
+#pragma unroll
+        for (int q = 0; q < PAIR_GROUP; q++) {
+            const uint32_t j = partner[grp.first + (q < (int)grp.count ? q : 0)];
+            rb[q] = reinterpret_cast<const uint4 *>(planes + (uint64_t)j * row_stride);
+        }
+        // carry-save counting as in the tile kernel: `ones` absorbs the two masks of a piece, the carries are POPCounted
+        uint32_t acc[PAIR_GROUP], ones[PAIR_GROUP];
+#pragma unroll
+        for (int q = 0; q < PAIR_GROUP; q++) { acc[q] = 0; ones[q] = 0; }
+        for (uint32_t v = v_lo + threadIdx.x; v < v_hi; v += PAIR_THREADS) {
+            const uint4 a = ld_stream(ra + v);
+            uint4 b[PAIR_GROUP];
+#pragma unroll
+            for (int q = 0; q < PAIR_GROUP; q++) b[q] = ld_stream(rb[q] + v);
+#pragma unroll
+            for (int q = 0; q < PAIR_GROUP; q++) {
+                const uint32_t m0 = (a.x ^ b[q].x) | (a.y ^ b[q].y);
+                const uint32_t m1 = (a.z ^ b[q].z) | (a.w ^ b[q].w);
+                const uint32_t o = ones[q];
+                ones[q] = o ^ m0 ^ m1;
+                acc[q] += __popc((o & m0) | (m1 & (o | m0)));
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < PAIR_GROUP; q++) {
+            acc[q] = 2u * acc[q] + __popc(ones[q]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+            for (int q = 0; q < PAIR_GROUP; q++) wsum[threadIdx.x >> 5][q] = acc[q];
+        }
+        __syncthreads();
+        if (threadIdx.x < grp.count) {
+            uint32_t t = 0;
+            for (int w = 0; w < PAIR_THREADS / 32; w++) t += wsum[w][threadIdx.x];
+            atomicAdd(&core_diff[orig_index[grp.first + threadIdx.x]], t);
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// TMA-staged shared-memory tiles (north_star: "128-bit vectorised XOR/popcount over TMA-staged
+// shared-memory tiles"). The host buckets the pairs by the pair of 64-row blocks their endpoints fall
+// in and cuts every bucket into batches of up to T2_BATCH pairs. A work item = (batch, column range).
+// Persistent CTAs (one per SM) take work items from a counter. Per 512-byte column chunk one elected
+// producer thread issues TWO instructions -- cp.async.bulk.tensor.2d with a 64-row x 512-byte box per
+// row block, mbarrier complete_tx -- into a 3-stage ring (3 x 64 KB); fifteen consumer warps wait on
+// the stage's `full` barrier, each compares its pairs (one 16-byte piece per lane per row, first row
+// kept in registers while it repeats) and arrives on the stage's `empty` barrier. Every staged row
+// serves all pairs of the batch that touch it (~6 at cfg1), which takes the L2 -> SM traffic from
+// 337 KB to ~50 KB per pair; DRAM sees each row about once per pass because the work items of one
+// column range run at the same time on all SMs.
+// ---------------------------------------------------------------------------
+constexpr int T2_BLOCK_ROWS = 64;
+constexpr int T2_CHUNK_BYTES = 512;
+constexpr int T2_STAGES = 3;
+constexpr int T2_WARPS = 15;                        // consumer warps (+ the producer warp = 512 threads: 128 registers each)
+constexpr int T2_THREADS = (T2_WARPS + 1) * 32;     // + one producer warp
+constexpr int T2_PPW = 20;                          // pairs per consumer warp
+constexpr int T2_BATCH = T2_WARPS * T2_PPW;         // 300
+constexpr uint32_t T2_STAGE_BYTES = 2 * T2_BLOCK_ROWS * T2_CHUNK_BYTES;   // 65536
+
+static inline size_t tile2_smem_bytes()
+{
+    return 1024 /* alignment slack */ + (size_t)T2_STAGES * T2_STAGE_BYTES + 2 * T2_STAGES * sizeof(uint64_t) + T2_BATCH * sizeof(uint32_t) + 16;
+}
+
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const void *tmap, uint32_t x, uint32_t y, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(T2_THREADS, 1) pair_tile2_kernel(
+    const __grid_constant__ CUtensorMap tmap, const TileBatch *batches, uint32_t n_work, uint32_t *work_counter,
     const uint16_t *tile_slots, const uint32_t *tile_orig, uint32_t *core_diff)
 {
-    extern __shared__ __align__(128) uint8_t tsm[];
-    uint32_t *meta = reinterpret_cast<uint32_t *>(tsm + (size_t)TILE_STAGES * TILE_ROWS * TILE_BYTES);
-    const TileBatch bt = batches[blockIdx.x];
+    extern __shared__ uint8_t t2_raw[];
+    uint8_t *base = t2_raw + ((1024u - (smem_u32(t2_raw) & 1023u)) & 1023u);      // TMA destinations: 128-byte aligned at least
+    uint8_t *stages = base;
+    uint64_t *full = reinterpret_cast<uint64_t *>(base + (size_t)T2_STAGES * T2_STAGE_BYTES);
+    uint64_t *empty = full + T2_STAGES;
+    uint32_t *meta = reinterpret_cast<uint32_t *>(empty + T2_STAGES);
+    uint32_t *work_s = meta + T2_BATCH;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    for (uint32_t i = threadIdx.x; i < TILE_BATCH; i += TILE_THREADS)
-        meta[i] = i < bt.count ? tile_slots[bt.first + i] : 0xFFFFu;
-
-    // staging: a stage is TILE_ROWS x 512 B = 2048 pieces of 16 B, 4 per thread. Piece p of a
-    // chunk belongs to row slot p/32 (slots 0..31 -> block_a, 32..63 -> block_b), byte (p%32)*16.
-    constexpr int PIECES = TILE_ROWS * TILE_BYTES / 16 / TILE_THREADS;      // 4
-    const uint8_t *src[PIECES];
-    uint32_t dst_off[PIECES];
-#pragma unroll
-    for (int k = 0; k < PIECES; k++) {
-        const uint32_t p = threadIdx.x + k * TILE_THREADS;
-        const uint32_t slot = p >> 5;
-        const uint32_t row = slot < 32 ? bt.block_a * 32 + slot : bt.block_b * 32 + (slot - 32);
-        const bool ok = row < n_rows && (slot < 32 || bt.block_b != bt.block_a);
-        src[k] = ok ? state + (uint64_t)row * row_stride + (uint64_t)bt.col_begin * TILE_BYTES + (p & 31u) * 16u : nullptr;
-        dst_off[k] = slot * TILE_BYTES + (p & 31u) * 16u;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < T2_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], T2_WARPS); }
+        fence_mbar_init();
     }
-    const uint32_t n_chunks = bt.col_end - bt.col_begin;
-    auto issue = [&](uint32_t c) {
-        uint8_t *stage = tsm + (size_t)(c % TILE_STAGES) * TILE_ROWS * TILE_BYTES;
-#pragma unroll
-        for (int k = 0; k < PIECES; k++)
-            if (src[k]) cp_async16(stage + dst_off[k], src[k] + (uint64_t)c * TILE_BYTES);
-        cp_async_commit();
-    };
-    issue(0);
-    if (n_chunks > 1) issue(1); else cp_async_commit();
+    __syncthreads();
 
-    uint32_t acc[TILE_PPW];
+    uint32_t it = 0;                 // chunks handled so far by this CTA (all work items): stage = it % 3, phase = (it / 3) & 1
+    for (;;) {
+        if (threadIdx.x == 0) *work_s = atomicAdd(work_counter, 1u);
+        __syncthreads();
+        const uint32_t w = *work_s;
+        if (w >= n_work) break;
+        const TileBatch bt = batches[w];
+        const uint32_t n_chunks = bt.col_end - bt.col_begin;
+        const bool diag = bt.block_a == bt.block_b;
+        for (uint32_t i = threadIdx.x; i < (uint32_t)T2_BATCH; i += T2_THREADS)
+            meta[i] = i < bt.count ? (uint32_t)tile_slots[bt.first + i] : 0xFFFFu;
+        __syncthreads();
+
+        if (warp == T2_WARPS) {
+            // ---- producer: one elected thread ----
+            if (lane == 0) {
+                for (uint32_t c = 0; c < n_chunks; c++) {
+                    const uint32_t k = it + c, s = k % T2_STAGES, ph = (k / T2_STAGES) & 1u;
+                    mbar_wait(&empty[s], ph ^ 1u);                      // all consumer warps have left the stage (fresh barrier: passes)
+                    mbar_arrive_expect_tx(&full[s], diag ? T2_STAGE_BYTES / 2 : T2_STAGE_BYTES);
+                    uint8_t *dst = stages + (size_t)s * T2_STAGE_BYTES;
+                    const uint32_t x = (bt.col_begin + c) * (T2_CHUNK_BYTES / 4);
+                    tma_load_2d(dst, &tmap, x, bt.block_a * T2_BLOCK_ROWS, &full[s]);
+                    if (!diag) tma_load_2d(dst + T2_STAGE_BYTES / 2, &tmap, x, bt.block_b * T2_BLOCK_ROWS, &full[s]);
+                }
+            }
+        } else {
+            // ---- consumers: pairs [warp * PPW, warp * PPW + PPW) of the batch ----
+            // Branch-free over the PPW slots of the warp (a slot without a pair compares row slot 0 with
+            // itself and is not written back), so the shared-memory loads of later pairs are issued
+            // while earlier ones are being counted. offb[q] = byte offset of the second row's piece in a
+            // stage; the first row's offsets are packed two per register and read only where the first
+            // row changes (`reload`, warp-uniform: the pairs of a batch are sorted by first row).
+            // Counting is carry-save: per pair one `ones` word absorbs the two 32-site masks of a chunk,
+            // only the carries are POPCounted (weight 2), so a chunk costs one POPC per pair instead of two.
+            uint32_t offb[T2_PPW], offa2[T2_PPW / 2];
+            uint32_t acc[T2_PPW], ones[T2_PPW];
+            uint32_t reload = 0;
+            {
+                uint32_t prev = 0xFFFFFFFFu;
 #pragma unroll
-    for (int q = 0; q < TILE_PPW; q++) acc[q] = 0;
-    __syncthreads();                                   // meta[] is complete
-    // per-warp pair metadata hoisted out of the column loop: byte offsets of both rows inside
-    // a stage (packed a | b << 16), number of real pairs, and which pairs start a new first row
-    uint32_t offs[TILE_PPW];
-    uint32_t nq = 0, reload = 0;
-    {
-        uint32_t prev = 0xFFFFFFFFu;
+                for (int q = 0; q < T2_PPW; q++) {
+                    uint32_t m = meta[warp * T2_PPW + q];
+                    if (m == 0xFFFFu) m = 0u;
+                    const uint32_t sa = m & 0xFFu, sb = (m >> 8) & 0xFFu;
+                    offb[q] = sb * T2_CHUNK_BYTES + lane * 16u;
+                    const uint32_t oa = sa * T2_CHUNK_BYTES + lane * 16u;                 // < 65536
+                    if (q & 1) offa2[q >> 1] |= oa << 16; else offa2[q >> 1] = oa;
+                    acc[q] = 0; ones[q] = 0;
+                    if (sa != prev) reload |= 1u << q;
+                    prev = sa;
+                }
+            }
+            for (uint32_t c = 0; c < n_chunks; c++) {
+                const uint32_t k = it + c, s = k % T2_STAGES, ph = (k / T2_STAGES) & 1u;
+                mbar_wait(&full[s], ph);
+                const uint32_t st_s = smem_u32(stages) + s * T2_STAGE_BYTES;
+                uint4 a = make_uint4(0, 0, 0, 0);
 #pragma unroll
-        for (int q = 0; q < TILE_PPW; q++) {
-            const uint32_t m = meta[warp * TILE_PPW + q];
-            const uint32_t sa = m & 0xFFu, sb = (m >> 8) & 0xFFu;
-            offs[q] = (sa * TILE_BYTES) | ((sb * TILE_BYTES) << 16);
-            if (m != 0xFFFFu) {
-                nq = q + 1;
-                if (sa != prev) reload |= 1u << q;
-                prev = sa;
+                for (int q = 0; q < T2_PPW; q++) {
+                    uint4 b;
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "r"(st_s + offb[q]));
+                    if ((reload >> q) & 1u) {
+                        const uint32_t oa = (q & 1) ? (offa2[q >> 1] >> 16) : (offa2[q >> 1] & 0xFFFFu);
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(st_s + oa));
+                    }
+                    const uint32_t m0 = (a.x ^ b.x) | (a.y ^ b.y);
+                    const uint32_t m1 = (a.z ^ b.z) | (a.w ^ b.w);
+                    const uint32_t o = ones[q];
+                    ones[q] = o ^ m0 ^ m1;
+                    acc[q] += __popc((o & m0) | (m1 & (o | m0)));       // carries of the three-input add
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+            }
+#pragma unroll
+            for (int q = 0; q < T2_PPW; q++) {
+                uint32_t v = 2u * acc[q] + __popc(ones[q]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                const uint32_t idx = warp * T2_PPW + q;
+                if (lane == 0 && idx < bt.count) atomicAdd(&core_diff[tile_orig[bt.first + idx]], v);
             }
         }
-    }
-
-    for (uint32_t c = 0; c < n_chunks; c++) {
-        if (c + 2 < n_chunks) issue(c + 2); else cp_async_commit();     // keep the group count uniform
-        cp_async_wait<2>();                                              // chunk c has landed (this thread)
-        __syncthreads();                                                 // ... and everybody else's pieces
-        const uint8_t *base = tsm + (size_t)(c % TILE_STAGES) * TILE_ROWS * TILE_BYTES + lane * 16;
-        uint4 a = make_uint4(0, 0, 0, 0);
-#pragma unroll
-        for (int q = 0; q < TILE_PPW; q++) {
-            if (q < (int)nq) {                       // warp-uniform
-                if ((reload >> q) & 1u) a = *reinterpret_cast<const uint4 *>(base + (offs[q] & 0xFFFFu));
-                const uint4 b = *reinterpret_cast<const uint4 *>(base + (offs[q] >> 16));
-                acc[q] += diff_sites4(a, b);
-            }
-        }
-        __syncthreads();                              // stage c%3 may be overwritten by chunk c+3 next iteration
-    }
-#pragma unroll
-    for (int q = 0; q < TILE_PPW; q++) {
-        uint32_t v = acc[q];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        const uint32_t idx = warp * TILE_PPW + q;
-        if (lane == 0 && idx < bt.count) atomicAdd(&core_diff[tile_orig[bt.first + idx]], v);
+        it += n_chunks;
+        __syncthreads();                 // meta[] and *work_s are rewritten by the next work item
     }
 }
 

@@ -195,6 +195,14 @@ struct pansim_ctx {
     uint16_t *d_tile_slots = nullptr;
     uint32_t *d_tile_orig = nullptr;
     size_t plan_batches = 0, plan_cap_batches = 0, plan_cap_tile_pairs = 0;
+    // plane form of the core rows for the distance kernels (distance.cuh), made by a pre-pass when the
+    // state has changed since the last one; TMA descriptor of it for the tile kernel
+    uint8_t *d_planes = nullptr;
+    uint64_t core_version = 1, planes_version = 0;     // bumped whenever the current core buffer changes
+    CUtensorMap planes_tmap;
+    bool planes_tmap_ok = false;
+    uint32_t *d_work_counter = nullptr;
+    bool use_tiles2 = true;              // PANSIM_TILES2=0: row-stationary groups only
     // pair buffers
     uint32_t *d_r1 = nullptr, *d_r2 = nullptr, *d_cd = nullptr, *d_in = nullptr, *d_un = nullptr;
     size_t pair_cap = 0;
@@ -652,6 +660,7 @@ int launch_core_hr(pansim_ctx *c, uint32_t gen, uint8_t *state, cudaStream_t st)
     hr_apply_kernel<<<div_up64((uint64_t)c->N * c->n_regions, HR_WARPS * HR_APPLY_ITEMS), HR_WARPS * 32, 0, st>>>(h);
     LAUNCH_CHECK(c);
     c->hr_parity ^= 1;
+    c->core_version++;
     return 0;
 }
 
@@ -703,6 +712,7 @@ int launch_core_step(pansim_ctx *c, uint32_t gen, bool rng, cudaStream_t st)
         core_mut_kernel<true, false><<<grid, CM_THREADS, c->core_smem, st>>>(a);
     LAUNCH_CHECK(c);
     c->core_cur ^= 1;
+    c->core_version++;
     c->hr_pending = false;
     if (hr) {
         if (defer) {
@@ -818,7 +828,7 @@ void pansim_destroy(pansim_ctx *c)
     void *ptrs[] = {c->core[0], c->core[1], c->d_hr_slots, c->d_hr_counts, c->d_hr_ovf, c->d_hr_ovf_count, c->d_core_img, c->acc[0], c->acc[1], c->d_parents_buf[0], c->d_parents_buf[1], c->d_parents_buf[2], c->d_lw, c->d_lethal, c->d_logfit, c->d_avgdist,
                     c->d_num_genes, c->d_inter_diag, c->d_tmp_a, c->d_tmp_b, c->d_weights, c->d_cum, c->d_err, c->d_inter, c->d_rowInvK, c->d_gain_planes,
                     c->d_gain_thr, c->tab_mut.d_thr, c->tab_hr.d_thr, c->d_r1, c->d_r2, c->d_cd, c->d_in, c->d_un,
-                    c->d_replay, c->d_hkeys, c->d_hvals, c->d_stage, c->d_groups, c->d_partner, c->d_orig, c->d_batches, c->d_tile_slots, c->d_tile_orig, c->d_dump_counters, c->d_mut_row, c->d_mut_site,
+                    c->d_planes, c->d_work_counter, c->d_replay, c->d_hkeys, c->d_hvals, c->d_stage, c->d_groups, c->d_partner, c->d_orig, c->d_batches, c->d_tile_slots, c->d_tile_orig, c->d_dump_counters, c->d_mut_row, c->d_mut_site,
                     c->d_mut_seq, c->d_mut_allele, c->d_hr_rec, c->d_hr_locus, c->d_hr_donor, c->d_hr_seq,
                     c->d_hr_value, c->d_dump_flip, c->d_dump_gain};
     for (void *p : ptrs)
@@ -975,6 +985,7 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
         c->fitness_blocked = (uint64_t)c->N * c->G > (1ull << 25);
         if (const char *e = getenv("PANSIM_FITNESS_BLOCKED")) c->fitness_blocked = atoi(e) != 0;
         if (const char *e = getenv("PANSIM_INTER_POPC")) c->inter_popc = atoi(e) != 0;
+        if (const char *e = getenv("PANSIM_TILES2")) c->use_tiles2 = atoi(e) != 0;
         if (const char *e = getenv("PANSIM_FINE_TIMING")) c->fine_timing = atoi(e) != 0;
         if (const char *e = getenv("PANSIM_PDL")) c->use_pdl = atoi(e);
         if (c->tab_hr.nsub && core_bytes) {
@@ -1033,7 +1044,6 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
         // launch shape of the core kernel
         c->core_smem = core_mut_smem_bytes(c->tab_mut.size, c->tab_hr.nsub ? c->tab_hr.size : 0u);
         if (const char *e = getenv("PANSIM_HR_DEFER")) c->hr_defer = atoi(e) != 0;
-        CU(c, cudaFuncSetAttribute(pair_core_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile_smem_bytes()));
         CU(c, cudaFuncSetAttribute(core_mut_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->core_smem));
         CU(c, cudaFuncSetAttribute(core_mut_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->core_smem));
         CU(c, cudaFuncSetAttribute(core_mut_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->core_smem));
@@ -1142,6 +1152,7 @@ int pansim_upload_core(pansim_ctx *c, const uint8_t *bytes)
     if (int rc = ensure_core_joined(c)) return rc;
     uint8_t *dst = c->core[c->core_cur];
     c->hr_pending = false;                       // the state is replaced
+    c->core_version++;
     for (uint32_t r0 = 0; r0 < c->N; r0 += rows_per) {
         const uint32_t nr = std::min(rows_per, c->N - r0);
         CU(c, cudaMemcpyAsync(c->d_stage, bytes + (size_t)r0 * c->Ll, (size_t)nr * c->Ll, cudaMemcpyHostToDevice, c->stream));
@@ -1183,6 +1194,7 @@ int pansim_set_initial(pansim_ctx *c, const uint8_t *core_row, const uint8_t *ac
         if (int rc = ensure_core_joined(c)) return rc;
         uint8_t *dst = c->core[c->core_cur];
         c->hr_pending = false;                   // the state is replaced
+        c->core_version++;
         pack_core_kernel<<<div_up64(c->core_stride / 4, 256), 256, 0, c->stream>>>(c->d_stage, c->Ll, 0, 1, dst, c->core_stride, c->d_err);
         LAUNCH_CHECK(c);
         if (c->N > 1) {
@@ -1542,6 +1554,7 @@ int pansim_step_replay(pansim_ctx *c, const pansim_events *ev)
         CU(c, cudaMemsetAsync(c->d_hkeys, 0, cap * 8, c->stream));
         CU(c, cudaMemsetAsync(c->d_hvals, 0, cap * 4, c->stream));
         uint8_t *state = c->core[c->core_cur];
+        c->core_version++;
         for (CoreWriteList *l : {&mut, &hr}) {
             if (!l->n) continue;
             replay_insert_kernel<<<div_up64(l->n, 256), 256, 0, c->stream>>>(*l, c->site_begin, c->site_end, c->Ll, c->d_hkeys, c->d_hvals, cap - 1);
@@ -1582,30 +1595,71 @@ static int ensure_pairs(pansim_ctx *c, size_t n)
     return 0;
 }
 
-// Build (or reuse) the plan for this pair list: pairs whose 32-row block pair holds enough
-// pairs go to the shared-memory tile kernel, the rest to the row-stationary group kernel.
+// Plane form of the current core buffer (distance.cuh) and its TMA descriptor; the pre-pass runs only
+// when the rows have changed since the last one.
+static int ensure_planes(pansim_ctx *c)
+{
+    const size_t core_bytes = (size_t)c->N * c->core_stride;
+    if (!c->d_planes) {
+        if (cudaMalloc(&c->d_planes, core_bytes) != cudaSuccess) FAIL(c, PANSIM_ERR_NOMEM, "cudaMalloc of %zu bytes (bit planes for the distance pass) failed", core_bytes);
+        CU(c, cudaMalloc(&c->d_work_counter, sizeof(uint32_t)));
+        c->planes_version = 0;
+        // 2-D tensor map over the plane rows: x = 32-bit words of a row, y = rows; box = 512 bytes x 64 rows
+        c->planes_tmap_ok = false;
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && fn &&
+            qres == cudaDriverEntryPointSuccess && c->N >= 1 && c->core_stride / 4 < (1ull << 32)) {
+            typedef CUresult (*encode_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                         const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+            const cuuint64_t gdim[2] = {c->core_stride / 4, c->N};
+            const cuuint64_t gstride[1] = {c->core_stride};
+            const cuuint32_t box[2] = {T2_CHUNK_BYTES / 4, T2_BLOCK_ROWS};
+            const cuuint32_t estr[2] = {1, 1};
+            const CUresult r = reinterpret_cast<encode_t>(fn)(&c->planes_tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, c->d_planes, gdim, gstride, box,
+                                                             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            c->planes_tmap_ok = r == CUDA_SUCCESS;
+        }
+        cudaGetLastError();
+        CU(c, cudaFuncSetAttribute(pair_tile2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tile2_smem_bytes()));
+    }
+    if (c->planes_version != c->core_version) {
+        const uint64_t n_vec4 = core_bytes / 16;
+        const uint32_t grid = (uint32_t)std::min<uint64_t>((n_vec4 + 255) / 256, (uint64_t)c->sm_count * 32);
+        core_planes_kernel<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const uint4 *>(c->core[c->core_cur]),
+                                                        reinterpret_cast<uint4 *>(c->d_planes), n_vec4);
+        LAUNCH_CHECK(c);
+        c->planes_version = c->core_version;
+    }
+    return 0;
+}
+
+// Build (or reuse) the plan for this pair list. Pairs are bucketed by the pair of 64-row blocks their
+// endpoints fall in; a bucket with enough pairs is cut into batches for the TMA tile kernel (every staged
+// row then serves several pairs), the rest goes to the row-stationary group kernel.
 static int ensure_pair_plan(pansim_ctx *c, const uint32_t *r1, const uint32_t *r2, size_t P)
 {
     if (c->plan_r1.size() == P && (c->plan_groups || c->plan_batches) &&
         memcmp(c->plan_r1.data(), r1, P * 4) == 0 && memcmp(c->plan_r2.data(), r2, P * 4) == 0)
         return 0;
-    const uint32_t NB = (c->N + 31) / 32;
+    const uint32_t NB = (c->N + T2_BLOCK_ROWS - 1) / T2_BLOCK_ROWS;
     const size_t n_keys = (size_t)NB * NB;
     std::vector<uint32_t> key(P);
     std::vector<uint32_t> kcount;
-    // the shared-memory tile kernel is correct but measured slower than the row-stationary
-    // group kernel on B200 at cfg2 (3.1-3.5 ms vs 2.3 ms per 10^5 pairs): opt-in only
-    const bool use_tiles = getenv("PANSIM_TILES") != nullptr && n_keys <= (1u << 24);
+    const bool use_tiles = c->use_tiles2 && n_keys <= (1u << 24);
     if (use_tiles) {
         kcount.assign(n_keys + 1, 0);
         for (size_t k = 0; k < P; k++) {
-            const uint32_t bi = r1[k] >> 5, bj = r2[k] >> 5;
+            const uint32_t bi = r1[k] / T2_BLOCK_ROWS, bj = r2[k] / T2_BLOCK_ROWS;
             key[k] = std::min(bi, bj) * NB + std::max(bi, bj);
             kcount[key[k] + 1]++;
         }
     }
-    const uint32_t dense_min = 24;     // below this a tile would stage rows it barely uses
-    // ---- dense part: tile batches ----
+    // a tile stages 64 or 128 rows per chunk: below this many pairs the rows are barely used and the
+    // row-stationary kernel (9 row reads per 8 pairs) moves less
+    const uint32_t dense_min = 96;
     std::vector<TileBatch> batches;
     std::vector<uint16_t> tslots;
     std::vector<uint32_t> torig;
@@ -1615,45 +1669,57 @@ static int ensure_pair_plan(pansim_ctx *c, const uint32_t *r1, const uint32_t *r
         for (size_t i = 0; i < n_keys; i++) kstart[i + 1] += kstart[i];
         std::vector<uint32_t> order(P), cur(kstart.begin(), kstart.end() - 1);
         for (size_t k = 0; k < P; k++) order[cur[key[k]]++] = (uint32_t)k;
-        const uint32_t cols = (uint32_t)(c->core_stride / TILE_BYTES);
+        const uint32_t cols = (uint32_t)(c->core_stride / T2_CHUNK_BYTES);
         size_t n_dense_batches = 0;
         for (size_t kk = 0; kk < n_keys; kk++) {
             const uint32_t cnt = kstart[kk + 1] - kstart[kk];
-            if (cnt >= dense_min) n_dense_batches += (cnt + TILE_BATCH - 1) / TILE_BATCH;
+            if (cnt >= dense_min) n_dense_batches += (cnt + T2_BATCH - 1) / T2_BATCH;
         }
-        // split the column range so that there are a few waves of CTAs
+        // column ranges: enough work items for ~8 per SM (the persistent CTAs balance themselves), ranges
+        // of at least 32 chunks so that the per-item prologue stays small
         uint32_t col_split = 1;
-        const size_t want = (size_t)c->sm_count * 2 * 3;
-        while (n_dense_batches && n_dense_batches * col_split < want && col_split < 8 && cols / (col_split * 2) >= 16) col_split *= 2;
+        while (n_dense_batches && n_dense_batches * col_split < (size_t)c->sm_count * 8 && cols / (col_split * 2) >= 32) col_split *= 2;
+        struct Raw { uint32_t ba, bb, first, count; };
+        std::vector<Raw> raw;
         for (size_t kk = 0; kk < n_keys; kk++) {
             const uint32_t cnt = kstart[kk + 1] - kstart[kk];
             if (cnt < dense_min) continue;
             const uint32_t ba = (uint32_t)(kk / NB), bb = (uint32_t)(kk % NB);
-            // slots of each pair, sorted by first slot (row-stationary reuse inside a warp)
+            // slots of each pair (0..63 block a, 64..127 block b), sorted by first slot: a warp keeps the
+            // first row's piece in registers while it repeats. The distance is symmetric, so a pair whose
+            // first endpoint lies in the later block is taken as (j, i).
             std::vector<std::pair<uint32_t, uint32_t>> v;      // (slot_a << 8 | slot_b, orig)
             v.reserve(cnt);
             for (uint32_t t = kstart[kk]; t < kstart[kk + 1]; t++) {
                 const uint32_t k = order[t];
                 is_dense[k] = 1;
-                auto slot = [&](uint32_t row) { return (row >> 5) == ba ? (row & 31u) : 32u + (row & 31u); };
-                v.push_back({(slot(r1[k]) << 8) | slot(r2[k]), k});
+                uint32_t i = r1[k], j = r2[k];
+                if (i / T2_BLOCK_ROWS != ba) std::swap(i, j);
+                const uint32_t sa = i % T2_BLOCK_ROWS, sb = (ba == bb ? 0u : (uint32_t)T2_BLOCK_ROWS) + j % T2_BLOCK_ROWS;
+                v.push_back({(sa << 8) | sb, k});
             }
             std::sort(v.begin(), v.end());
-            for (uint32_t f = 0; f < cnt; f += TILE_BATCH) {
-                const uint32_t n = std::min<uint32_t>(TILE_BATCH, cnt - f);
-                for (uint32_t sp = 0; sp < col_split; sp++) {
-                    TileBatch b;
-                    b.block_a = ba; b.block_b = bb; b.first = (uint32_t)tslots.size(); b.count = n;
-                    b.col_begin = (uint32_t)((uint64_t)cols * sp / col_split);
-                    b.col_end = (uint32_t)((uint64_t)cols * (sp + 1) / col_split);
-                    batches.push_back(b);
-                }
-                for (uint32_t t = f; t < f + n; t++) {
-                    tslots.push_back((uint16_t)((v[t].first >> 8) | ((v[t].first & 0xFFu) << 8)));   // low = slot_a
+            // equal batches (a bucket of 400 pairs becomes 2 x 200, not 384 + 16)
+            const uint32_t nb = (cnt + T2_BATCH - 1) / T2_BATCH;
+            for (uint32_t b = 0; b < nb; b++) {
+                const uint32_t f = (uint32_t)((uint64_t)cnt * b / nb), e = (uint32_t)((uint64_t)cnt * (b + 1) / nb);
+                raw.push_back({ba, bb, (uint32_t)tslots.size(), e - f});
+                for (uint32_t t = f; t < e; t++) {
+                    tslots.push_back((uint16_t)((v[t].first >> 8) | ((v[t].first & 0xFFu) << 8)));   // low byte = slot_a
                     torig.push_back(v[t].second);
                 }
             }
         }
+        // work items in column-range-major order: the items that run at the same time read the same
+        // column range of all rows, so DRAM sees every row about once per pass
+        for (uint32_t sp = 0; sp < col_split; sp++)
+            for (const Raw &rw : raw) {
+                TileBatch b;
+                b.block_a = rw.ba; b.block_b = rw.bb; b.first = rw.first; b.count = rw.count;
+                b.col_begin = (uint32_t)((uint64_t)cols * sp / col_split);
+                b.col_end = (uint32_t)((uint64_t)cols * (sp + 1) / col_split);
+                batches.push_back(b);
+            }
     }
     // ---- sparse part: row-stationary groups (counting sort by first row) ----
     std::vector<uint32_t> start(c->N + 1, 0);
@@ -1707,6 +1773,7 @@ static int ensure_pair_plan(pansim_ctx *c, const uint32_t *r1, const uint32_t *r
 // rows_active = number of distinct rows the plan touches (sizes the L2-resident column chunk)
 static int launch_pair_core(pansim_ctx *c, uint32_t *d_cd, size_t P, uint32_t rows_active, bool clear)
 {
+    if (int rc = ensure_planes(c)) return rc;
     const uint32_t row_vec4 = (uint32_t)(c->core_stride / 16);
     // column chunk sized so that rows x chunk stays L2 resident
     uint64_t chunk_bytes = (48ull << 20) / std::max(1u, rows_active);
@@ -1721,14 +1788,17 @@ static int launch_pair_core(pansim_ctx *c, uint32_t *d_cd, size_t P, uint32_t ro
     if (n_chunks > 65535) { n_chunks = 65535; chunk_vec4 = (row_vec4 + n_chunks - 1) / n_chunks; chunk_vec4 = ((chunk_vec4 + 255) / 256) * 256; n_chunks = (row_vec4 + chunk_vec4 - 1) / chunk_vec4; }
     if (clear) CU(c, cudaMemsetAsync(d_cd, 0, P * 4, c->stream));      // both kernels accumulate with integer atomics
     if (c->plan_batches) {
-        pair_core_tile_kernel<<<(uint32_t)c->plan_batches, TILE_THREADS, tile_smem_bytes(), c->stream>>>(
-            c->core[c->core_cur], c->core_stride, c->N, c->d_batches, c->d_tile_slots, c->d_tile_orig, d_cd);
+        if (!c->planes_tmap_ok) FAIL(c, PANSIM_ERR_CUDA, "no TMA descriptor for the plane rows (cuTensorMapEncodeTiled unavailable)");
+        CU(c, cudaMemsetAsync(c->d_work_counter, 0, sizeof(uint32_t), c->stream));
+        const uint32_t grid = (uint32_t)std::min<size_t>(c->plan_batches, (size_t)c->sm_count);
+        pair_tile2_kernel<<<grid, T2_THREADS, tile2_smem_bytes(), c->stream>>>(
+            c->planes_tmap, c->d_batches, (uint32_t)c->plan_batches, c->d_work_counter, c->d_tile_slots, c->d_tile_orig, d_cd);
         LAUNCH_CHECK(c);
     }
     if (c->plan_groups) {
         const uint32_t gx = (uint32_t)std::min<size_t>(c->plan_groups, 1u << 20);
-        pair_core_grouped_kernel<<<dim3(gx, n_chunks), PAIR_THREADS, 0, c->stream>>>(
-            c->core[c->core_cur], c->core_stride, chunk_vec4, row_vec4, c->d_groups, (uint32_t)c->plan_groups,
+        pair_planes_grouped_kernel<<<dim3(gx, n_chunks), PAIR_THREADS, 0, c->stream>>>(
+            c->d_planes, c->core_stride, chunk_vec4, row_vec4, c->d_groups, (uint32_t)c->plan_groups,
             c->d_partner, c->d_orig, d_cd);
         LAUNCH_CHECK(c);
     }
