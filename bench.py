@@ -222,8 +222,17 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; pansim_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    # diagnostics (tools/gpu_call_8d.sh): which ingredient of a multi-rank run changes the per-rank step time
+    backend = os.environ.get("BENCH_DIST_BACKEND", "nccl")
+    no_comm = os.environ.get("BENCH_NO_COMM") == "1"
+    no_shard = os.environ.get("BENCH_NO_SHARD") == "1"
+    fake_world, fake_rank = int(os.environ.get("BENCH_FAKE_WORLD", "0")), int(os.environ.get("BENCH_FAKE_RANK", "0"))
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        if backend == "nccl":
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        else:
+            dist.init_process_group(backend)
+    red_dev = "cuda" if backend == "nccl" else "cpu"
 
     def barrier():
         if world > 1:
@@ -233,7 +242,7 @@ def main():
     def max_over_ranks(x: float) -> float:
         if world == 1:
             return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        t = torch.tensor([x], dtype=torch.float64, device=red_dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
@@ -243,22 +252,29 @@ def main():
     # this rank's slab: columns [rank*L, (rank+1)*L) of a (world*L)-site alignment
     from pansim_b200.sharding import SITE_ALIGN, ShardedPansim, broadcast_unique_id, column_shards
     L = CFG2["core_size"]
-    Lslab = L if world == 1 else ((L + SITE_ALIGN - 1) // SITE_ALIGN) * SITE_ALIGN   # whole regions per rank
-    total_L = L if world == 1 else Lslab * world
+    cfg_world, cfg_rank = (fake_world, fake_rank) if fake_world else ((1, 0) if no_shard else (world, rank))
+    Lslab = L if cfg_world == 1 else ((L + SITE_ALIGN - 1) // SITE_ALIGN) * SITE_ALIGN   # whole regions per rank
+    total_L = L if cfg_world == 1 else Lslab * cfg_world
     kw = dict(CFG2)
     kw["core_size"] = total_L
-    # keep the per-site rates of cfg2: lambda scales with the alignment length (main.rs:275)
+    # Weak scaling = the same work on every rank. The per-site core rates of cfg2 are kept as the alignment
+    # grows (lambda scales with its length, main.rs:275). The reference ties the HGT event count of the
+    # ACCESSORY genome to the core mutation count (main.rs:280: round(n_core_mutations * HGT_rate)), so an
+    # N-times longer alignment would also make the replicated accessory genome turn over N times faster and
+    # its selection chain heavier on every rank (measured: 198 instead of 166 us per generation at N = 8,
+    # profiles/r02_scaling_diag.md). HGT_rate / N keeps the accessory genome exactly cfg2's.
+    kw["HGT_rate"] = pb.Params().HGT_rate / cfg_world
     p = pb.Params(**kw)
     d = pb.derive(p)
 
     # ---- multi-GPU parity, visible to the driver: a small column-sharded run must equal the unsharded one
     shard_parity = None
-    if world > 1:
+    if world > 1 and not (no_comm or no_shard):
         shard_parity = check_shard_parity(pb, ShardedPansim, rank, world, local_rank, dist, torch)
 
-    site_begin, site_end = (0, 0) if world == 1 else column_shards(total_L, world)[rank]
+    site_begin, site_end = (0, 0) if cfg_world == 1 else column_shards(total_L, cfg_world)[cfg_rank]
     sim = pb.Pansim.from_params(p, device=local_rank, site_begin=site_begin, site_end=site_end)
-    if world > 1:
+    if world > 1 and not (no_comm or no_shard):
         sim.comm_init_rank(world, rank, broadcast_unique_id(rank))      # NCCL communicator inside the library
     info = sim.info()
 
@@ -273,7 +289,7 @@ def main():
     def gather_ranks(x: float):
         if world == 1:
             return [x]
-        t = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t = torch.zeros(world, dtype=torch.float64, device=red_dev)
         t[rank] = x
         dist.all_reduce(t)
         return [float(v) for v in t.tolist()]
@@ -308,6 +324,16 @@ def main():
     mut_ms = core_ms - hr_ms                        # core_mut_kernel: gather + deferred recombination + SNPs
     launches = int(tm.launches)
     select_ms, acc_ms = tm.select_ms / K, tm.acc_step_ms / K
+    if os.environ.get("BENCH_DIAG") == "1":        # diagnostics: the generation batches only
+        if rank == 0:
+            print(json.dumps({"diag": os.environ.get("BENCH_DIAG_NAME", ""), "world": world, "backend": backend, "no_comm": no_comm,
+                              "no_shard": no_shard, "fake_world": fake_world, "site_begin": int(site_begin),
+                              "us_per_step": 1e3 * dev_ms / K, "core_us": 1e3 * mut_ms, "select_us": 1e3 * select_ms,
+                              "acc_us": 1e3 * acc_ms, "per_rank_us": [1e3 * x / K for x in batch_rank_ms[med]]}), file=_JSON_OUT, flush=True)
+        sim.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- distance pass (device time of the kernels; pairs resident; N > 1: + ncclAllReduce in the library) ----
     n_dist = max(3, min(10, K))
@@ -396,6 +422,9 @@ def main():
                    "core_size_per_gpu": int(info.local_sites),
                    "sharding": "columns; accessory replicated; no collective in the generation step; "
                                "distance pass: ncclAllReduce of the core counts inside the library",
+                   "weak_scaling": "every rank holds a cfg2 slab (1.2 Mbp x 1000) of an N x 1.2 Mbp alignment; per-site core rates "
+                                   "and the accessory genome's event counts are cfg2's at every N (HGT_rate / N, because "
+                                   "main.rs:280 ties the HGT count to the alignment length)",
                    "l2": "inputs larger than L2 (2 x %.0f MB packed state, double buffered)" % (info.core_state_bytes / 1e6),
                    "timing": "CUDA events on the library stream around each batch of K generations, max over ranks, "
                              "median of the R batches"},

@@ -252,6 +252,8 @@ int pansim_group_run_generations_stats(pansim_group *g, uint32_t gen0, uint32_t 
 typedef int (*pansim_pairs_cb)(void *user, uint32_t row_begin, uint32_t row_end, size_t n_pairs,
                                const uint32_t *core_diff, const uint32_t *inter, const uint32_t *uni);
 int pansim_group_all_pairs(pansim_group *g, size_t chunk_pairs, pansim_pairs_cb cb, void *user);
+/* last walk: wall time (callbacks included), device time of shard 0 inside the reduce-scatters, pairs walked */
+int pansim_group_all_pairs_timing(pansim_group *g, float *wall_ms, float *nccl_ms, uint64_t *pairs);
 int pansim_group_gene_counts(pansim_group *g, uint32_t *counts);                          /* population.rs:840-856 */
 int pansim_group_download_acc(pansim_group *g, uint8_t *acc_out);
 int pansim_group_download_core(pansim_group *g, uint8_t *core_onehot_out);               /* [N x core_size] */

@@ -28,7 +28,7 @@ EXPORTED = [
     "pansim_comm_unique_id", "pansim_comm_init_rank", "pansim_comm_info",
     "pansim_group_create", "pansim_group_destroy", "pansim_group_last_error", "pansim_group_size", "pansim_group_ctx",
     "pansim_group_set_initial", "pansim_group_set_selection", "pansim_group_run_generations", "pansim_group_pair_counts",
-    "pansim_group_run_generations_stats", "pansim_group_all_pairs", "pansim_group_gene_counts",
+    "pansim_group_run_generations_stats", "pansim_group_all_pairs", "pansim_group_all_pairs_timing", "pansim_group_gene_counts",
     "pansim_group_download_acc", "pansim_group_download_core", "pansim_group_export_core_csv",
 ]
 COMM_ID_BYTES = 128
@@ -181,6 +181,7 @@ def lib():
     sig("pansim_group_pair_counts", cint, vp, vp, vp, sz, vp, vp, vp)
     sig("pansim_group_run_generations_stats", cint, vp, u32, u32, vp, vp, sz, vp)
     sig("pansim_group_all_pairs", cint, vp, sz, PAIRS_CB, vp)
+    sig("pansim_group_all_pairs_timing", cint, vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint64))
     sig("pansim_group_gene_counts", cint, vp, vp)
     sig("pansim_group_download_acc", cint, vp, vp)
     sig("pansim_group_download_core", cint, vp, vp)

@@ -27,6 +27,7 @@ struct AccArgs {
     uint32_t n_rows, n_genes, stride_words;
     uint2 key;
     uint32_t gen;
+    const uint32_t *gen_dev;      // nullptr, or a device word added to gen (replayed CUDA graphs)
     // gene compartments (main.rs:341-367): scalars, not arrays, so that the kernels never index
     // the parameter block dynamically (that would force a per-thread local copy of it)
     uint32_t lo0, hi0, lo1, hi1;   // genes with weight 1.0 in compartment 0 / 1 (empty: lo == hi)
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(256) acc_gather_flip_kernel(const AccArgs a)
         uint32_t active = 0;
         if (a.flip_thr0) active |= m0;
         if (a.flip_thr1) active |= m1;
-        const uint32_t flips = bernoulli_word(a.key, a.gen, STREAM_ACC_FLIP, row, w, active,
+        const uint32_t flips = bernoulli_word(a.key, a.gen + (a.gen_dev ? __ldg(a.gen_dev) : 0u), STREAM_ACC_FLIP, row, w, active,
                                               PlanesConst{a.flip_thr0, a.flip_thr1, m0, m1});
         const uint32_t v = src[w] ^ flips;
         dst[w] = v;
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(256) acc_hgt_apply_kernel(const AccArgs a)
     if (a.hgt_scale1 > 0.0) valid |= comp_mask_for_word(w, a.lo1, a.hi1);
     const uint32_t cur = a.new_state[idx];
     const uint32_t active = valid & ~cur;      // a hit on a present gene writes 1 over 1
-    const uint32_t gain = bernoulli_word(a.key, a.gen, STREAM_ACC_HGT, row, w, active,
+    const uint32_t gain = bernoulli_word(a.key, a.gen + (a.gen_dev ? __ldg(a.gen_dev) : 0u), STREAM_ACC_HGT, row, w, active,
                                          PlanesTable(a.gain_planes + (uint64_t)w * 32u));
     if (gain) a.new_state[idx] = cur | gain;
     if (DUMP) a.dump_gain[idx] = gain;

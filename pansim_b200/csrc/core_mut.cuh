@@ -98,6 +98,8 @@ struct CoreMutArgs {
     uint32_t mut_size, mut_nsub, mut_kmax;
     // recombination events of generation hr_gen still pending on old_state (hr_nsub = 0: none)
     uint32_t hr_size, hr_nsub, hr_kmax, hr_gen;
+    const uint32_t *gen_dev;  // nullptr, or a device word added to gen / hr_gen (replayed CUDA graphs: the generation number of a
+                              // captured launch is relative to a counter the graph advances itself)
     uint32_t hr_k0;           // first threshold of the 32-wide window hr_count_from_uniform_s tries first (<= hr_size - 32)
     uint32_t hr_lemire_t;     // 2^32 mod (n_rows - 1), see hr_event
     // optional event dump (parity instrumentation)
@@ -259,12 +261,12 @@ struct MutChunk {
 // marks the last event of its cell within the window (population.rs:745), dw = the donor's word.
 struct HrWindow { uint32_t K, pk, dw; };
 
-__device__ __forceinline__ HrWindow hr_window_fetch(const CoreMutArgs &a, const uint32_t *hr_thr, uint32_t hr_thr_s, uint32_t prow,
+__device__ __forceinline__ HrWindow hr_window_fetch(const CoreMutArgs &a, uint32_t hr_gen, const uint32_t *hr_thr, uint32_t hr_thr_s, uint32_t prow,
                                                     uint32_t reg, uint32_t lane, uint32_t base, uint32_t K_known)
 {
     const uint32_t greg = a.region0 + reg;
     const uint32_t lim = greg == a.last_greg ? a.lim_last : REGION_SITES;
-    const HrEvent ev = hr_event(greg, prow, a.hr_gen, a.rk, base + lane, a.n_rows - 1u, a.hr_lemire_t);
+    const HrEvent ev = hr_event(greg, prow, hr_gen, a.rk, base + lane, a.n_rows - 1u, a.hr_lemire_t);
     // lanes that drew the same site: asked for before the count is known (the match unit is slow and
     // the count needs a shared-memory round trip of its own), validity is folded in afterwards
     const uint32_t same = __match_any_sync(0xffffffffu, ev.pos);
@@ -272,7 +274,7 @@ __device__ __forceinline__ HrWindow hr_window_fetch(const CoreMutArgs &a, const 
     h.K = K_known;
     if (base == 0u) {
         h.K = hr_count_from_uniform_s(hr_thr_s, a.hr_size, a.hr_kmax, a.hr_k0, __shfl_sync(0xffffffffu, ev.w, 0), lane);
-        if (a.hr_nsub > 1) h.K += hr_count_extra(greg, prow, a.hr_gen, a.key, hr_thr, a.hr_size, a.hr_nsub, a.hr_kmax, lane);
+        if (a.hr_nsub > 1) h.K += hr_count_extra(greg, prow, hr_gen, a.key, hr_thr, a.hr_size, a.hr_nsub, a.hr_kmax, lane);
     }
     // events base .. K-1 exist: they sit in the lanes below K - base. A site beyond the ragged end of the
     // alignment is thinned away (the same site in every lane of its match group, so the group drops as a whole).
@@ -356,6 +358,8 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
     const uint32_t warp = threadIdx.x >> 5;
     uint32_t lane = threadIdx.x & 31;
     asm volatile("" : "+r"(lane));          // keep it in a register (otherwise %tid.x is re-read at every use)
+    const uint32_t gen_off = a.gen_dev ? __ldg(a.gen_dev) : 0u;
+    const uint32_t gen = a.gen + gen_off, hr_gen = a.hr_gen + gen_off;
     uint8_t *stages = m.stages + (size_t)warp * CM_STAGES * REGION_BYTES;
     uint64_t *bars = m.bars + warp * CM_STAGES;
     const uint32_t *tab = m.tab;
@@ -405,7 +409,7 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
     const bool hr_on = RNG && a.hr_nsub != 0u;
     HrWindow hw_cur{0u, 0u, 0u};
     uint32_t prow = hr_on ? PANSIM_CM_PARENT(row) : 0u, nprow = prow;      // parent of `row` / of the next item's row
-    if (hr_on) hw_cur = hr_window_fetch(a, m.hr_thr, hr_thr_s, prow, blk_reg0 + breg, lane, 0u, 0u);
+    if (hr_on) hw_cur = hr_window_fetch(a, hr_gen, m.hr_thr, hr_thr_s, prow, blk_reg0 + breg, lane, 0u, 0u);
     uint32_t s = 0, par = 0;                 // stage of item j and the phase parity of its mbarrier
     for (uint32_t j = 0; j < n_my; j++) {
         uint32_t *sw = reinterpret_cast<uint32_t *>(stages + s * REGION_BYTES);     // generic pointer: ragged edge only
@@ -416,7 +420,7 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
         const uint32_t greg = a.region0 + reg;
         const uint64_t reg_site0 = (uint64_t)greg * REGION_SITES;          // event dump only
         const uint32_t lim = greg == a.last_greg ? a.lim_last : REGION_SITES;
-        const uint4 mctr = make_ctr(greg * 32u + lane, row, a.gen, STREAM_CORE_MUT);
+        const uint4 mctr = make_ctr(greg * 32u + lane, row, gen, STREAM_CORE_MUT);
         uint4 c0 = make_uint4(0, 0, 0, 0), c1 = make_uint4(0, 0, 0, 0);
         uint32_t k = 0;
         if (RNG && a.mut_nsub) {
@@ -441,7 +445,7 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
                 hr_window_apply(sw_s, hw_cur);
 #pragma unroll 1
                 for (uint32_t base = 32u; base < hw_cur.K; base += 32u)
-                    hr_window_apply(sw_s, hr_window_fetch(a, m.hr_thr, hr_thr_s, prow, reg, lane, base, hw_cur.K));
+                    hr_window_apply(sw_s, hr_window_fetch(a, hr_gen, m.hr_thr, hr_thr_s, prow, reg, lane, base, hw_cur.K));
             }
             // first window of the NEXT item, fetched into the registers just consumed: its donor
             // loads are in flight while this item's SNP events are applied
@@ -449,7 +453,7 @@ __device__ __forceinline__ void mut_cta_items(const CoreMutArgs &a, const MutSme
                 uint32_t nrow = row + d_row, nreg = breg + d_reg;
                 if (nreg >= blk_regs) { nreg -= blk_regs; nrow++; }
                 nprow = nrow == row ? prow : PANSIM_CM_PARENT(nrow);
-                hw_cur = hr_window_fetch(a, m.hr_thr, hr_thr_s, nprow, blk_reg0 + nreg, lane, 0u, 0u);
+                hw_cur = hr_window_fetch(a, hr_gen, m.hr_thr, hr_thr_s, nprow, blk_reg0 + nreg, lane, 0u, 0u);
             }
         }
 

@@ -219,7 +219,7 @@ __device__ __forceinline__ uint32_t diff_planes(const uint4 a, const uint4 b)
 
 // row-stationary groups (see pair_core_grouped_kernel) on the plane form: the sparse remainder of a
 // sampled pair list and the exact all-pairs row blocks
-__global__ void __launch_bounds__(PAIR_THREADS) pair_planes_grouped_kernel(
+__global__ void __launch_bounds__(PAIR_THREADS, 4) pair_planes_grouped_kernel(
     const uint8_t *planes, uint64_t row_stride, uint32_t chunk_vec4, uint32_t row_vec4, const PairGroup *groups,
     uint32_t n_groups, const uint32_t *partner, const uint32_t *orig_index, uint32_t *core_diff)
 {
@@ -461,7 +461,8 @@ __global__ void __launch_bounds__(256) pair_acc_kernel(const uint32_t *acc, uint
 // form: the products are rounded into shared memory before they are added (Rust has no contraction).
 // out[4] = { avg_core, std_core, avg_acc, std_acc } (the column order of _per_gen.tsv, main.rs:546).
 constexpr int STATS_CHUNK = 1024;
-constexpr int STATS_THREADS = 128;      // warp 0: core producer, 1: core chain, 2: accessory producer, 3: accessory chain
+constexpr int STATS_PROD_WARPS = 4;     // producer warps per vector: a chunk is 8 loads deep per lane, well under the chain's 8.4k cycles
+constexpr int STATS_THREADS = (2 * STATS_PROD_WARPS + 2) * 32;   // warps 0-3: core producers, 4-7: accessory producers, 8: core chain, 9: accessory chain
 
 struct PairStatsArgs {
     const uint32_t *core_diff, *inter, *uni;
@@ -475,8 +476,9 @@ __global__ void __launch_bounds__(STATS_THREADS) pair_stats_kernel(const PairSta
     __shared__ double buf[2][2][STATS_CHUNK];      // [vector][stage][element]
     __shared__ double mean_s[2];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t vec = warp >> 1;                // 0 = core distances, 1 = accessory distances
-    const bool producer = (warp & 1u) == 0u;
+    const bool producer = warp < 2u * STATS_PROD_WARPS;
+    const uint32_t vec = producer ? warp / STATS_PROD_WARPS : warp - 2u * STATS_PROD_WARPS;     // 0 = core distances, 1 = accessory distances
+    const uint32_t plane = (warp % STATS_PROD_WARPS) * 32u + lane;                               // producer lane within its vector
     const uint32_t n = a.n_pairs;
     const uint32_t n_chunks = (n + STATS_CHUNK - 1) / STATS_CHUNK;
     const double dn = (double)n;
@@ -484,7 +486,8 @@ __global__ void __launch_bounds__(STATS_THREADS) pair_stats_kernel(const PairSta
     auto produce = [&](uint32_t c, int pass, double mean) {
         double *dst = buf[vec][c & 1u];
         const uint32_t k0 = c * STATS_CHUNK, k1 = min(n, k0 + STATS_CHUNK);
-        for (uint32_t k = k0 + lane; k < k1; k += 32) {
+#pragma unroll 4
+        for (uint32_t k = k0 + plane; k < k1; k += 32u * STATS_PROD_WARPS) {
             double d;
             if (vec == 0) {
                 d = __ddiv_rn((double)a.core_diff[k], a.core_size);                                          // population.rs:822

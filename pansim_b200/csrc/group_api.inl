@@ -22,6 +22,10 @@ struct pansim_group {
     std::vector<cudaEvent_t> ev_compute, ev_done[2];
     uint32_t *h_cnt[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     size_t h_cap = 0;
+    // device time of the reduce-scatter on shard 0 (timed events around every block's collective) and wall time of the last walk
+    cudaEvent_t ev_rs0[2] = {nullptr, nullptr}, ev_rs1[2] = {nullptr, nullptr};
+    float last_nccl_ms = 0.f, last_wall_ms = 0.f;
+    uint64_t last_pairs = 0;
 };
 
 namespace {
@@ -60,7 +64,7 @@ int group_allreduce(pansim_group *g, uint32_t *const *bufs, size_t n)
     NcclApi &api = nccl_api();
     ncclResult_t r = api.GroupStart();
     for (size_t i = 0; i < g->ctx.size() && r == ncclSuccess; i++)
-        r = api.AllReduce(bufs[i], bufs[i], n, ncclUint32, ncclSum, g->comms[i], g->ctx[i]->stream);
+        r = api.AllReduce(bufs[i], bufs[i], n, ncclUint32, ncclSum, g->comms[i], g->ctx[i]->ps);
     const ncclResult_t r2 = api.GroupEnd();
     if (r == ncclSuccess) r = r2;
     if (r != ncclSuccess) GFAIL(g, PANSIM_ERR_CUDA, "ncclAllReduce over the shards failed: %s", api.GetErrorString(r));
@@ -140,6 +144,7 @@ void pansim_group_destroy(pansim_group *g)
         cudaDeviceSynchronize();
         if (i < g->stream_comm.size() && g->stream_comm[i]) cudaStreamDestroy(g->stream_comm[i]);
         if (i < g->ev_compute.size() && g->ev_compute[i]) cudaEventDestroy(g->ev_compute[i]);
+        if (i == 0) for (int s = 0; s < 2; s++) { if (g->ev_rs0[s]) cudaEventDestroy(g->ev_rs0[s]); if (g->ev_rs1[s]) cudaEventDestroy(g->ev_rs1[s]); }
         for (int s = 0; s < 2; s++)
             if (i < g->ev_done[s].size() && g->ev_done[s][i]) cudaEventDestroy(g->ev_done[s][i]);
     }
@@ -231,32 +236,33 @@ int pansim_group_run_generations_stats(pansim_group *g, uint32_t gen0, uint32_t 
         if (!rc) rc = ensure_stats(c, n, P, true);
         if (!rc) rc = pair_prepare(c, r1, r2, P);
         if (rc) return gfail_from(g, (int)i, rc);
-        c->pdl_now = false;
         timing_begin(c);
     }
     std::vector<uint32_t *> bufs(ns);
+    std::vector<uint32_t *> in_(ns), un_(ns);
     for (uint32_t gen = 0; gen < n; gen++) {
         const int slot = (int)(gen & 1u);
         for (size_t i = 0; i < ns; i++) {
             pansim_ctx *c = g->ctx[i];
             cudaSetDevice(c->cfg.device);
-            int rc = step_device(c, gen0 + gen);
-            uint32_t *cd = slot ? c->d_cnt2[0] : c->d_cd, *in = slot ? c->d_cnt2[1] : c->d_in, *un = slot ? c->d_cnt2[2] : c->d_un;
-            if (!rc && c->ev_stats_valid[slot]) cudaStreamWaitEvent(c->stream, c->ev_stats[slot], 0);
-            if (!rc) rc = pair_launch(c, P, cd, i == 0 ? in : nullptr, i == 0 ? un : nullptr);
-            if (rc) return gfail_from(g, (int)i, rc);
-            bufs[i] = cd;
+            if (int rc = stats_generation(c, gen0 + gen, slot, P, i == 0, &bufs[i], &in_[i], &un_[i])) return gfail_from(g, (int)i, rc);
         }
         if (int rc = group_allreduce(g, bufs.data(), P)) return rc;
-        pansim_ctx *c0 = g->ctx[0];
-        cudaSetDevice(c0->cfg.device);
-        uint32_t *in0 = slot ? c0->d_cnt2[1] : c0->d_in, *un0 = slot ? c0->d_cnt2[2] : c0->d_un;
-        if (int rc = launch_pair_stats(c0, slot, P, bufs[0], in0, un0, c0->d_stats + (size_t)gen * 4)) return gfail_from(g, 0, rc);
+        for (size_t i = 0; i < ns; i++) {
+            pansim_ctx *c = g->ctx[i];
+            cudaSetDevice(c->cfg.device);
+            if (i == 0) {
+                if (int rc = launch_pair_stats(c, slot, P, bufs[0], in_[0], un_[0], c->d_stats + (size_t)gen * 4)) return gfail_from(g, 0, rc);
+            } else {
+                cudaEventRecord(c->ev_pairs[slot], c->ps);          // pass done on this shard (launch_pair_stats records it on shard 0)
+                c->ev_pairs_valid[slot] = true;
+            }
+        }
     }
     for (size_t i = 0; i < ns; i++) {
         pansim_ctx *c = g->ctx[i];
         cudaSetDevice(c->cfg.device);
-        if (int rc = join_core_stream(c)) return gfail_from(g, (int)i, rc);
+        if (int rc = stats_batch_end(c)) return gfail_from(g, (int)i, rc);
         timing_end(c);
     }
     pansim_ctx *c0 = g->ctx[0];
@@ -330,12 +336,24 @@ int pansim_group_all_pairs(pansim_group *g, size_t chunk_pairs, pansim_pairs_cb 
         if (!rc) rc = ensure_stats(c, 1, padded_max, true);       // second set of count vectors
         if (rc) return gfail_from(g, (int)i, rc);
     }
+    if (!g->ev_rs0[0]) {
+        cudaSetDevice(g->ctx[0]->cfg.device);
+        for (int s = 0; s < 2; s++) { cudaEventCreate(&g->ev_rs0[s]); cudaEventCreate(&g->ev_rs1[s]); }
+    }
+    g->last_nccl_ms = 0.f; g->last_pairs = 0;
+    const auto wall0 = std::chrono::steady_clock::now();
     auto deliver = [&](size_t b) -> int {
         const int set = (int)(b & 1u);
         for (size_t i = 0; i < ns; i++) {
             cudaSetDevice(g->ctx[i]->cfg.device);
             if (cudaEventSynchronize(g->ev_done[set][i]) != cudaSuccess) GFAIL(g, PANSIM_ERR_CUDA, "all-pairs block %zu failed on shard %zu: %s", b, i, cudaGetErrorString(cudaGetLastError()));
         }
+        if (ns > 1) {
+            float ms = 0.f;
+            cudaSetDevice(g->ctx[0]->cfg.device);
+            if (cudaEventElapsedTime(&ms, g->ev_rs0[set], g->ev_rs1[set]) == cudaSuccess) g->last_nccl_ms += ms;
+        }
+        g->last_pairs += blocks[b].P;
         return cb(user, blocks[b].i0, blocks[b].i1, blocks[b].P, g->h_cnt[set][0], g->h_cnt[set][1], g->h_cnt[set][2]);
     };
     for (size_t b = 0; b < blocks.size(); b++) {
@@ -355,6 +373,8 @@ int pansim_group_all_pairs(pansim_group *g, size_t chunk_pairs, pansim_pairs_cb 
             cudaStreamWaitEvent(g->stream_comm[i], g->ev_compute[i], 0);
         }
         if (ns > 1) {
+            cudaSetDevice(g->ctx[0]->cfg.device);
+            cudaEventRecord(g->ev_rs0[set], g->stream_comm[0]);
             ncclResult_t r = api.GroupStart();
             for (size_t i = 0; i < ns && r == ncclSuccess; i++) {
                 pansim_ctx *c = g->ctx[i];
@@ -362,6 +382,8 @@ int pansim_group_all_pairs(pansim_group *g, size_t chunk_pairs, pansim_pairs_cb 
                 r = api.ReduceScatter(cd, cd + i * slice, slice, ncclUint32, ncclSum, g->comms[i], g->stream_comm[i]);
             }
             const ncclResult_t r2 = api.GroupEnd();
+            cudaSetDevice(g->ctx[0]->cfg.device);
+            cudaEventRecord(g->ev_rs1[set], g->stream_comm[0]);
             if (r == ncclSuccess) r = r2;
             if (r != ncclSuccess) GFAIL(g, PANSIM_ERR_CUDA, "ncclReduceScatter of the all-pairs counts failed: %s", api.GetErrorString(r));
         }
@@ -383,7 +405,20 @@ int pansim_group_all_pairs(pansim_group *g, size_t chunk_pairs, pansim_pairs_cb 
             if (int rc = deliver(b - 1)) return rc;
     }
     if (int rc = deliver(blocks.size() - 1)) return rc;
-    return group_sync_all(g, PANSIM_ERR_WEIGHTS, PANSIM_WEIGHTS_MSG);
+    const int rc_end = group_sync_all(g, PANSIM_ERR_WEIGHTS, PANSIM_WEIGHTS_MSG);
+    g->last_wall_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+    return rc_end;
+}
+
+// wall time of the last pansim_group_all_pairs walk (callbacks included), device time shard 0 spent in the
+// reduce-scatters (they run on the second stream, overlapped with the kernels of the next block), pairs walked
+int pansim_group_all_pairs_timing(pansim_group *g, float *wall_ms, float *nccl_ms, uint64_t *pairs)
+{
+    if (!g) return PANSIM_ERR_INVALID;
+    if (wall_ms) *wall_ms = g->last_wall_ms;
+    if (nccl_ms) *nccl_ms = g->last_nccl_ms;
+    if (pairs) *pairs = g->last_pairs;
+    return 0;
 }
 
 // ---- replicated / assembled state ------------------------------------------------------------

@@ -4,6 +4,7 @@
 #include "../../include/pansim_b200.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -211,6 +212,11 @@ struct pansim_ctx {
     size_t cnt2_cap = 0;
     double *d_stats = nullptr, *h_stats = nullptr;       // per-generation statistics (4 doubles each), device / pinned
     size_t stats_cap = 0;
+    // the stream the distance pass runs on: c->stream, except inside the --print_dist batch where the pass of
+    // generation g runs on stream_pairs beside the selection chain and the core step of generation g+1
+    cudaStream_t ps = nullptr, stream_pairs = nullptr;
+    cudaEvent_t ev_acc_done = nullptr, ev_mat = nullptr;
+    bool ev_pairs_valid[2] = {false, false};
     cudaStream_t stream_stats2[2] = {nullptr, nullptr};   // statistics kernels of consecutive generations run side by side
     cudaEvent_t ev_pairs[2] = {nullptr, nullptr}, ev_stats[2] = {nullptr, nullptr};
     bool ev_stats_valid[2] = {false, false};
@@ -257,6 +263,30 @@ struct pansim_ctx {
     cudaEvent_t t_begin = nullptr, t_end = nullptr;
     uint32_t launches = 0;
 
+    // CUDA graphs of the selection chain (competition, fitness, parent draw, accessory step) of ONE generation
+    // for the device-resident batches: six phases (three parents buffers x two accessory buffers), one
+    // executable graph each. The core kernel stays an ordinary launch on its own low-priority stream.
+    bool use_graph = true;               // PANSIM_GRAPH=0: every kernel of the chain is launched on its own
+    bool graph_spans = true;             // PANSIM_GRAPH_SPANS=0: no event-record nodes (kernel-group timing) inside the graphs
+    bool chain_graph_now = false;        // set by the batch entry points
+    bool capturing = false;
+    const uint32_t *gen_dev_now = nullptr;   // while capturing: kernels take the generation as args.gen + *gen_dev
+    uint32_t *d_gen_base = nullptr;
+    uint32_t gen_base_host = 0xFFFFFFFFu;    // value d_gen_base will hold when the work enqueued so far has run
+    struct GraphKey { int parents_idx, acc_cur, fitness_mode; bool competition, timing, neutral, fitness_valid, fitness_blocked; };
+    struct GraphEntry {
+        GraphKey key{};
+        cudaGraphExec_t exec = nullptr;
+        EventPool pool;                  // events referenced by the graph's record nodes (never recycled)
+        std::vector<Span> spans;
+        uint32_t kernels = 0;            // kernel launches captured
+        uint32_t used = 0;               // launches in the current timed call (scales the spans in pansim_get_timing)
+        int acc_cur_after = 0;           // host-side state the captured calls leave behind
+        bool fitness_valid_after = false;
+    };
+    std::vector<GraphEntry *> graphs;
+    GraphEntry *cap = nullptr;           // entry being captured
+
     uint32_t core_grid = 0, core_items_per_warp = 1;
     uint32_t core_items_batch = 0;        // items per warp in the device-resident batch (0 = same as core_items_per_warp)
     size_t core_smem = 0;
@@ -297,19 +327,32 @@ struct ScopedSpan {
     int group;
     cudaStream_t st;
     cudaEvent_t a = nullptr;
+    bool on = false;
     ScopedSpan(pansim_ctx *ctx, int g, cudaStream_t stream = nullptr) : c(ctx), group(g), st(stream ? stream : ctx->stream)
     {
-        if (c->timing_enabled) {
-            a = c->pool.get();
-            cudaEventRecord(a, st);
+        on = c->timing_enabled && !(c->capturing && !c->graph_spans);
+        if (on) {
+            if (c->capturing) {         // an event-record NODE of the graph: it holds the time of the last replay
+                a = c->cap->pool.get();
+                cudaEventRecordWithFlags(a, st, cudaEventRecordExternal);
+            } else {
+                a = c->pool.get();
+                cudaEventRecord(a, st);
+            }
         }
     }
     ~ScopedSpan()
     {
-        if (c->timing_enabled) {
-            cudaEvent_t b = c->pool.get();
-            cudaEventRecord(b, st);
-            c->spans.push_back({a, b, group});
+        if (on) {
+            if (c->capturing) {
+                cudaEvent_t b = c->cap->pool.get();
+                cudaEventRecordWithFlags(b, st, cudaEventRecordExternal);
+                c->cap->spans.push_back({a, b, group});
+            } else {
+                cudaEvent_t b = c->pool.get();
+                cudaEventRecord(b, st);
+                c->spans.push_back({a, b, group});
+            }
         }
     }
 };
@@ -346,6 +389,7 @@ void timing_begin(pansim_ctx *c)
     c->launches = 0;
     c->spans.clear();
     c->pool.reset();
+    for (auto *e : c->graphs) e->used = 0;
     if (c->timing_enabled) {
         c->t_begin = c->pool.get();
         cudaEventRecord(c->t_begin, c->stream);
@@ -421,7 +465,7 @@ int check_device_flag(pansim_ctx *c, int code, const char *what)
 int comm_allreduce_counts(pansim_ctx *c, uint32_t *d_counts, size_t n)
 {
     if (!c->comm || c->comm_size < 2 || !d_counts || !n) return 0;
-    NCK(c, nccl_api().AllReduce(d_counts, d_counts, n, ncclUint32, ncclSum, c->comm, c->stream));
+    NCK(c, nccl_api().AllReduce(d_counts, d_counts, n, ncclUint32, ncclSum, c->comm, c->ps));
     c->launches++;
     timing_end(c);          // the collective belongs to the pass it completes (total_ms of pansim_get_timing)
     return 0;
@@ -511,6 +555,7 @@ int launch_select(pansim_ctx *c, uint32_t gen, bool use_avgdist)
     a.competition_strength = c->cfg.competition_strength;
     a.key = make_uint2((uint32_t)c->cfg.seed, (uint32_t)(c->cfg.seed >> 32));
     a.gen = gen;
+    a.gen_dev = c->gen_dev_now;
     a.tmp_a = c->d_tmp_a;
     a.tmp_b = c->d_tmp_b;
     a.weights = c->d_weights;
@@ -541,6 +586,7 @@ void fill_acc_args(pansim_ctx *c, AccArgs &a, uint32_t gen)
     a.stride_words = c->acc_stride_words;
     a.key = make_uint2((uint32_t)c->cfg.seed, (uint32_t)(c->cfg.seed >> 32));
     a.gen = gen;
+    a.gen_dev = c->gen_dev_now;
     if (c->cfg.n_compartments > 0) { a.lo0 = c->cfg.comp_lo[0]; a.hi0 = c->cfg.comp_hi[0]; }
     if (c->cfg.n_compartments > 1) { a.lo1 = c->cfg.comp_lo[1]; a.hi1 = c->cfg.comp_hi[1]; }
     a.flip_thr0 = c->flip_thr[0]; a.flip_thr1 = c->flip_thr[1];
@@ -607,6 +653,7 @@ void fill_core_args(pansim_ctx *c, CoreMutArgs &a, uint32_t gen)
     a.key = make_uint2((uint32_t)c->cfg.seed, (uint32_t)(c->cfg.seed >> 32));
     a.rk = philox_key_schedule(a.key);
     a.gen = gen;
+    a.gen_dev = c->gen_dev_now;
     a.const_img = c->d_core_img; a.mut_size = c->tab_mut.size; a.mut_nsub = c->tab_mut.nsub; a.mut_kmax = c->tab_mut.kmax;
     a.hr_size = c->tab_hr.size;
     a.hr_lemire_t = c->N > 1 ? (uint32_t)((1ull << 32) % (c->N - 1)) : 0u; a.hr_kmax = c->tab_hr.kmax; a.hr_gen = c->hr_pending_gen;
@@ -683,6 +730,7 @@ int core_materialize(pansim_ctx *c, cudaStream_t st)
 {
     if (st == c->stream)
         if (int rc = ensure_core_joined(c)) return rc;
+    if (st == c->stream_pairs && c->core_unjoined) CU(c, cudaStreamWaitEvent(st, c->ev_core_last, 0));   // c->stream stays unjoined
     if (!c->hr_pending) return 0;
     ScopedSpan sp(c, TG_CORE_HR, st);
     if (int rc = launch_core_hr(c, c->hr_pending_gen, c->core[c->core_cur], st)) return rc;
@@ -746,7 +794,8 @@ int next_parents_buffer(pansim_ctx *c)
 
 // accessory step on the chain stream, fused core step on the core stream; both
 // read the current parents buffer, which must have been produced on c->stream.
-int launch_population_steps(pansim_ctx *c, uint32_t gen)
+// the core step of generation `gen` on the core stream, behind the parents of the current slot
+int launch_core_part(pansim_ctx *c, uint32_t gen)
 {
     const int i = c->parents_idx;
     CU(c, cudaEventRecord(c->ev_parents[i], c->stream));
@@ -759,6 +808,12 @@ int launch_population_steps(pansim_ctx *c, uint32_t gen)
     CU(c, cudaEventRecord(c->ev_core_last, c->stream_core));
     c->core_done_valid[i] = true;
     c->core_unjoined = true;
+    return 0;
+}
+
+int launch_population_steps(pansim_ctx *c, uint32_t gen)
+{
+    if (int rc = launch_core_part(c, gen)) return rc;
     {
         ScopedSpan s(c, TG_ACC);
         if (int rc = launch_acc_step(c, gen)) return rc;
@@ -769,19 +824,108 @@ int launch_population_steps(pansim_ctx *c, uint32_t gen)
 // after a batch of generations: later work on c->stream must see the core state
 int join_core_stream(pansim_ctx *c) { return ensure_core_joined(c); }
 
+// the selection chain of one generation: competition (if any) -> fitness -> parents
+int launch_chain_select(pansim_ctx *c, uint32_t gen)
+{
+    ScopedSpan s(c, TG_SELECT);
+    bool use_avg = false;
+    if (c->cfg.competition_strength > 0.0) {          // main.rs:438-440
+        if (int rc = launch_competition(c)) return rc;
+        use_avg = true;
+    }
+    return launch_select(c, gen, use_avg);
+}
+
+__global__ void gen_base_add_kernel(uint32_t *gen_base, uint32_t n) { *gen_base += n; }
+
+// Selection chain + accessory step of generation `gen` as one graph launch on c->stream. The graph of the
+// current phase (parents slot, accessory buffer, ...) is captured on first use from the very calls the
+// launch-by-launch path makes; the fitness kernel's side stream enters the capture through its fork event
+// and is joined before the parent draw. Generation numbers inside are relative to the device word
+// d_gen_base, which the last node advances by one, so a phase's graph serves every generation of that phase.
+int chain_graph_step(pansim_ctx *c, uint32_t gen)
+{
+    if (!c->d_gen_base) {
+        CU(c, cudaMalloc(&c->d_gen_base, sizeof(uint32_t)));
+        CU(c, cudaMemsetAsync(c->d_gen_base, 0xFF, sizeof(uint32_t), c->stream));
+    }
+    if (int rc = join_fitness(c)) return rc;                    // nothing uncaptured may be waited for inside a capture
+    if (c->cfg.competition_strength > 0.0 && !c->d_inter) CU(c, cudaMalloc(&c->d_inter, (size_t)c->N * c->N * sizeof(uint32_t)));
+    pansim_ctx::GraphKey key;
+    memset(&key, 0, sizeof key);
+    key.parents_idx = c->parents_idx; key.acc_cur = c->acc_cur; key.fitness_mode = c->fitness_mode;
+    key.competition = c->cfg.competition_strength > 0.0; key.timing = c->timing_enabled && c->graph_spans; key.neutral = c->neutral;
+    key.fitness_valid = c->fitness_valid; key.fitness_blocked = c->fitness_blocked;
+    pansim_ctx::GraphEntry *ge = nullptr;
+    for (auto *e : c->graphs)
+        if (memcmp(&e->key, &key, sizeof key) == 0) ge = e;
+    // the generation the graph's kernels add their relative 0 to
+    if (c->gen_base_host != gen) {
+        CU(c, cudaMemcpyAsync(c->d_gen_base, &gen, sizeof gen, cudaMemcpyHostToDevice, c->stream));      // pageable source: staged before the call returns
+        c->gen_base_host = gen;
+    }
+    if (!ge) {
+        ge = new pansim_ctx::GraphEntry();
+        ge->key = key;
+        const uint32_t launches0 = c->launches;
+        CU(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        c->capturing = true;
+        c->cap = ge;
+        c->gen_dev_now = c->d_gen_base;
+        int rc = launch_chain_select(c, 0u);
+        if (!rc) {
+            ScopedSpan s(c, TG_ACC);
+            rc = launch_acc_step(c, 0u);
+        }
+        if (!rc) rc = join_fitness(c);
+        if (!rc) {
+            gen_base_add_kernel<<<1, 1, 0, c->stream>>>(c->d_gen_base, 1u);
+            if (cudaGetLastError() != cudaSuccess) rc = PANSIM_ERR_CUDA;
+        }
+        c->capturing = false;
+        c->cap = nullptr;
+        c->gen_dev_now = nullptr;
+        ge->kernels = c->launches - launches0 + 1u;
+        c->launches = launches0;
+        ge->acc_cur_after = c->acc_cur;
+        ge->fitness_valid_after = c->fitness_valid;
+        cudaGraph_t graph = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+        c->fitness_join_pending = false;                        // ev_join is a captured event now
+        cudaError_t ei = cudaSuccess;
+        if (!rc && e == cudaSuccess && graph) ei = cudaGraphInstantiate(&ge->exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (rc || e != cudaSuccess || ei != cudaSuccess || !ge->exec) {
+            cudaGetLastError();
+            ge->pool.destroy();
+            delete ge;
+            if (rc) return rc;
+            FAIL(c, PANSIM_ERR_CUDA, "CUDA graph capture of the selection chain failed: %s", cudaGetErrorString(e != cudaSuccess ? e : ei));
+        }
+        c->graphs.push_back(ge);
+    } else {
+        // what the captured calls do to the host-side state
+        c->acc_cur = ge->acc_cur_after;
+        c->fitness_valid = ge->fitness_valid_after;
+        c->avgdist_valid = key.competition;
+    }
+    CU(c, cudaGraphLaunch(ge->exec, c->stream));
+    c->launches += ge->kernels;
+    ge->used++;
+    c->gen_base_host = gen + 1u;
+    return 0;
+}
+
 int step_device(pansim_ctx *c, uint32_t gen)
 {
     if (int rc = next_parents_buffer(c)) return rc;
-    {
-        ScopedSpan s(c, TG_SELECT);
-        bool use_avg = false;
-        if (c->cfg.competition_strength > 0.0) {          // main.rs:438-440
-            if (int rc = launch_competition(c)) return rc;
-            use_avg = true;
-        }
-        if (int rc = launch_select(c, gen, use_avg)) return rc;
+    if (c->chain_graph_now && !c->capturing) {
+        if (int rc = chain_graph_step(c, gen)) return rc;       // parents + accessory step of this generation
+        if (int rc = launch_core_part(c, gen)) return rc;
+    } else {
+        if (int rc = launch_chain_select(c, gen)) return rc;
+        if (int rc = launch_population_steps(c, gen)) return rc;
     }
-    if (int rc = launch_population_steps(c, gen)) return rc;
     c->avgdist_valid = false;
     return 0;
 }
@@ -833,6 +977,12 @@ void pansim_destroy(pansim_ctx *c)
                     c->d_hr_value, c->d_dump_flip, c->d_dump_gain};
     for (void *p : ptrs)
         if (p) cudaFree(p);
+    for (auto *e : c->graphs) {
+        if (e->exec) cudaGraphExecDestroy(e->exec);
+        e->pool.destroy();
+        delete e;
+    }
+    if (c->d_gen_base) cudaFree(c->d_gen_base);
     if (c->h_parents) cudaFreeHost(c->h_parents);
     for (int i = 0; i < 3; i++) {
         if (c->h_parents_up[i]) cudaFreeHost(c->h_parents_up[i]);
@@ -847,6 +997,9 @@ void pansim_destroy(pansim_ctx *c)
         if (c->ev_stats[i]) cudaEventDestroy(c->ev_stats[i]);
     }
     for (auto st : c->stream_stats2) if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
+    if (c->stream_pairs) { cudaStreamSynchronize(c->stream_pairs); cudaStreamDestroy(c->stream_pairs); }
+    if (c->ev_acc_done) cudaEventDestroy(c->ev_acc_done);
+    if (c->ev_mat) cudaEventDestroy(c->ev_mat);
     if (c->h_err) cudaFreeHost(c->h_err);
     c->pool.destroy();
     for (int i = 0; i < 3; i++) {
@@ -914,6 +1067,7 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
             CU(c, cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, hi));
             CU(c, cudaStreamCreateWithPriority(&c->stream_core, cudaStreamNonBlocking, lo));
             CU(c, cudaStreamCreateWithPriority(&c->stream_aux, cudaStreamNonBlocking, hi));
+            c->ps = c->stream;
             CU(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
             CU(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
         }
@@ -986,6 +1140,8 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
         if (const char *e = getenv("PANSIM_FITNESS_BLOCKED")) c->fitness_blocked = atoi(e) != 0;
         if (const char *e = getenv("PANSIM_INTER_POPC")) c->inter_popc = atoi(e) != 0;
         if (const char *e = getenv("PANSIM_TILES2")) c->use_tiles2 = atoi(e) != 0;
+        if (const char *e = getenv("PANSIM_GRAPH")) c->use_graph = atoi(e) != 0;
+        if (const char *e = getenv("PANSIM_GRAPH_SPANS")) c->graph_spans = atoi(e) != 0;
         if (const char *e = getenv("PANSIM_FINE_TIMING")) c->fine_timing = atoi(e) != 0;
         if (const char *e = getenv("PANSIM_PDL")) c->use_pdl = atoi(e);
         if (c->tab_hr.nsub && core_bytes) {
@@ -1130,6 +1286,13 @@ int pansim_get_timing(pansim_ctx *c, pansim_timing *o)
         CU(c, cudaEventElapsedTime(&ms, s.a, s.b));
         g[s.group] += ms;
     }
+    for (auto *e : c->graphs)       // the record nodes of a graph hold the times of its LAST launch: scaled to its launches in this call
+        if (e->used)
+            for (auto &s : e->spans) {
+                float ms = 0;
+                if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) g[s.group] += ms * (float)e->used;
+                else cudaGetLastError();
+            }
     if (c->fine_timing)
         fprintf(stderr, "[pansim fine timing, ms over the batch] inter(+fitness join) %.4f avg %.4f select %.4f flip %.4f gain %.4f hgt %.4f | groups: select %.4f acc %.4f core %.4f\n",
                 g[TG_D_INTER], g[TG_D_AVG], g[TG_D_SEL], g[TG_D_FLIP], g[TG_D_GAIN], g[TG_D_HGT], g[TG_SELECT], g[TG_ACC], g[TG_CORE]);
@@ -1442,17 +1605,24 @@ int pansim_step(pansim_ctx *c, uint32_t gen) { return pansim_run_generations(c, 
 
 #define PANSIM_WEIGHTS_MSG "WeightedIndex::new would fail: a weight is negative/NaN or the total is not positive (population.rs:440)"
 
-// enqueue n generations (asynchronous); the caller synchronises and inspects the device flags
+// enqueue n generations (asynchronous); the caller synchronises and inspects the device flags.
+// The selection chain of every generation is ONE graph launch (chain_graph_step), so the host issues
+// about ten calls per generation instead of twenty-five: with eight ranks on one host that enqueue path,
+// not the GPUs, was what limited the step.
 static int run_generations_enqueue(pansim_ctx *c, uint32_t gen0, uint32_t n)
 {
     if (int rc = require_state(c)) return rc;
     CU(c, cudaSetDevice(c->cfg.device));
     if (c->dump_enabled) CU(c, cudaMemsetAsync(c->d_dump_counters, 0, 2 * sizeof(uint32_t), c->stream));
     c->pdl_now = false;
+    c->ps = c->stream;
     timing_begin(c);
-    for (uint32_t g = 0; g < n; g++)
-        if (int rc = step_device(c, gen0 + g)) return rc;
-    if (int rc = join_core_stream(c)) return rc;
+    c->chain_graph_now = c->use_graph && !c->dump_enabled && !c->fine_timing && n >= 8;
+    int rc = 0;
+    for (uint32_t g = 0; g < n && !rc; g++) rc = step_device(c, gen0 + g);
+    c->chain_graph_now = false;
+    if (rc) return rc;
+    if (int rc2 = join_core_stream(c)) return rc2;
     timing_end(c);
     return 0;
 }
@@ -1628,7 +1798,7 @@ static int ensure_planes(pansim_ctx *c)
     if (c->planes_version != c->core_version) {
         const uint64_t n_vec4 = core_bytes / 16;
         const uint32_t grid = (uint32_t)std::min<uint64_t>((n_vec4 + 255) / 256, (uint64_t)c->sm_count * 32);
-        core_planes_kernel<<<grid, 256, 0, c->stream>>>(reinterpret_cast<const uint4 *>(c->core[c->core_cur]),
+        core_planes_kernel<<<grid, 256, 0, c->ps>>>(reinterpret_cast<const uint4 *>(c->core[c->core_cur]),
                                                         reinterpret_cast<uint4 *>(c->d_planes), n_vec4);
         LAUNCH_CHECK(c);
         c->planes_version = c->core_version;
@@ -1786,18 +1956,18 @@ static int launch_pair_core(pansim_ctx *c, uint32_t *d_cd, size_t P, uint32_t ro
     uint32_t chunk_vec4 = (uint32_t)(chunk_bytes / 16);
     uint32_t n_chunks = (row_vec4 + chunk_vec4 - 1) / chunk_vec4;
     if (n_chunks > 65535) { n_chunks = 65535; chunk_vec4 = (row_vec4 + n_chunks - 1) / n_chunks; chunk_vec4 = ((chunk_vec4 + 255) / 256) * 256; n_chunks = (row_vec4 + chunk_vec4 - 1) / chunk_vec4; }
-    if (clear) CU(c, cudaMemsetAsync(d_cd, 0, P * 4, c->stream));      // both kernels accumulate with integer atomics
+    if (clear) CU(c, cudaMemsetAsync(d_cd, 0, P * 4, c->ps));      // both kernels accumulate with integer atomics
     if (c->plan_batches) {
         if (!c->planes_tmap_ok) FAIL(c, PANSIM_ERR_CUDA, "no TMA descriptor for the plane rows (cuTensorMapEncodeTiled unavailable)");
-        CU(c, cudaMemsetAsync(c->d_work_counter, 0, sizeof(uint32_t), c->stream));
+        CU(c, cudaMemsetAsync(c->d_work_counter, 0, sizeof(uint32_t), c->ps));
         const uint32_t grid = (uint32_t)std::min<size_t>(c->plan_batches, (size_t)c->sm_count);
-        pair_tile2_kernel<<<grid, T2_THREADS, tile2_smem_bytes(), c->stream>>>(
+        pair_tile2_kernel<<<grid, T2_THREADS, tile2_smem_bytes(), c->ps>>>(
             c->planes_tmap, c->d_batches, (uint32_t)c->plan_batches, c->d_work_counter, c->d_tile_slots, c->d_tile_orig, d_cd);
         LAUNCH_CHECK(c);
     }
     if (c->plan_groups) {
         const uint32_t gx = (uint32_t)std::min<size_t>(c->plan_groups, 1u << 20);
-        pair_planes_grouped_kernel<<<dim3(gx, n_chunks), PAIR_THREADS, 0, c->stream>>>(
+        pair_planes_grouped_kernel<<<dim3(gx, n_chunks), PAIR_THREADS, 0, c->ps>>>(
             c->d_planes, c->core_stride, chunk_vec4, row_vec4, c->d_groups, (uint32_t)c->plan_groups,
             c->d_partner, c->d_orig, d_cd);
         LAUNCH_CHECK(c);
@@ -1834,19 +2004,19 @@ static int pair_prepare(pansim_ctx *c, const uint32_t *r1, const uint32_t *r2, s
 static int pair_launch(pansim_ctx *c, size_t P, uint32_t *d_cd, uint32_t *d_in, uint32_t *d_un)
 {
     if (d_cd && c->Ll)
-        if (int rc = core_materialize(c, c->stream)) return rc;     // recombination events still pending on the rows
+        if (int rc = core_materialize(c, c->ps)) return rc;     // recombination events still pending on the rows
     if (d_cd) {
-        ScopedSpan s(c, TG_PAIR_CORE);
+        ScopedSpan s(c, TG_PAIR_CORE, c->ps);
         if (c->Ll == 0) {
-            CU(c, cudaMemsetAsync(d_cd, 0, P * 4, c->stream));
+            CU(c, cudaMemsetAsync(d_cd, 0, P * 4, c->ps));
         } else {
             if (int rc = launch_pair_core(c, d_cd, P, c->N, true)) return rc;
         }
     }
     if (d_in || d_un) {
-        ScopedSpan s(c, TG_PAIR_ACC);
+        ScopedSpan s(c, TG_PAIR_ACC, c->ps);
         const uint32_t grid = (uint32_t)std::min<size_t>((P + 7) / 8, (size_t)c->sm_count * 16);
-        pair_acc_kernel<<<grid ? grid : 1, 256, 0, c->stream>>>(c->acc[c->acc_cur], c->acc_stride_words, c->acc_words, c->d_r1, c->d_r2, (uint32_t)P, d_in, d_un);
+        pair_acc_kernel<<<grid ? grid : 1, 256, 0, c->ps>>>(c->acc[c->acc_cur], c->acc_stride_words, c->acc_words, c->d_r1, c->d_r2, (uint32_t)P, d_in, d_un);
         LAUNCH_CHECK(c);
     }
     return 0;
@@ -1855,6 +2025,7 @@ static int pair_launch(pansim_ctx *c, size_t P, uint32_t *d_cd, uint32_t *d_in, 
 static int pair_counts_impl(pansim_ctx *c, const uint32_t *r1, const uint32_t *r2, size_t P, uint32_t *d_cd,
                             uint32_t *d_in, uint32_t *d_un)
 {
+    c->ps = c->stream;
     if (int rc = pair_prepare(c, r1, r2, P)) return rc;
     timing_begin(c);
     if (int rc = pair_launch(c, P, d_cd, d_in, d_un)) return rc;
@@ -1902,6 +2073,9 @@ static int ensure_stats(pansim_ctx *c, size_t n_gen, size_t P, bool second_count
     if (!c->stream_stats2[0]) {
         int lo = 0, hi = 0;
         CU(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(c, cudaStreamCreateWithPriority(&c->stream_pairs, cudaStreamNonBlocking, lo));
+        CU(c, cudaEventCreateWithFlags(&c->ev_acc_done, cudaEventDisableTiming));
+        CU(c, cudaEventCreateWithFlags(&c->ev_mat, cudaEventDisableTiming));
         for (int i = 0; i < 2; i++) {
             CU(c, cudaStreamCreateWithPriority(&c->stream_stats2[i], cudaStreamNonBlocking, hi));
             CU(c, cudaEventCreateWithFlags(&c->ev_pairs[i], cudaEventDisableTiming));
@@ -1930,7 +2104,8 @@ static int ensure_stats(pansim_ctx *c, size_t n_gen, size_t P, bool second_count
 static int launch_pair_stats(pansim_ctx *c, int slot, size_t P, const uint32_t *d_cd, const uint32_t *d_in, const uint32_t *d_un,
                              double *d_out)
 {
-    CU(c, cudaEventRecord(c->ev_pairs[slot], c->stream));
+    CU(c, cudaEventRecord(c->ev_pairs[slot], c->ps));
+    c->ev_pairs_valid[slot] = true;
     cudaStream_t st = c->stream_stats2[slot];
     CU(c, cudaStreamWaitEvent(st, c->ev_pairs[slot], 0));
     PairStatsArgs a;
@@ -1949,6 +2124,53 @@ static int launch_pair_stats(pansim_ctx *c, int slot, size_t P, const uint32_t *
 static int require_whole_alignment(pansim_ctx *c, const char *what)
 {
     if (c->Ll != c->L && !c->comm) FAIL(c, PANSIM_ERR_STATE, "%s on a column shard needs a communicator (pansim_comm_init_rank): core counts are partial", what);
+    return 0;
+}
+
+// One generation of the --print_dist batch on one context. The generation step goes to its usual
+// streams; the distance pass of this generation goes to stream_pairs, so it runs beside the selection
+// chain and the core step of the NEXT generation instead of in front of them:
+//   pass(g) starts after core step g and accessory step g; it first materialises the recombination
+//   events of g in the current core buffer (core step g+1 waits for that and applies nothing itself);
+//   accessory step g+2 recycles the buffer pass(g) reads, so generation g+2 waits for pass(g) -- which
+//   is also the back-pressure that keeps the steps at most two generations ahead of the passes;
+//   the count vectors alternate between two sets (the statistics kernel of g reads set g & 1).
+static int stats_generation(pansim_ctx *c, uint32_t gen, int slot, size_t P, bool want_acc, uint32_t **cd_out, uint32_t **in_out,
+                            uint32_t **un_out)
+{
+    c->pdl_now = false;
+    c->ps = c->stream;
+    if (c->ev_pairs_valid[slot]) CU(c, cudaStreamWaitEvent(c->stream, c->ev_pairs[slot], 0));          // pass(g-2) done
+    c->chain_graph_now = c->use_graph && !c->dump_enabled && !c->fine_timing;
+    const int rc_step = step_device(c, gen);
+    c->chain_graph_now = false;
+    if (rc_step) return rc_step;
+    cudaStream_t sp = c->stream_pairs;
+    CU(c, cudaEventRecord(c->ev_acc_done, c->stream));
+    CU(c, cudaStreamWaitEvent(sp, c->ev_acc_done, 0));
+    if (c->ev_stats_valid[slot]) CU(c, cudaStreamWaitEvent(sp, c->ev_stats[slot], 0));               // statistics(g-2) have read this set
+    c->ps = sp;
+    uint32_t *cd = slot ? c->d_cnt2[0] : c->d_cd, *in = slot ? c->d_cnt2[1] : c->d_in, *un = slot ? c->d_cnt2[2] : c->d_un;
+    if (c->Ll) {
+        if (int rc = core_materialize(c, sp)) { c->ps = c->stream; return rc; }
+        CU(c, cudaEventRecord(c->ev_mat, sp));
+        CU(c, cudaStreamWaitEvent(c->stream_core, c->ev_mat, 0));       // the next core step reads the materialised rows
+    }
+    const int rc = pair_launch(c, P, cd, want_acc ? in : nullptr, want_acc ? un : nullptr);
+    if (rc) { c->ps = c->stream; return rc; }
+    *cd_out = cd; *in_out = in; *un_out = un;
+    return 0;        // c->ps stays on stream_pairs: the caller's all-reduce and statistics launch follow the pass
+}
+
+// after the last generation: c->stream joins the core stream, the passes and the statistics
+static int stats_batch_end(pansim_ctx *c)
+{
+    c->ps = c->stream;
+    if (int rc = join_core_stream(c)) return rc;
+    for (int i = 0; i < 2; i++) {
+        if (c->ev_pairs_valid[i]) CU(c, cudaStreamWaitEvent(c->stream, c->ev_pairs[i], 0));
+        if (c->ev_stats_valid[i]) CU(c, cudaStreamWaitEvent(c->stream, c->ev_stats[i], 0));
+    }
     return 0;
 }
 
@@ -1985,22 +2207,14 @@ int pansim_run_generations_stats(pansim_ctx *c, uint32_t gen0, uint32_t n, const
     if (int rc = ensure_stats(c, n, P, true)) return rc;
     if (int rc = pair_prepare(c, r1, r2, P)) return rc;
     if (c->dump_enabled) CU(c, cudaMemsetAsync(c->d_dump_counters, 0, 2 * sizeof(uint32_t), c->stream));
-    c->pdl_now = false;
     timing_begin(c);
     for (uint32_t g = 0; g < n; g++) {
-        if (int rc = step_device(c, gen0 + g)) return rc;
-        const int slot = (int)(g & 1u);
-        uint32_t *cd = slot ? c->d_cnt2[0] : c->d_cd, *in = slot ? c->d_cnt2[1] : c->d_in, *un = slot ? c->d_cnt2[2] : c->d_un;
-        // the statistics kernel of two generations ago still reads this set of count vectors
-        if (c->ev_stats_valid[slot]) CU(c, cudaStreamWaitEvent(c->stream, c->ev_stats[slot], 0));
-        if (int rc = pair_launch(c, P, cd, in, un)) return rc;
+        uint32_t *cd = nullptr, *in = nullptr, *un = nullptr;
+        if (int rc = stats_generation(c, gen0 + g, (int)(g & 1u), P, true, &cd, &in, &un)) return rc;
         if (int rc = comm_allreduce_counts(c, cd, P)) return rc;
-        if (int rc = launch_pair_stats(c, slot, P, cd, in, un, c->d_stats + (size_t)g * 4)) return rc;
+        if (int rc = launch_pair_stats(c, (int)(g & 1u), P, cd, in, un, c->d_stats + (size_t)g * 4)) return rc;
     }
-    if (int rc = join_core_stream(c)) return rc;
-    // the batch ends when the last statistics are in: c->stream joins both statistics streams
-    for (int i = 0; i < 2; i++)
-        if (c->ev_stats_valid[i]) CU(c, cudaStreamWaitEvent(c->stream, c->ev_stats[i], 0));
+    if (int rc = stats_batch_end(c)) return rc;
     timing_end(c);
     CU(c, cudaMemcpyAsync(c->h_stats, c->d_stats, (size_t)n * 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (int rc = check_device_flag(c, PANSIM_ERR_WEIGHTS, "WeightedIndex::new would fail: a weight is negative/NaN or the total is not positive (population.rs:440)")) return rc;
@@ -2014,6 +2228,7 @@ static int pair_counts_rows_impl(pansim_ctx *c, uint32_t row_begin, uint32_t row
                                  uint32_t *d_un, size_t *n_out)
 {
     if (row_begin > row_end || row_end > c->N) FAIL(c, PANSIM_ERR_INVALID, "row block [%u, %u) out of range", row_begin, row_end);
+    c->ps = c->stream;
     const uint32_t nr = row_end - row_begin;
     std::vector<uint32_t> off(nr + 1, 0);
     uint64_t P = 0;

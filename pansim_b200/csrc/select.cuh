@@ -506,6 +506,7 @@ struct SelectArgs {
     double competition_strength;
     uint2 key;
     uint32_t gen;
+    const uint32_t *gen_dev;      // nullptr, or a device word added to gen (replayed CUDA graphs)
     double *tmp_a, *tmp_b;        // [N] scratch
     double *weights;              // [N] out: final weights (population.rs:389-437)
     double *cumulative;           // [N] out
@@ -623,7 +624,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_parents_small_kernel(const
 #pragma unroll
     for (int k = 0; k < SEL_PER; k++) {
         const uint32_t i = tid + k * SEL_THREADS;
-        const uint4 r = philox4x32_10(make_ctr(i, 0u, a.gen, STREAM_PARENTS), a.key);
+        const uint4 r = philox4x32_10(make_ctr(i, 0u, a.gen + (a.gen_dev ? __ldg(a.gen_dev) : 0u), STREAM_PARENTS), a.key);
         const uint64_t bits = (((uint64_t)r.x << 32) | r.y) >> 11;
         const double u = (double)bits * 0x1.0p-53 * total;
         uint32_t l = 0, h = n - 1;
@@ -741,7 +742,7 @@ __global__ void __launch_bounds__(THREADS) select_parents_kernel(const SelectArg
     }
     // N draws: u ~ U[0,total), index = #cumulative[0..n-1) <= u
     for (uint32_t i = tid; i < n; i += THREADS) {
-        const uint4 r = philox4x32_10(make_ctr(i, 0u, a.gen, STREAM_PARENTS), a.key);
+        const uint4 r = philox4x32_10(make_ctr(i, 0u, a.gen + (a.gen_dev ? __ldg(a.gen_dev) : 0u), STREAM_PARENTS), a.key);
         const uint64_t bits = (((uint64_t)r.x << 32) | r.y) >> 11;
         const double u = (double)bits * 0x1.0p-53 * total;
         uint32_t l = 0, h = n - 1;

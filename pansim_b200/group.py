@@ -92,6 +92,19 @@ class PansimGroup:
         self._check(self._lib.pansim_group_all_pairs(self._h, chunk_pairs, _ffi.PAIRS_CB(cb), None))
         return parts
 
+    def walk_all_pairs(self, chunk_pairs: int = 4_000_000, sink=None) -> dict:
+        """The same walk without keeping the vectors: `sink(i0, i1, core_diff, inter, union)` per block (views,
+        valid during the call) or nothing. Returns wall ms, reduce-scatter device ms on shard 0, pairs."""
+        def cb(_user, i0, i1, n, cd, it, un):
+            if sink is not None:
+                sink(i0, i1, np.ctypeslib.as_array(cd, (n,)), np.ctypeslib.as_array(it, (n,)), np.ctypeslib.as_array(un, (n,)))
+            return 0
+
+        self._check(self._lib.pansim_group_all_pairs(self._h, chunk_pairs, _ffi.PAIRS_CB(cb), None))
+        wall, nccl, pairs = C.c_float(), C.c_float(), C.c_uint64()
+        self._check(self._lib.pansim_group_all_pairs_timing(self._h, C.byref(wall), C.byref(nccl), C.byref(pairs)))
+        return dict(wall_ms=wall.value, nccl_ms_shard0=nccl.value, pairs=pairs.value)
+
     def gene_counts(self) -> np.ndarray:
         out = np.empty(self.G, np.uint32)
         self._check(self._lib.pansim_group_gene_counts(self._h, _ptr(out)))

@@ -952,3 +952,39 @@ def test_selection_weights_for_large_populations(N):
     assert (par == par2).all() and par.max() < N
     # the favoured individuals are drawn more often: mean weight of the drawn parents exceeds the plain mean
     assert w[par].mean() > w.mean()
+
+
+@pytest.mark.parametrize("kw", [
+    dict(pop_size=120, core_size=8192 * 6 + 5, HR_rate=0.5, prop_positive=0.1, competition_strength=0.4),
+    dict(pop_size=64, core_size=30000, HR_rate=0.0),                       # no recombination: nothing pending between generations
+    dict(pop_size=90, core_size=8192 * 3, HR_rate=1.0, core_mu=0.2, pan_genes=100, core_genes=100),   # no accessory genome
+])
+def test_graph_replay_equals_launch_by_launch(monkeypatch, kw):
+    """Device-resident batches launch the selection chain + accessory step of every generation as ONE CUDA
+    graph (six phases of the buffer rotation, relative generation numbers + a device counter the graph
+    advances). States, parents, pair counts and per-generation statistics must equal those of the same
+    batches enqueued kernel by kernel (PANSIM_GRAPH=0), across several calls (graph cache, all phases, a
+    reader between the calls that materialises the pending recombination)."""
+    p = small_params(n_gen=3, **kw)
+    d = pb.derive(p)
+    rng = np.random.default_rng(81)
+    core, acc = random_state(rng, p.pop_size, p.core_size, d.pan_size)
+    sel = rng.normal(0, 0.05, d.pan_size)
+    r1, r2 = sample_pairs(rng, p.pop_size, 200)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("PANSIM_GRAPH", mode)
+        with make(p) as sim:
+            sim.upload(core, acc)
+            sim.set_selection(sel)
+            sim.run_generations(0, 60)
+            a = (sim.download_core(), sim.download_acc(), sim.parents())
+            sim.run_generations(60, 26)              # starts in another phase of the buffer rotation
+            cd = sim.pair_counts(r1, r2)[0]
+            sim.run_generations(86, 25)
+            sim.run_generations(111, 7)              # short batch: launch by launch
+            st = sim.run_generations_stats(118, 9, r1, r2)
+            b = (sim.download_core(), sim.download_acc(), sim.parents())
+            out[mode] = a + (cd, st) + b
+    for x, y in zip(out["0"], out["1"]):
+        assert (x == y).all()
