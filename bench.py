@@ -383,6 +383,17 @@ def main():
     for _ in range(3):
         st1 = sim.pair_stats(r1, r2)                       # d2h 4 f64
     e2e_stats_ms = 1e3 * (time.perf_counter() - t0) / 3
+    # --print_matrices: _core_genome.csv (2 bytes of text per site) expanded on the GPU and streamed through
+    # two pinned chunks; /dev/null as the file takes the disk out of the number (PCIe + the pipeline remain)
+    export = None
+    if world == 1 and rank == 0:
+        sim.write_core_csv("/dev/null")
+        t0 = time.perf_counter()
+        nbytes = sim.write_core_csv("/dev/null")
+        dt = time.perf_counter() - t0
+        export = {"bytes": int(nbytes), "seconds": dt, "GBps": nbytes / dt / 1e9,
+                  "what": "pansim_write_core_csv to /dev/null: text expansion kernel + device-to-host copies of 32 MB pinned chunks, "
+                          "double buffered (population.rs:877-879 builds the same text with to_string + join per element)"}
     clocks = sampler.stop(t_load0, time.time()) if sampler else None
     sim.close()
 
@@ -473,6 +484,8 @@ def main():
                 "path": "pansim_select_parents (average_distance + sample_indices, one read-back) -> pansim_step_with_parents, "
                         "host vectors; the step call returns with the core kernel in flight, each run ends with a device synchronize"},
     }
+    if export is not None:
+        line["export_core_csv"] = export
     if shard_parity is not None:
         line["shard_parity"] = bool(shard_parity)
     if cfg4 is not None:

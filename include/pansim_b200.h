@@ -102,6 +102,9 @@ int pansim_download_acc(pansim_ctx *ctx, uint8_t *acc_out);
 /* `A,C,G,T\n` text rows of _core_genome.csv (population.rs:877-879) expanded on
  * the GPU: out holds rows [row_begin,row_end), each 2*local_sites bytes. */
 int pansim_export_core_csv(pansim_ctx *ctx, uint32_t row_begin, uint32_t row_end, char *out);
+/* the whole _core_genome.csv (population.rs:865-882) written by the library: text expanded on the GPU,
+ * streamed through two pinned host chunks (kernel + copy of chunk k+1 overlap the write of chunk k) */
+int pansim_write_core_csv(pansim_ctx *ctx, const char *path, uint64_t *bytes_out);
 /* selection coefficients s[G] (main.rs:287-319), used as ln(1 + s_j) */
 int pansim_set_selection(pansim_ctx *ctx, const double *s);
 

@@ -24,7 +24,7 @@ EXPORTED = [
     "pansim_core_distance", "pansim_acc_distance", "pansim_gene_counts", "pansim_get_info",
     "pansim_get_timing", "pansim_set_timing", "pansim_enable_event_dump",
     "pansim_fetch_event_dump", "pansim_free_event_dump", "pansim_get_rates",
-    "pansim_select_parents", "pansim_pair_stats", "pansim_run_generations_stats",
+    "pansim_select_parents", "pansim_pair_stats", "pansim_run_generations_stats", "pansim_write_core_csv",
     "pansim_comm_unique_id", "pansim_comm_init_rank", "pansim_comm_info",
     "pansim_group_create", "pansim_group_destroy", "pansim_group_last_error", "pansim_group_size", "pansim_group_ctx",
     "pansim_group_set_initial", "pansim_group_set_selection", "pansim_group_run_generations", "pansim_group_pair_counts",
@@ -165,6 +165,7 @@ def lib():
     sig("pansim_free_event_dump", None, C.POINTER(EventDump))
     sig("pansim_get_rates", cint, vp, vp)
     sig("pansim_select_parents", cint, vp, u32, vp, vp)
+    sig("pansim_write_core_csv", cint, vp, C.c_char_p, C.POINTER(C.c_uint64))
     sig("pansim_pair_stats", cint, vp, vp, vp, sz, vp)
     sig("pansim_run_generations_stats", cint, vp, u32, u32, vp, vp, sz, vp)
     sig("pansim_comm_unique_id", cint, vp)

@@ -234,6 +234,10 @@ struct pansim_ctx {
     uint32_t *d_hvals = nullptr;
     size_t hash_cap = 0;
 
+    // CSV export: two device + two pinned host chunks (double buffering), completion events
+    char *d_csv[2] = {nullptr, nullptr}, *h_csv[2] = {nullptr, nullptr};
+    cudaEvent_t ev_csv[2] = {nullptr, nullptr};
+    size_t csv_cap = 0;
     // staging for upload/download
     uint8_t *d_stage = nullptr;
     size_t stage_cap = 0;
@@ -989,6 +993,11 @@ void pansim_destroy(pansim_ctx *c)
         if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
     }
     if (c->h_avg) cudaFreeHost(c->h_avg);
+    for (int b = 0; b < 2; b++) {
+        if (c->h_csv[b]) cudaFreeHost(c->h_csv[b]);
+        if (c->d_csv[b]) cudaFree(c->d_csv[b]);
+        if (c->ev_csv[b]) cudaEventDestroy(c->ev_csv[b]);
+    }
     if (c->h_stats) cudaFreeHost(c->h_stats);
     if (c->d_stats) cudaFree(c->d_stats);
     for (auto q : c->d_cnt2) if (q) cudaFree(q);
@@ -1398,24 +1407,79 @@ int pansim_download_core(pansim_ctx *c, uint8_t *out)
     return 0;
 }
 
-int pansim_export_core_csv(pansim_ctx *c, uint32_t row_begin, uint32_t row_end, char *out)
+// `A,C,G,T\n` rows of _core_genome.csv (population.rs:877-879), expanded on the GPU and streamed out
+// through two pinned host buffers: while chunk k is handed to `sink` (copied into the caller's buffer,
+// or written to a file), the kernel and the device-to-host copy of chunk k+1 are in flight.
+// sink(chunk_ptr, bytes) returns 0 to go on.
+extern "C++" {
+template <typename Sink>
+static int export_core_csv_stream(pansim_ctx *c, uint32_t row_begin, uint32_t row_end, Sink &&sink)
 {
-    if (!c || !out || row_begin > row_end || row_end > c->N) return PANSIM_ERR_INVALID;
+    if (row_begin > row_end || row_end > c->N) FAIL(c, PANSIM_ERR_INVALID, "rows [%u, %u) out of range", row_begin, row_end);
     CU(c, cudaSetDevice(c->cfg.device));
-    if (c->Ll == 0) return 0;
+    if (c->Ll == 0 || row_begin == row_end) return 0;
     if (int rc = core_materialize(c, c->stream)) return rc;
     if (int rc = check_hr_flag(c)) return rc;
     const size_t row_bytes = 2 * (size_t)c->Ll;
-    uint32_t rows_per = (uint32_t)std::max<uint64_t>(1, (256ull << 20) / row_bytes);
-    if (int rc = ensure_stage(c, (size_t)std::min<uint32_t>(rows_per, std::max(1u, row_end - row_begin)) * row_bytes)) return rc;
-    const uint64_t wpr = (c->Ll + 15) / 16;
-    for (uint32_t r0 = row_begin; r0 < row_end; r0 += rows_per) {
-        const uint32_t nr = std::min(rows_per, row_end - r0);
-        export_core_csv_kernel<<<div_up64((uint64_t)nr * wpr, 256), 256, 0, c->stream>>>(c->core[c->core_cur], c->core_stride, c->Ll, r0, nr, (char *)c->d_stage);
-        LAUNCH_CHECK(c);
-        CU(c, cudaMemcpyAsync(out + (size_t)(r0 - row_begin) * row_bytes, c->d_stage, (size_t)nr * row_bytes, cudaMemcpyDeviceToHost, c->stream));
-        CU(c, cudaStreamSynchronize(c->stream));
+    const size_t chunk_target = 32ull << 20;
+    const uint32_t rows_per = (uint32_t)std::max<size_t>(1, chunk_target / row_bytes);
+    const size_t chunk_bytes = (size_t)std::min<uint32_t>(rows_per, row_end - row_begin) * row_bytes;
+    if (chunk_bytes > c->csv_cap) {
+        for (int b = 0; b < 2; b++) {
+            if (c->h_csv[b]) cudaFreeHost(c->h_csv[b]);
+            if (c->d_csv[b]) cudaFree(c->d_csv[b]);
+            c->h_csv[b] = nullptr; c->d_csv[b] = nullptr;
+        }
+        c->csv_cap = 0;
+        for (int b = 0; b < 2; b++) {
+            if (cudaMallocHost(&c->h_csv[b], chunk_bytes) != cudaSuccess || cudaMalloc(&c->d_csv[b], chunk_bytes) != cudaSuccess)
+                FAIL(c, PANSIM_ERR_NOMEM, "staging buffers of %zu bytes for the CSV export failed", chunk_bytes);
+            if (!c->ev_csv[b]) CU(c, cudaEventCreateWithFlags(&c->ev_csv[b], cudaEventDisableTiming));
+        }
+        c->csv_cap = chunk_bytes;
     }
+    const uint64_t wpr = (c->Ll + 15) / 16;
+    auto enqueue = [&](uint32_t r0, int b) -> int {
+        const uint32_t nr = std::min(rows_per, row_end - r0);
+        export_core_csv_kernel<<<div_up64((uint64_t)nr * wpr, 256), 256, 0, c->stream>>>(c->core[c->core_cur], c->core_stride, c->Ll, r0, nr, c->d_csv[b]);
+        LAUNCH_CHECK(c);
+        CU(c, cudaMemcpyAsync(c->h_csv[b], c->d_csv[b], (size_t)nr * row_bytes, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaEventRecord(c->ev_csv[b], c->stream));
+        return 0;
+    };
+    int b = 0;
+    if (int rc = enqueue(row_begin, 0)) return rc;
+    for (uint32_t r0 = row_begin; r0 < row_end; r0 += rows_per, b ^= 1) {
+        const uint32_t nr = std::min(rows_per, row_end - r0);
+        if (r0 + rows_per < row_end)
+            if (int rc = enqueue(r0 + rows_per, b ^ 1)) return rc;         // next chunk in flight while this one is consumed
+        CU(c, cudaEventSynchronize(c->ev_csv[b]));
+        if (sink(c->h_csv[b], (size_t)nr * row_bytes)) FAIL(c, PANSIM_ERR_INVALID, "CSV export: the sink failed (short write?)");
+    }
+    return 0;
+}
+}  // extern "C++"
+
+int pansim_export_core_csv(pansim_ctx *c, uint32_t row_begin, uint32_t row_end, char *out)
+{
+    if (!c || !out) return PANSIM_ERR_INVALID;
+    char *dst = out;
+    return export_core_csv_stream(c, row_begin, row_end, [&](const char *p, size_t n) { memcpy(dst, p, n); dst += n; return 0; });
+}
+
+// _core_genome.csv of population.rs:865-882 written by the library itself: the pinned chunks go
+// straight to the file, no second host copy. bytes_out (may be NULL) = bytes written.
+int pansim_write_core_csv(pansim_ctx *c, const char *path, uint64_t *bytes_out)
+{
+    if (!c || !path) return PANSIM_ERR_INVALID;
+    FILE *f = fopen(path, "wb");
+    if (!f) FAIL(c, PANSIM_ERR_INVALID, "cannot create %s", path);
+    uint64_t total = 0;
+    const int rc = export_core_csv_stream(c, 0, c->N, [&](const char *p, size_t n) { total += n; return fwrite(p, 1, n, f) == n ? 0 : 1; });
+    const int rc2 = fclose(f);
+    if (bytes_out) *bytes_out = total;
+    if (rc) return rc;
+    if (rc2) FAIL(c, PANSIM_ERR_INVALID, "closing %s failed", path);
     return 0;
 }
 

@@ -93,7 +93,7 @@ void pansim::Populations::write(const std::string &outpref)
         std::vector<char> buf((size_t)step * 2 * L);
         for (uint32_t r0 = 0; r0 < N; r0 += step) {
             const uint32_t r1 = (uint32_t)std::min<size_t>(N, r0 + step);
-            gcheck(pansim_group_export_core_csv(grp_, r0, r1, buf.data()));
+            gcheck(pansim_group_export_core_csv(grp_, r0, r1, buf.data()));   // one GPU: pinned double-buffered stream (pansim_export_core_csv)
             f.write(buf.data(), (std::streamsize)((size_t)(r1 - r0) * 2 * L));
         }
     }

@@ -413,11 +413,14 @@ class Pansim:
         return out
 
     # -- writers (population.rs:865-897) ------------------------------------
+    def write_core_csv(self, path: str) -> int:
+        """_core_genome.csv written by the library (GPU text expansion, pinned double-buffered streaming); bytes written."""
+        n = C.c_uint64(0)
+        self._check(self._lib.pansim_write_core_csv(self._h, path.encode(), C.byref(n)))
+        return n.value
+
     def write(self, outpref: str):
-        with open(outpref + "_core_genome.csv", "wb") as f:
-            step = max(1, (64 << 20) // max(1, 2 * self.local_sites))
-            for r0 in range(0, self.N, step):
-                f.write(self.export_core_csv(r0, min(self.N, r0 + step)))
+        self.write_core_csv(outpref + "_core_genome.csv")
         acc = self.download_acc()
         with open(outpref + "_pangenome.csv", "w") as f:
             ones = ["1"] * self.cfg.core_genes                                   # :891

@@ -988,3 +988,28 @@ def test_graph_replay_equals_launch_by_launch(monkeypatch, kw):
             out[mode] = a + (cd, st) + b
     for x, y in zip(out["0"], out["1"]):
         assert (x == y).all()
+
+
+def test_write_core_csv_streams_the_same_text(tmp_path):
+    """pansim_write_core_csv (GPU text expansion, two pinned chunks in flight) writes exactly the rows
+    pansim_export_core_csv returns, over several chunks and with pending recombination materialised first."""
+    p = small_params(pop_size=600, core_size=40000, n_gen=2, HR_rate=0.5)
+    d = pb.derive(p)
+    rng = np.random.default_rng(91)
+    core, acc = random_state(rng, p.pop_size, p.core_size, d.pan_size)
+    with make(p) as sim:
+        sim.upload(core, acc)
+        sim.run_generations(0, 2)                      # recombination of generation 1 still pending
+        path = str(tmp_path / "core.csv")
+        n = sim.write_core_csv(path)
+        assert n == 2 * p.pop_size * p.core_size       # 48 MB: two 32 MB chunks
+        state = sim.download_core()
+        text = open(path, "rb").read()
+        assert text == sim.export_core_csv(0, p.pop_size)
+    lut = np.zeros(9, np.uint8)
+    lut[[1, 2, 4, 8]] = np.frombuffer(b"ACGT", np.uint8)
+    want = np.empty((p.pop_size, p.core_size, 2), np.uint8)
+    want[:, :, 0] = lut[state]
+    want[:, :, 1] = ord(",")
+    want[:, -1, 1] = ord("\n")
+    assert text == want.tobytes()

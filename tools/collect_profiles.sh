@@ -1,20 +1,26 @@
 #!/bin/bash
-# Run on the GPU box (gpurun): final bench line, ncu launch list and ncu --set full summaries -> gpurun_out/
+# Run on the GPU box (gpurun): tests, final bench lines, ncu launch list, ncu --set full summaries and the
+# targeted DRAM / L2 counter passes -> gpurun_out/ (copy what is to be kept into profiles/).
 set -u
 out=gpurun_out
-tag=${1:-r01}
-python bench.py > $out/${tag}_bench_final.json 2> $out/${tag}_bench_final.err
+tag=${1:-r02}
+python -m pytest tests -m gpu -q > $out/${tag}_gpu_tests.txt 2>&1; echo "pytest rc=$?" >> $out/${tag}_gpu_tests.txt; tail -3 $out/${tag}_gpu_tests.txt
+python bench.py > $out/${tag}_bench_final.json 2> $out/${tag}_bench_final.err; echo "bench rc=$?"
 python bench.py --impl reference --steps 2 --warmup 0 > $out/${tag}_bench_reference.json 2>> $out/${tag}_bench_final.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches_bench_steps5.csv \
-    python bench.py --steps 5 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
-python tools/launch_summary.py $out/${tag}_launches_bench_steps5.csv > $out/${tag}_launches_summary.txt
+B="python bench.py --steps 8 --warmup 3 --repeats 2 --no-cpu-baseline --no-cfg4"
+$B > $out/${tag}_plain_short.json 2> $out/${tag}_plain_short.err &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/${tag}_launches_bench_steps8.csv $B > /dev/null 2>&1
+python tools/launch_summary.py $out/${tag}_launches_bench_steps8.csv > $out/${tag}_launches_summary.txt
 : > $out/${tag}_ncu_summary.txt
-# launch 7 of core_mut_kernel (0-based) is the first with recombination events pending after a materialised state
-for spec in "core_mut_kernel 7" "hr_collect_kernel 1" "hr_apply_kernel 1" "acc_inter_mma_kernel 5" "fitness_lane_kernel 3" "fitness_kernel 1" \
-            "avg_distance_kernel 5" "select_parents_small_kernel 5" "acc_gather_flip_kernel 5" "acc_gain_threshold_kernel 5" \
-            "acc_hgt_apply_kernel 5" "pair_core_grouped_kernel 2"; do
+for spec in "core_mut_kernel 7" "pair_tile2_kernel 1" "core_planes_kernel 1" "pair_stats_kernel 1" "acc_inter_mma_kernel 5" "fitness_lane_kernel 3" \
+            "avg_distance_kernel 5" "select_parents_small_kernel 5" "acc_gather_flip_kernel 5" "acc_gain_threshold_kernel 5" "acc_hgt_apply_kernel 5" \
+            "hr_collect_kernel 1" "hr_apply_kernel 1"; do
     set -- $spec
-    timeout 300 ncu --set full --clock-control none --import-source on -k regex:$1 --launch-skip $2 -c 1 -f \
-        -o $out/${tag}_prof_$1 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $out/ncu_$1.log 2>&1
+    timeout 400 ncu --set full --clock-control none --import-source on -k regex:$1 --launch-skip $2 -c 1 -f \
+        -o $out/${tag}_prof_$1 $B > $out/ncu_$1.log 2>&1
     python profiles/ncu_summary.py $out/${tag}_prof_$1.ncu-rep >> $out/${tag}_ncu_summary.txt 2>&1
 done
+M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,dram__sectors_read.sum,dram__sectors_write.sum,lts__t_bytes.sum,lts__t_sectors.sum,lts__t_sectors_op_read.sum,lts__t_sectors_op_write.sum,lts__t_sector_hit_rate.pct,lts__t_sectors_srcunit_tex.sum,lts__t_sectors_srcunit_ltcfabric.sum,smsp__inst_executed.sum
+ncu --metrics $M --clock-control none -k regex:core_mut_kernel -s 4 -c 3 --csv --log-file $out/${tag}_l2_core_mut_rng.csv $B > /dev/null 2>&1
+ncu --metrics $M --clock-control none -k regex:'pair_tile2_kernel|core_planes_kernel|pair_acc_kernel' -s 3 -c 6 --csv --log-file $out/${tag}_l2_pair.csv $B > /dev/null 2>&1
+echo collected
