@@ -324,6 +324,7 @@ def main():
     mut_ms = core_ms - hr_ms                        # core_mut_kernel: gather + deferred recombination + SNPs
     launches = int(tm.launches)
     select_ms, acc_ms = tm.select_ms / K, tm.acc_step_ms / K
+    distinct_parents = int(len(np.unique(sim.parents())))      # rows the gather of the last generation actually read
     if os.environ.get("BENCH_DIAG") == "1":        # diagnostics: the generation batches only
         if rank == 0:
             print(json.dumps({"diag": os.environ.get("BENCH_DIAG_NAME", ""), "world": world, "backend": backend, "no_comm": no_comm,
@@ -369,7 +370,7 @@ def main():
         barrier()
         t0 = time.perf_counter()
         for g in range(Ke):
-            avg, parents = sim.select_parents(gen + g)         # average_distance + sample_indices: d2h N f64 + N u32
+            avg, parents = sim.select_parents(gen + g, reuse=True)   # average_distance + sample_indices: d2h N f64 + N u32
             sim.step_with_parents(gen + g, parents)            # h2d N u32
         barrier()
         e2e_runs.append(max_over_ranks(1e3 * (time.perf_counter() - t0) / Ke))
@@ -451,6 +452,11 @@ def main():
                      "frac": achieved / peak,
                      "traffic": (tr_core["dram_read_bytes"] + tr_core["dram_write_bytes"]) if tr_core else None,
                      "traffic_source": tr_core["source"] if tr_core else None,
+                     "traffic_note": "gather-by-parent reads every DISTINCT parent row from DRAM once, the children of the same parent "
+                                     "hit in L2: with cfg2's selection + competition only %d of %d individuals were parents in the last "
+                                     "generation, so the read side is far below the 300 MB of algorithmic reads; the neutral control "
+                                     "(profiles/r02_l2_core_mut_rng.csv, ~630 distinct parents) reads 528 MB" % (distinct_parents, N),
+                     "distinct_parents_last_generation": distinct_parents,
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": core_bytes, "launch_ms": mut_ms,
                      "core_genome_frac": core_bytes / (core_ms * 1e-3) / 1e9 / peak if core_ms > 0 else None,
@@ -465,6 +471,13 @@ def main():
                       "streaming_frac_of_hbm_peak": pair_bytes * P / (pair_ms * 1e-3) / 1e9 / peak,
                       "word_compares_per_pair": words_per_pair,
                       "popc_pipe_frac": (P / (pair_ms * 1e-3)) * words_per_pair / popc_peak,
+                      "popc_pipe_note": "SURVEY.md 8d model: one POPC per 32-bit word-compare at 16 POPC/clk/SM. The plane-form kernels "
+                                        "count 64 sites (4 words) with ONE POPC (carry-save), so this fraction can exceed 1; the model that "
+                                        "bounds them is the ALU pipe: per 64 sites 4 LOP3 (masks) + 2 LOP3 (carry-save) + 1 POPC (a quarter "
+                                        "of the LOP3 rate = 4 slots) + 1 IADD = 11 slots at 64 slots/clk/SM",
+                      "alu_slots_per_64_sites": 11,
+                      "alu_model_frac": (P / (pair_ms * 1e-3)) * ((info.local_sites + 63) // 64) * 11 / (64 * 148 * 1.965e9),
+                      "thread_instructions_per_word_compare": (tr_pair["warp_instructions"] * 32 / (P * words_per_pair)) if tr_pair else None,
                       "compulsory_dram_bytes": compulsory,
                       "dram_bytes_per_pass": (tr_pair["dram_read_bytes"] + tr_pair["dram_write_bytes"]) if tr_pair else None,
                       "dram_over_compulsory": ((tr_pair["dram_read_bytes"] + tr_pair["dram_write_bytes"]) / compulsory) if tr_pair else None,

@@ -1909,10 +1909,19 @@ static int ensure_pair_plan(pansim_ctx *c, const uint32_t *r1, const uint32_t *r
             const uint32_t cnt = kstart[kk + 1] - kstart[kk];
             if (cnt >= dense_min) n_dense_batches += (cnt + T2_BATCH - 1) / T2_BATCH;
         }
-        // column ranges: enough work items for ~8 per SM (the persistent CTAs balance themselves), ranges
-        // of at least 32 chunks so that the per-item prologue stays small
+        // Column ranges. (i) enough work items for ~8 per SM (the persistent CTAs balance themselves); (ii) the
+        // rows of one range, N x range bytes, are what all concurrently running items read: at most ~40 MB so
+        // that the range stays in L2 while its items run and DRAM sees every row once per pass (measured at
+        // cfg1: 4 ranges of 75 MB -> 580 MB of DRAM reads, 8 ranges of 37 MB -> 306 MB = 1.02 x the rows; finer
+        // ranges only add per-item prologues: 16 -> 1.56 ms, 32 -> 1.77 ms against 1.49 ms); (iii) ranges of at
+        // least 16 chunks.
         uint32_t col_split = 1;
         while (n_dense_batches && n_dense_batches * col_split < (size_t)c->sm_count * 8 && cols / (col_split * 2) >= 32) col_split *= 2;
+        const uint64_t slab_target = 40ull << 20;
+        const uint32_t by_l2 = (uint32_t)std::min<uint64_t>(cols, ((uint64_t)c->N * c->core_stride + slab_target - 1) / slab_target);
+        col_split = std::max(col_split, by_l2);
+        if (cols / col_split < 16) col_split = std::max(1u, cols / 16);
+        if (const char *e = getenv("PANSIM_TILE_COLSPLIT")) col_split = (uint32_t)std::max(1, std::min((int)cols, atoi(e)));
         struct Raw { uint32_t ba, bb, first, count; };
         std::vector<Raw> raw;
         for (size_t kk = 0; kk < n_keys; kk++) {

@@ -180,11 +180,21 @@ class Pansim:
         self._check(self._lib.pansim_sample_indices(self._h, gen, _ptr(avg), _ptr(out)))
         return out
 
-    def select_parents(self, gen: int):
-        """main.rs:435-443 in one call (one synchronisation): (avg_pairwise_dists, parents)."""
-        avg = np.empty(self.N, np.float64)
-        out = np.empty(self.N, np.uint32)
-        self._check(self._lib.pansim_select_parents(self._h, gen, _ptr(avg), _ptr(out)))
+    def select_parents(self, gen: int, reuse: bool = False):
+        """main.rs:435-443 in one call (one synchronisation): (avg_pairwise_dists, parents).
+        reuse=True returns the object's own two arrays (overwritten by the next call) instead of fresh ones:
+        a generation loop that only hands the parents on to step_with_parents saves the allocations."""
+        if reuse:
+            if not hasattr(self, "_sel_bufs"):
+                a, o = np.empty(self.N, np.float64), np.empty(self.N, np.uint32)
+                self._sel_bufs = (a, o, _ptr(a), _ptr(o))
+            avg, out, pa, po = self._sel_bufs
+        else:
+            avg, out = np.empty(self.N, np.float64), np.empty(self.N, np.uint32)
+            pa, po = _ptr(avg), _ptr(out)
+        rc = self._lib.pansim_select_parents(self._h, gen, pa, po)
+        if rc != OK:
+            self._check(rc)
         return avg, out
 
     def weights(self):
@@ -202,9 +212,12 @@ class Pansim:
 
     def step_with_parents(self, gen: int, parents):
         """main.rs:445-464 with host-supplied parents (generate mode)."""
-        p = np.ascontiguousarray(parents, np.uint32)
+        p = parents if (isinstance(parents, np.ndarray) and parents.dtype == np.uint32 and parents.flags.c_contiguous) \
+            else np.ascontiguousarray(parents, np.uint32)
         assert p.shape == (self.N,)
-        self._check(self._lib.pansim_step_with_parents(self._h, gen, _ptr(p)))
+        rc = self._lib.pansim_step_with_parents(self._h, gen, p.ctypes.data)
+        if rc != OK:
+            self._check(rc)
 
     def step(self, gen: int):
         """main.rs:435-464 entirely on the device."""
