@@ -236,6 +236,8 @@ int pansim_comm_info(pansim_ctx *ctx, int *n_ranks, int *rank);
  *     single-context ones and cite the same reference lines; each enqueues on every shard before it
  *     synchronises, so a single host thread keeps all devices busy. */
 typedef struct pansim_group pansim_group;
+/* column shard [begin, end) that shard i of n holds (whole 8192-site regions; needs no device) */
+int  pansim_shard_bounds(uint64_t core_size, int n_shards, int shard, uint64_t *site_begin, uint64_t *site_end);
 int  pansim_group_create(const pansim_config *cfg, int n_devices, const int *devices, pansim_group **out);
 void pansim_group_destroy(pansim_group *g);
 const char *pansim_group_last_error(const pansim_group *g);   /* g == NULL: last pansim_group_create failure */

@@ -26,7 +26,7 @@ EXPORTED = [
     "pansim_fetch_event_dump", "pansim_free_event_dump", "pansim_get_rates",
     "pansim_select_parents", "pansim_pair_stats", "pansim_run_generations_stats", "pansim_write_core_csv",
     "pansim_comm_unique_id", "pansim_comm_init_rank", "pansim_comm_info",
-    "pansim_group_create", "pansim_group_destroy", "pansim_group_last_error", "pansim_group_size", "pansim_group_ctx",
+    "pansim_shard_bounds", "pansim_group_create", "pansim_group_destroy", "pansim_group_last_error", "pansim_group_size", "pansim_group_ctx",
     "pansim_group_set_initial", "pansim_group_set_selection", "pansim_group_run_generations", "pansim_group_pair_counts",
     "pansim_group_run_generations_stats", "pansim_group_all_pairs", "pansim_group_all_pairs_timing", "pansim_group_gene_counts",
     "pansim_group_download_acc", "pansim_group_download_core", "pansim_group_export_core_csv",
@@ -171,6 +171,7 @@ def lib():
     sig("pansim_comm_unique_id", cint, vp)
     sig("pansim_comm_init_rank", cint, vp, cint, cint, vp)
     sig("pansim_comm_info", cint, vp, C.POINTER(cint), C.POINTER(cint))
+    sig("pansim_shard_bounds", cint, C.c_uint64, cint, cint, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64))
     sig("pansim_group_create", cint, C.POINTER(Config), cint, vp, C.POINTER(vp))
     sig("pansim_group_destroy", None, vp)
     sig("pansim_group_last_error", C.c_char_p, vp)

@@ -86,6 +86,18 @@ void group_shards(uint64_t core_size, int n, std::vector<std::pair<uint64_t, uin
 
 }  // namespace
 
+// the column shard [begin, end) of shard i of n: whole 8192-site regions, as even as the alignment allows
+// (no device needed; pansim_b200/sharding.py: column_shards computes the same split)
+int pansim_shard_bounds(uint64_t core_size, int n_shards, int shard, uint64_t *site_begin, uint64_t *site_end)
+{
+    if (n_shards < 1 || shard < 0 || shard >= n_shards || !site_begin || !site_end) return PANSIM_ERR_INVALID;
+    std::vector<std::pair<uint64_t, uint64_t>> s;
+    group_shards(core_size, n_shards, s);
+    *site_begin = s[shard].first;
+    *site_end = s[shard].second;
+    return 0;
+}
+
 int pansim_group_create(const pansim_config *cfg, int n_devices, const int *devices, pansim_group **out)
 {
     if (!cfg || !out || n_devices < 1) { g_create_error = "pansim_group_create: bad argument"; return PANSIM_ERR_INVALID; }

@@ -1208,6 +1208,7 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
 
         // launch shape of the core kernel
         c->core_smem = core_mut_smem_bytes(c->tab_mut.size, c->tab_hr.nsub ? c->tab_hr.size : 0u);
+        if (const char *e = getenv("PANSIM_CORE_SMEM_PAD_KB")) c->core_smem += (size_t)std::max(0, atoi(e)) * 1024;   // experiment: cap the CTAs per SM
         if (const char *e = getenv("PANSIM_HR_DEFER")) c->hr_defer = atoi(e) != 0;
         CU(c, cudaFuncSetAttribute(core_mut_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->core_smem));
         CU(c, cudaFuncSetAttribute(core_mut_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->core_smem));

@@ -68,3 +68,20 @@ def test_partial_counts_allreduce_world2(L):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_library_shards_equal_python_shards():
+    """pansim_group_* (one process, N GPUs) and the torchrun plumbing must cut the alignment at the same
+    sites: pansim_shard_bounds (C ABI, no device needed) against sharding.column_shards."""
+    import ctypes as C
+    from pansim_b200 import _ffi
+    lib = _ffi.lib()
+    for L in (1, 8191, 8192, 8193, 1_200_000, 5_000_000, 12_345_678):
+        for n in (1, 2, 3, 4, 7, 8):
+            want = column_shards(L, n)
+            for i in range(n):
+                b, e = C.c_uint64(), C.c_uint64()
+                assert lib.pansim_shard_bounds(L, n, i, C.byref(b), C.byref(e)) == 0
+                assert (b.value, e.value) == want[i], (L, n, i)
+    b, e = C.c_uint64(), C.c_uint64()
+    assert lib.pansim_shard_bounds(100, 2, 2, C.byref(b), C.byref(e)) == -1
