@@ -44,6 +44,20 @@ def one_case(rng, idx):
     os.environ.pop("PANSIM_HR_DEFER", None)
     for a, b in zip(states["0"], states["1"]):
         assert (a == b).all(), f"case {idx}: deferred != immediate {kw}"
+    # batches through the chain graphs (and the --print_dist batch) == kernel-by-kernel launches
+    rs1, rs2 = sample_pairs(rng, N, 500)
+    gstates = {}
+    for graph in ("1", "0"):
+        os.environ["PANSIM_GRAPH"] = graph
+        with pb.Pansim.from_params(p) as sim:
+            sim.upload(core, acc)
+            sim.set_selection(sel)
+            sim.run_generations(0, 9)
+            st = sim.run_generations_stats(9, 8, rs1, rs2)
+            gstates[graph] = (sim.download_core(), sim.download_acc(), sim.parents(), st)
+    os.environ.pop("PANSIM_GRAPH", None)
+    for a, b in zip(gstates["0"], gstates["1"]):
+        assert (a == b).all(), f"case {idx}: graph batch != plain launches {kw}"
     ocore, opan = ob.Population(core.copy(), True, cg), ob.Population(acc.copy(), False, cg)
     with pb.Pansim.from_params(p) as sim:
         sim.upload(core, acc)
@@ -57,11 +71,16 @@ def one_case(rng, idx):
             assert (ng == ong).all() and (lf == olf).all(), f"case {idx}: fitness {kw}"
             if np.isfinite(ow).all() and ow.sum() > 0:
                 np.testing.assert_allclose(w / w.sum(), ow / ow.sum(), rtol=1e-10, atol=1e-300)
-        r1, r2 = sample_pairs(rng, N, 300)
+        r1, r2 = sample_pairs(rng, N, int(rng.choice([7, 300, 3000, 20000])))      # few pairs: groups only; many: TMA tile batches
         cd, it, un = sim.pair_counts(r1, r2)
         assert (cd == ocore.pair_counts(r1, r2)).all(), f"case {idx}: pair core {kw}"
         oi, ou = opan.pair_counts(r1, r2)
         assert (it == oi).all() and (un == ou).all(), f"case {idx}: pair acc {kw}"
+        # on-device statistics == the oracle's left-to-right sums over the same distances
+        core_d, acc_d = sim.distances_from_counts(cd, it, un)
+        sc, ac = ob.standard_deviation(core_d)
+        sa, aa = ob.standard_deviation(acc_d)
+        assert sim.pair_stats(r1, r2) == (ac, sc, aa, sa), f"case {idx}: pair_stats {kw}"
         i0 = int(rng.integers(0, N))
         i1 = int(rng.integers(i0, N + 1))
         cd, it, un = sim.pair_counts_rows(i0, i1)
