@@ -83,8 +83,9 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, const PhiloxKeys &rk)
 // Philox4x32-7: the same bijection with seven rounds, the smallest round count of the family that is
 // Crush-resistant (Salmon et al., SC'11, table 2: Philox4x32-7 passes BigCrush; ten rounds is the
 // paper's safety margin). The core kernel is instruction-issue bound and makes 3.5 calls per lane per
-// 2 KiB region, so three rounds fewer are ~5 % of its instructions. Parent draws and the accessory
-// streams keep ten rounds. PANSIM_CORE_PHILOX_ROUNDS=10 at compile time restores the margin.
+// 2 KiB region, so three rounds fewer are ~5 % of its instructions. The accessory flip / HGT streams
+// (two calls per 32-gene word, beside the core kernel on the same SMs) use the same seven rounds; the
+// parent draws keep ten. PANSIM_CORE_PHILOX_ROUNDS=10 at compile time restores the margin everywhere.
 #ifndef PANSIM_CORE_PHILOX_ROUNDS
 #define PANSIM_CORE_PHILOX_ROUNDS 7
 #endif
