@@ -176,9 +176,9 @@ def test_fitness_and_average_distance_bit_exact():
 @pytest.mark.parametrize("N,G,dens", [(200, 4000, 0.25), (131, 1030, 0.5), (65, 31, 0.3), (300, 33, 0.9), (2, 5, 0.5),
                                       (1100, 70, 0.5), (1024, 2100, 0.75)])
 def test_competition_and_fitness_kernels_over_shapes(N, G, dens):
-    """The intersection counts run as an integer MMA over 64x64 pair tiles and 32-word chunks
-    (select.cuh K2a), the distances and the fitness sum as per-row sequential f64 chains fed from
-    shared memory in rounds of 256 / 1024 values: shapes with several tiles, ragged last tiles,
+    """The intersection counts run on the tensor cores over 128 x 128 pair tiles (tcgen05, select.cuh
+    K2a), the distances and the fitness sum as per-row sequential f64 chains fed from shared memory
+    in rounds of 256 / 1024 values: shapes with several tiles, ragged last tiles,
     a ragged last word and fewer rows than one tile must all stay bit-exact. Parent selection has a
     register/shared-memory kernel up to 1024 individuals and a global-memory one above."""
     rng = np.random.default_rng(N + G)
@@ -201,6 +201,28 @@ def test_competition_and_fitness_kernels_over_shapes(N, G, dens):
     ow, ong, olf = opan.selection_weights(pb.derive(p).avg_gene_num, oavg, sel, False, p.genome_size_penalty, 1.0)
     assert (ng == ong).all() and (lf == olf).all()
     np.testing.assert_allclose(w / w.sum(), ow / ow.sum(), rtol=1e-11)
+
+
+@pytest.mark.parametrize("umma", ["0", "1", "2", "3"])
+@pytest.mark.parametrize("rcp", ["0", "1"])
+def test_competition_kernel_variants_are_bit_exact(monkeypatch, umma, rcp):
+    """Every implementation of the competition term behind PANSIM_INTER_UMMA / PANSIM_AVG_RCP gives the oracle's
+    bits: tcgen05.mma with operands expanded in the CTA (2: 128-byte, 3: 64-byte swizzled rows) or fed by TMA from a
+    byte-expanded matrix (1), warp-level mma.sync (0); IEEE division or the reciprocal-table quotient
+    (tools/check_recip_division.c). Shapes: several 128-row tiles with a ragged last one, gene counts off the
+    64 / 128-gene stage size, fewer rows than a tile, no core genes (denominator 0 is not reachable here)."""
+    monkeypatch.setenv("PANSIM_INTER_UMMA", umma)
+    monkeypatch.setenv("PANSIM_AVG_RCP", rcp)
+    for N, pan, cg, dens in [(300, 900, 200, 0.5), (130, 37, 0, 0.9), (1025, 4229, 100, 0.02), (257, 300, 0, 1.0), (5, 40, 37, 0.3)]:
+        rng = np.random.default_rng(N + pan)
+        G = pan - cg
+        core, acc = random_state(rng, N, 20, G, dens)
+        p = pb.Params(pop_size=N, core_size=20, pan_genes=pan, core_genes=cg, competition_strength=0.5)
+        oavg = ob.Population(acc, False, cg).average_distance()
+        with make(p) as sim:
+            sim.upload(core, acc)
+            avg = sim.average_distance()
+        assert np.array_equal(avg, oavg), (N, pan, cg, dens, int((avg != oavg).sum()))
 
 
 def test_average_distance_identical_population_is_min_positive():
