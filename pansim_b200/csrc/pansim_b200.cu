@@ -186,10 +186,11 @@ struct pansim_ctx {
     uint32_t acc_kpad = 0;            // genes per row of d_acc_bytes (a multiple of UM_KBYTES)
     CUtensorMap acc_bytes_tmap;
     bool acc_bytes_tmap_ok = false;
-    // PANSIM_AVG_RCP: 1 = quotients of the mean-distance kernel from a reciprocal table (bit-identical to the IEEE division,
-    // 12 % fewer instructions), 0 = IEEE division. Measured in the generation pipeline (cfg2): the table variant's second
-    // dependent load per round costs more latency than its instructions save (157.8 vs 155.0 us per generation), so it is opt-in.
-    bool avg_rcp = false;
+    // PANSIM_AVG_RCP: 0 = IEEE division in the mean-distance kernel; 1 = quotients from a reciprocal table (bit-identical,
+    // 12 % fewer instructions, but a second dependent load per round: 157.8 against 155.0 us per generation at cfg2);
+    // 2 = the table kernel software-pipelined over the rounds (avg_distance_pipe_kernel: 3.6 -> 2.2 M instructions per
+    // launch, 154.4 against 154.7 us per generation)
+    int avg_rcp = 2;
     double *d_rcp = nullptr;          // RN(1 / b), b = 0 .. G + core_genes
     bool fitness_blocked = false; // large shapes: blocked (fixed-association) fitness sum instead of the sequential chain
 
@@ -613,7 +614,10 @@ int launch_competition(pansim_ctx *c)
     LAUNCH_CHECK(c);
     fs.reset();
     FineSpan fs2(c, TG_D_AVG);
-    if (c->avg_rcp && c->d_rcp)
+    if (c->avg_rcp == 2 && c->d_rcp)
+        avg_distance_pipe_kernel<<<div_up64(c->N, AVG_WARPS), AVG_WARPS * 32, 0, c->stream>>>(c->d_inter, c->d_inter_diag, c->N,
+                                                                             c->cfg.core_genes, c->d_rcp, c->d_avgdist);
+    else if (c->avg_rcp && c->d_rcp)
         avg_distance_kernel<true><<<div_up64(c->N, AVG_WARPS), AVG_WARPS * 32, 0, c->stream>>>(c->d_inter, c->d_inter_diag, c->N,
                                                                               c->cfg.core_genes, c->d_rcp, c->d_avgdist);
     else
@@ -1232,7 +1236,7 @@ int pansim_create(const pansim_config *cfg, pansim_ctx **out)
         if (const char *e = getenv("PANSIM_FITNESS_BLOCKED")) c->fitness_blocked = atoi(e) != 0;
         if (const char *e = getenv("PANSIM_INTER_POPC")) c->inter_popc = atoi(e) != 0;
         if (const char *e = getenv("PANSIM_INTER_UMMA")) c->inter_umma = atoi(e);
-        if (const char *e = getenv("PANSIM_AVG_RCP")) c->avg_rcp = atoi(e) != 0;
+        if (const char *e = getenv("PANSIM_AVG_RCP")) c->avg_rcp = atoi(e);
         if (const char *e = getenv("PANSIM_TILES2")) c->use_tiles2 = atoi(e) != 0;
         if (const char *e = getenv("PANSIM_GRAPH")) c->use_graph = atoi(e) != 0;
         if (const char *e = getenv("PANSIM_GRAPH_SPANS")) c->graph_spans = atoi(e) != 0;

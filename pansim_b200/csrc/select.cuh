@@ -855,6 +855,95 @@ __global__ void __launch_bounds__(AVG_WARPS * 32) avg_distance_kernel(const uint
     }
 }
 
+// The same kernel (warp per individual, reciprocal-table quotients) software-pipelined over the rounds, for the
+// generation pipeline where the warp shares its scheduler with eight core-kernel warps and every exposed global-load
+// latency is paid in full: while the chain of round r runs over one half of a double-buffered ring,
+//   * the reciprocals of round r + 1 are fetched (their addresses come from intersection counts loaded a round earlier),
+//   * its quotients are evaluated into the other half of the ring between the two halves of the chain,
+//   * the intersection counts and gene counts of round r + 2 are requested.
+// The loads are volatile asm so that they are issued where they are written; two values per shared-memory load in the
+// chain. Same additions in the same order: same bits.
+__device__ __forceinline__ uint32_t ldg_u32_v(const void *p)
+{
+    uint32_t v;
+    asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ldg_f64_v(const void *p)
+{
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+__global__ void __launch_bounds__(AVG_WARPS * 32, 4) avg_distance_pipe_kernel(const uint32_t *inter, const int32_t *num_genes,
+                                                                             uint32_t n_rows, uint32_t core_genes,
+                                                                             const double *__restrict__ rcp, double *avgdist)
+{
+    constexpr int PER = AVG_RING / 32;               // distances per lane per round
+    __shared__ __align__(16) double ring[AVG_WARPS][2][AVG_RING];
+    pdl_launch_dependents();       // the parent-selection CTA may take its SM slot now (it waits for this grid)
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t i = blockIdx.x * AVG_WARPS + warp;
+    if (i >= n_rows) return;
+    const uint32_t ki = (uint32_t)num_genes[i] + core_genes;
+    const uint32_t *irow = inter + (uint64_t)i * n_rows;
+    uint32_t in[PER], kj[PER];
+    double rr[PER];
+    auto load_counts = [&](uint32_t j0) {            // past the end: clamped (the values become +0.0 below)
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            const uint32_t j = min(j0 + q * 32 + lane, n_rows - 1u);
+            in[q] = ldg_u32_v(irow + j);
+            kj[q] = ldg_u32_v(num_genes + j);
+        }
+    };
+    auto load_rcp = [&]() {
+#pragma unroll
+        for (int q = 0; q < PER; q++) rr[q] = ldg_f64_v(rcp + (ki + kj[q] - in[q]));
+    };
+    auto quotients = [&](uint32_t j0, double *buf) {
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            const uint32_t j = j0 + q * 32 + lane;
+            const double da = (double)(in[q] + core_genes), db = (double)(ki + kj[q] - in[q]);
+            const double q0 = da * rr[q];
+            const double d = 1.0 - fma(fma(-q0, db, da), rr[q], q0);                  // population.rs:144-145
+            buf[q * 32 + lane] = (j < n_rows && j != i) ? d : 0.0;                    // +0.0 never changes the (non-negative) sum
+        }
+    };
+    double sum = 0.0;
+    auto chain = [&](uint32_t base_s) {              // AVG_RING / 2 values, in order
+#pragma unroll
+        for (int c = 0; c < AVG_RING / 2; c += 2) {
+            double x0, x1;
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x0), "=d"(x1) : "r"(base_s + c * 8u));
+            sum += x0;
+            sum += x1;
+        }
+    };
+    load_counts(0u);
+    load_rcp();
+    quotients(0u, ring[warp][0]);
+    load_counts(AVG_RING);
+    __syncwarp();
+    uint32_t b = 0;
+    for (uint32_t j0 = 0; j0 < n_rows; j0 += AVG_RING, b ^= 1u) {
+        const uint32_t cur = smem_u32(ring[warp][b]);
+        load_rcp();                                              // round r + 1
+        chain(cur);
+        quotients(j0 + AVG_RING, ring[warp][b ^ 1u]);
+        load_counts(j0 + 2 * AVG_RING);                          // round r + 2
+        chain(cur + (AVG_RING / 2) * 8u);
+        __syncwarp();
+    }
+    if (lane == 0) {
+        double fd = sum / (double)(n_rows - 1u);
+        if (fd == 0.0) fd = DBL_MIN;                                  // :774-776
+        avgdist[i] = fd;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // K3: weights (three softmaxes multiplied, population.rs:325-393), the all-zero
 // rule (:403,435-437), WeightedIndex<f64> (cumulative + binary search, :440)

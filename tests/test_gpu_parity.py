@@ -204,12 +204,12 @@ def test_competition_and_fitness_kernels_over_shapes(N, G, dens):
 
 
 @pytest.mark.parametrize("umma", ["0", "1", "2", "3"])
-@pytest.mark.parametrize("rcp", ["0", "1"])
+@pytest.mark.parametrize("rcp", ["0", "1", "2"])
 def test_competition_kernel_variants_are_bit_exact(monkeypatch, umma, rcp):
     """Every implementation of the competition term behind PANSIM_INTER_UMMA / PANSIM_AVG_RCP gives the oracle's
     bits: tcgen05.mma with operands expanded in the CTA (2: 128-byte, 3: 64-byte swizzled rows) or fed by TMA from a
-    byte-expanded matrix (1), warp-level mma.sync (0); IEEE division or the reciprocal-table quotient
-    (tools/check_recip_division.c). Shapes: several 128-row tiles with a ragged last one, gene counts off the
+    byte-expanded matrix (1), warp-level mma.sync (0); IEEE division (0) or the reciprocal-table quotient
+    (tools/check_recip_division.c; 1, and 2 = software-pipelined over the rounds). Shapes: several 128-row tiles with a ragged last one, gene counts off the
     64 / 128-gene stage size, fewer rows than a tile, no core genes (denominator 0 is not reachable here)."""
     monkeypatch.setenv("PANSIM_INTER_UMMA", umma)
     monkeypatch.setenv("PANSIM_AVG_RCP", rcp)

@@ -38,7 +38,7 @@ def main():
         opan = ob.Population(acc.copy(), False, cg)
         oavg = opan.average_distance()
         ow, ong, olf = opan.selection_weights(d.avg_gene_num, oavg, sel, False, p.genome_size_penalty, p.competition_strength)
-        for umma, lane, fit in itertools.product(UMMA, "01", "0"):
+        for umma, lane, fit in itertools.product(UMMA, "012", "0"):
             os.environ["PANSIM_INTER_UMMA"] = umma
             os.environ["PANSIM_AVG_RCP"] = lane
             os.environ["PANSIM_FITNESS_MODE"] = fit
