@@ -1,4 +1,5 @@
-// dependent-chain latency of DADD / DFMA / IADD on one warp (cycles per operation)
+// dependent-chain latency of DADD / DFMA / IMAD / FADD on one warp (cycles per operation)
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/experiments/fp64_latency tools/experiments/fp64_latency.cu
 #include <cstdio>
 #include <cstdint>
 #include <cuda_runtime.h>
