@@ -160,9 +160,9 @@ struct pansim_ctx {
     double *d_lw = nullptr, *d_logfit = nullptr, *d_avgdist = nullptr;
     uint32_t *d_lethal = nullptr;         // bit g: ln(1 + s_g) = -inf (s_g = -1)
     // PANSIM_FITNESS_MODE: 1 = two warps per row (28 us, but ~500 CTAs resident beside the core kernel),
-    // 2 = one lane per row (44 us, 8 CTAs), 0 = by entry point: two warps per row where the host waits on
-    // the chain (lowest latency), one lane per row in the device-resident batch (the core kernel keeps its
-    // SM slots: +7 % generations/s). All three give the same bits.
+    // 2 = one lane per row (30 us, 8 CTAs), 0 = by entry point: two warps per row where the host waits on
+    // the chain, one lane per row in the device-resident batch (the core kernel keeps its SM slots:
+    // 154 against 175-189 us per generation at cfg2). All three give the same bits.
     int fitness_mode = 0;
     int32_t *d_num_genes = nullptr;
     int32_t *d_inter_diag = nullptr;      // gene counts as the diagonal of the intersection matrix (select.cuh K2a)
