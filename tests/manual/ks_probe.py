@@ -1,3 +1,4 @@
+"""KS / t-test probe of whole runs, GPU against the oracle, over 120 seeds (run by hand under gpurun from the repo root)."""
 import sys, os, numpy as np
 sys.path.insert(0, os.getcwd())
 import pansim_b200 as pb

@@ -66,7 +66,7 @@ KS_FAMILY = len(SCALARS) * len(CONFIGS)
 def test_ks_gpu_vs_oracle_over_20_seeds(name):
     """20 GPU seeds vs 20 oracle seeds per summary scalar, two-sample KS, family-wise alpha 0.01
     (Bonferroni over the 18 comparisons). Both sides are deterministic given their seeds.
-    tools/ks_probe.py runs the same comparison on 120 seeds."""
+    tests/manual/ks_probe.py runs the same comparison on 120 seeds."""
     kw = CONFIGS[name]
     report = _ks(*_summaries(kw, range(20), range(1000, 1020)))
     bad = {k: v for k, v in report.items() if not v > KS_ALPHA / KS_FAMILY}

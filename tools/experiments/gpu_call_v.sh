@@ -4,9 +4,9 @@ set -u
 out=gpurun_out
 tag=r02v
 mkdir -p $out
-timeout -k 10 300 python tools/experiments/check_chain_variants.py 0 > $out/${tag}_check0.txt 2>&1
+timeout -k 10 300 python tests/manual/check_chain_variants.py 0 > $out/${tag}_check0.txt 2>&1
 echo "check0 rc=$?"; tail -3 $out/${tag}_check0.txt; grep -c "^ok" $out/${tag}_check0.txt; grep "MISMATCH" $out/${tag}_check0.txt | head -20
-timeout -k 10 300 python tools/experiments/check_chain_variants.py 1 > $out/${tag}_check1.txt 2>&1
+timeout -k 10 300 python tests/manual/check_chain_variants.py 1 > $out/${tag}_check1.txt 2>&1
 rc1=$?
 echo "check1 rc=$rc1"; tail -3 $out/${tag}_check1.txt; grep -c "^ok" $out/${tag}_check1.txt; grep "MISMATCH" $out/${tag}_check1.txt | head -20
 run() { name=$1; shift

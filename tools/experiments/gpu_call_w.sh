@@ -5,7 +5,7 @@ out=gpurun_out
 tag=r02w
 mkdir -p $out
 ./tools/experiments/fp64_latency > $out/${tag}_fp64_latency.txt 2>&1; cat $out/${tag}_fp64_latency.txt
-timeout -k 10 400 python tools/experiments/check_chain_variants.py 012 > $out/${tag}_check.txt 2>&1
+timeout -k 10 400 python tests/manual/check_chain_variants.py 012 > $out/${tag}_check.txt 2>&1
 echo "check rc=$?"; tail -2 $out/${tag}_check.txt; grep -c "^ok" $out/${tag}_check.txt; grep "MISMATCH\|Error\|error" $out/${tag}_check.txt | head -20
 run() { name=$1; shift
 env BENCH_DIAG=1 BENCH_DIAG_NAME=$name "$@" timeout 300 python bench.py --no-cpu-baseline --no-cfg4 --repeats 5 > $out/${tag}_diag_$name.json 2> $out/${tag}_diag_$name.err || tail -2 $out/${tag}_diag_$name.err

@@ -4,7 +4,7 @@ set -u
 out=gpurun_out
 tag=r02x
 mkdir -p $out
-timeout -k 10 400 python tools/experiments/check_chain_variants.py 012 > $out/${tag}_check.txt 2>&1
+timeout -k 10 400 python tests/manual/check_chain_variants.py 012 > $out/${tag}_check.txt 2>&1
 echo "check rc=$?"; tail -2 $out/${tag}_check.txt; grep -c "^ok" $out/${tag}_check.txt; grep "MISMATCH\|Error\|error" $out/${tag}_check.txt | head -20
 timeout -k 10 900 python -m pytest tests -x -q -m gpu > $out/${tag}_gpu_tests.txt 2>&1; echo "pytest rc=$?"; tail -5 $out/${tag}_gpu_tests.txt
 run() { name=$1; shift
